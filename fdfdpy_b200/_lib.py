@@ -1,0 +1,119 @@
+"""ctypes binding of libfdfd_b200.so (the C ABI in include/fdfd_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device answers, every
+compute entry point raises.  ``load()`` only dlopens the library (works without a GPU, so the
+symbol table can be checked on a CPU box).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfdfd_b200.so")
+
+c128 = np.complex128
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+
+class LevelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("nb", C.c_int), ("kmax", C.c_int), ("mmax", C.c_int), ("ncls", C.c_int),
+                ("child_mmax", C.c_int),
+                ("cls", _ip), ("k_cls", _ip), ("ch1", _ip), ("ch2", _ip), ("c1map", _ip), ("c2map", _ip),
+                ("x0", _ip), ("y0", _ip), ("slot_lx", _ip), ("slot_ly", _ip), ("slot_right", _ip),
+                ("slot_up", _ip)]
+
+
+# name -> (restype, argtypes); mirrors include/fdfd_b200.h one to one
+SIGNATURES = {
+    "fdfd_version": (C.c_int, []),
+    "fdfd_last_error": (C.c_char_p, []),
+    "fdfd_device_count": (C.c_int, [_ip]),
+    "fdfd_set_device": (C.c_int, [C.c_int]),
+    "fdfd_mem_info": (C.c_int, [_dp, _dp]),
+    "fdfd_malloc": (C.c_int, [C.POINTER(_vp), C.c_double]),
+    "fdfd_free": (C.c_int, [_vp]),
+    "fdfd_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_double]),
+    "fdfd_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_double]),
+    "fdfd_op_sync": (C.c_int, [_vp]),
+    "fdfd_op_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                 C.c_int, C.c_double]),
+    "fdfd_op_destroy": (None, [_vp]),
+    "fdfd_op_assemble_host": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "fdfd_op_assemble_dev": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "fdfd_op_get_sfactors_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "fdfd_op_get_planes_host": (C.c_int, [_vp, _vp]),
+    "fdfd_op_apply_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
+    "fdfd_op_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
+    "fdfd_op_derive_fields_host": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fdfd_op_derive_fields_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fdfd_direct_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    "fdfd_direct_add_level": (C.c_int, [_vp, C.POINTER(LevelDesc)]),
+    "fdfd_direct_destroy": (None, [_vp]),
+    "fdfd_direct_factor": (C.c_int, [_vp, _vp]),
+    "fdfd_direct_stats": (C.c_int, [_vp, _dp, _dp]),
+    "fdfd_direct_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
+    "fdfd_direct_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
+    "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                         _ip, _dp, _ip]),
+    "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                        _ip, _dp, _ip]),
+    "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fdfd_mode_solve_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                       C.c_int, C.c_int, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FdfdError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FdfdError("libfdfd_b200.so is not built (run `python -m fdfdpy_b200.build` or "
+                        "__graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise FdfdError(load().fdfd_last_error().decode("utf-8", "replace"))
+
+
+def require_gpu():
+    lib = load()
+    n = C.c_int(0)
+    if lib.fdfd_device_count(C.byref(n)) != 0 or n.value < 1:
+        raise FdfdError("no CUDA device available: fdfdpy_b200 has no CPU path ({})".format(
+            lib.fdfd_last_error().decode("utf-8", "replace")))
+    return n.value
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_vp)
+
+
+def as_c128(a):
+    return np.ascontiguousarray(a, dtype=c128)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)

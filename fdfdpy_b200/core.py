@@ -1,0 +1,202 @@
+"""Python handles over the C ABI: the device-resident Maxwell operator and the direct solver.
+
+These are the objects the reference-shaped API in simulation.py / linalg.py is built from.
+Nothing here computes on the CPU: arrays are marshalled to libfdfd_b200.so and back.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_c128, as_i32, check, ptr
+from .ndplan import build_plan
+
+POL = {"Ez": 0, "Hz": 1}
+_plan_cache = {}
+
+
+def get_plan(nx, ny):
+    key = (int(nx), int(ny))
+    if key not in _plan_cache:
+        _plan_cache[key] = build_plan(*key)
+    return _plan_cache[key]
+
+
+class MaxwellOperator:
+    """A = Dxf mu^-1 Dxb + Dyf mu^-1 Dyb + w^2 eps on the device (reference: linalg.py:39 construct_A).
+
+    Behaves like the scipy matrix the reference keeps in ``Simulation.A`` as far as the hot path
+    needs: ``shape``, ``dot``; ``to_scipy()`` exports it as CSR for inspection.
+    """
+
+    def __init__(self, omega, eps_r, dl, NPML, pol, L0, averaging=True, eps_nl=None):
+        _lib.require_gpu()
+        self.lib = _lib.load()
+        if pol not in POL:
+            raise ValueError("something went wrong and pol is not one of Ez, Hz, instead was given {}".format(pol))
+        eps_r = np.asarray(eps_r)
+        if eps_r.ndim != 2:
+            raise ValueError("eps_r must be a 2-D array")
+        self.nx, self.ny = eps_r.shape
+        self.shape = (self.nx * self.ny, self.nx * self.ny)
+        self.pol = pol
+        self.omega, self.dl, self.L0 = float(omega), float(dl), float(L0)
+        self.NPML = [int(NPML[0]), int(NPML[1])]
+        self.h = C.c_void_p()
+        check(self.lib.fdfd_op_create(C.byref(self.h), self.nx, self.ny, self.omega, self.dl, self.NPML[0],
+                                      self.NPML[1], POL[pol], self.L0))
+        self._direct = None
+        self.assemble(eps_r, eps_nl, averaging)
+
+    def assemble(self, eps_r, eps_nl=None, averaging=True):
+        er = as_c128(eps_r)
+        if er.shape != (self.nx, self.ny):
+            raise ValueError("eps_r shape changed; build a new operator")
+        en = None if eps_nl is None else as_c128(np.broadcast_to(eps_nl, er.shape))
+        check(self.lib.fdfd_op_assemble_host(self.h, ptr(er), ptr(en), int(bool(averaging))))
+        self.has_nl = en is not None
+        if self._direct is not None:
+            self._direct.factored = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                self.lib.fdfd_op_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- matrix-like surface
+    def dot(self, x, fused=False):
+        x = as_c128(x)
+        nvec = x.size // (self.nx * self.ny)
+        y = np.empty_like(x)
+        check(self.lib.fdfd_op_apply_host(self.h, ptr(x), ptr(y), nvec, int(fused)))
+        return y
+
+    def planes(self):
+        out = np.empty((5, self.nx, self.ny), dtype=np.complex128)
+        check(self.lib.fdfd_op_get_planes_host(self.h, ptr(out)))
+        return out
+
+    def sfactors(self):
+        arrs = [np.empty(n, dtype=np.complex128) for n in (self.nx, self.nx, self.ny, self.ny)]
+        check(self.lib.fdfd_op_get_sfactors_host(self.h, *[ptr(a) for a in arrs]))
+        return tuple(arrs)
+
+    def to_scipy(self, matrix_format="csr"):
+        """Export A as a scipy sparse matrix (format conversion of the device planes, no solve)."""
+        import scipy.sparse as sp
+        c0, cxm, cxp, cym, cyp = self.planes()
+        nx, ny = self.nx, self.ny
+        ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        row = (ii * ny + jj).ravel()
+        cols = [row, (((ii - 1) % nx) * ny + jj).ravel(), (((ii + 1) % nx) * ny + jj).ravel(),
+                (ii * ny + (jj - 1) % ny).ravel(), (ii * ny + (jj + 1) % ny).ravel()]
+        vals = np.concatenate([p.ravel() for p in (c0, cxm, cxp, cym, cyp)])
+        A = sp.coo_matrix((vals, (np.tile(row, 5), np.concatenate(cols))), shape=self.shape)
+        return A.asformat(matrix_format)
+
+    def derive_fields(self, X):
+        X = as_c128(X)
+        f1, f2 = np.empty_like(X), np.empty_like(X)
+        check(self.lib.fdfd_op_derive_fields_host(self.h, ptr(X), ptr(f1), ptr(f2)))
+        return f1.reshape(self.nx, self.ny), f2.reshape(self.nx, self.ny)
+
+    # ---- solvers
+    def direct(self, tile=32):
+        if self._direct is None:
+            self._direct = DirectSolver(self, tile=tile)
+        return self._direct
+
+    def solve(self, b, max_refine=3, tol=1e-12):
+        """Direct solve with the cached factorisation (factorises on first use)."""
+        return self.direct().solve(b, max_refine=max_refine, tol=tol)
+
+    def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10,
+               precondition=False):
+        b = as_c128(b)
+        x = np.zeros_like(b) if x0 is None else as_c128(x0).copy()
+        it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+        pre = None
+        if precondition:
+            d = self.direct()
+            if not d.factored:
+                d.factor()
+            pre = d.h
+        check(self.lib.fdfd_krylov_solve_host(self.h, pre, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
+                                              float(tol), int(maxiter), int(fused), int(check_every),
+                                              C.byref(it), C.byref(rr), C.byref(conv)))
+        return x.reshape(b.shape), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
+
+
+class DirectSolver:
+    """Structured direct solver handle (reference: linalg.py:123 solver_direct / pardisoSolver)."""
+
+    def __init__(self, op, tile=32):
+        self.op = op
+        self.lib = op.lib
+        self.h = C.c_void_p()
+        check(self.lib.fdfd_direct_create(C.byref(self.h), op.nx, op.ny, int(tile)))
+        self.levels = get_plan(op.nx, op.ny)
+        keep = []
+        for lv in self.levels:
+            d = _lib.LevelDesc()
+            d.kind = 0 if lv.kind == "leaf" else 1
+            d.nb, d.kmax, d.mmax, d.ncls = lv.nb, lv.kmax, lv.mmax, lv.ncls
+            d.child_mmax = getattr(lv, "child_mmax", 0)
+            names = ["cls", "k_cls"] + (["x0", "y0", "slot_lx", "slot_ly", "slot_right", "slot_up"]
+                                        if lv.kind == "leaf" else ["ch1", "ch2", "c1map", "c2map"])
+            for nme in names:
+                arr = as_i32(getattr(lv, nme))
+                keep.append(arr)
+                setattr(d, nme, arr.ctypes.data_as(C.POINTER(C.c_int)))
+            check(self.lib.fdfd_direct_add_level(self.h, C.byref(d)))
+        del keep
+        self.factored = False
+        self.last_relres = None
+        self.last_refine_steps = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                self.lib.fdfd_direct_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    def factor(self):
+        check(self.lib.fdfd_direct_factor(self.h, self.op.h))
+        self.factored = True
+
+    def stats(self):
+        fb, ff = C.c_double(0), C.c_double(0)
+        check(self.lib.fdfd_direct_stats(self.h, C.byref(fb), C.byref(ff)))
+        return dict(factor_bytes=fb.value, factor_flops=ff.value)
+
+    def solve(self, b, max_refine=3, tol=1e-12):
+        if not self.factored:
+            self.factor()
+        b = as_c128(b)
+        n = self.op.nx * self.op.ny
+        nrhs = b.size // n
+        x = np.empty_like(b)
+        rr, steps = C.c_double(0), C.c_int(0)
+        check(self.lib.fdfd_direct_solve_host(self.h, self.op.h, ptr(b), ptr(x), nrhs, int(max_refine), float(tol),
+                                              C.byref(rr), C.byref(steps)))
+        self.last_relres, self.last_refine_steps = rr.value, steps.value
+        return x
+
+
+def mode_solve(eps_line, omega, dl, pol, L0, neff, order=1, averaged=False):
+    """``order`` eigenpairs of the 1-D waveguide operator nearest (w sqrt(mu0' eps0') neff)^2,
+    closest first (reference: source/mode.py:91-92 -> solver_eigs)."""
+    _lib.require_gpu()
+    lib = _lib.load()
+    eps_line = np.ascontiguousarray(np.real(eps_line), dtype=np.float64).reshape(-1)
+    n = eps_line.size
+    vals = np.empty(order, dtype=np.float64)
+    vecs = np.empty((order, n), dtype=np.float64)
+    check(lib.fdfd_mode_solve_host(ptr(eps_line), n, float(omega), float(dl), POL[pol], float(L0), float(neff),
+                                   int(order), int(bool(averaged)), ptr(vals), ptr(vecs)))
+    return vals, vecs

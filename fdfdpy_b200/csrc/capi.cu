@@ -1,0 +1,199 @@
+// extern "C" surface of libfdfd_b200.so; declarations and reference citations in include/fdfd_b200.h
+#include <vector>
+#include "krylov.cuh"
+#include "mode.cuh"
+#include "zgemm.cuh"
+#include "../../include/fdfd_b200.h"
+
+namespace {
+struct DevBuf {
+    cplx* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t count) {
+        FDFD_CHECK(cudaMalloc(&p, sizeof(cplx) * count));
+        return 0;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int fdfd_version(void) { return 100; }
+const char* fdfd_last_error(void) { return g_fdfd_err; }
+
+int fdfd_device_count(int* count) { FDFD_CHECK(cudaGetDeviceCount(count)); return 0; }
+int fdfd_set_device(int device) { FDFD_CHECK(cudaSetDevice(device)); return 0; }
+int fdfd_mem_info(double* free_bytes, double* total_bytes) {
+    size_t f, t;
+    FDFD_CHECK(cudaMemGetInfo(&f, &t));
+    *free_bytes = (double)f; *total_bytes = (double)t;
+    return 0;
+}
+int fdfd_malloc(void** dev_ptr, double bytes) { FDFD_CHECK(cudaMalloc(dev_ptr, (size_t)bytes)); return 0; }
+int fdfd_free(void* dev_ptr) { FDFD_CHECK(cudaFree(dev_ptr)); return 0; }
+int fdfd_memcpy_h2d(void* dev, const void* host, double bytes) {
+    FDFD_CHECK(cudaMemcpy(dev, host, (size_t)bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int fdfd_memcpy_d2h(void* host, const void* dev, double bytes) {
+    FDFD_CHECK(cudaMemcpy(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int fdfd_op_sync(fdfd_op* op) { FDFD_CHECK(cudaStreamSynchronize(op->stream)); return 0; }
+
+int fdfd_op_create(fdfd_op** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol,
+                   double L0) {
+    if (!(omega > 0)) FDFD_FAIL("omega must be positive");
+    if (!(dl > 0)) FDFD_FAIL("dl must be positive");
+    if (!(L0 > 0)) FDFD_FAIL("L0 must be positive");
+    if (npml_x < 0 || npml_y < 0) FDFD_FAIL("NPML entries must be >= 0");
+    return op_create(out, nx, ny, omega, dl, npml_x, npml_y, pol, L0);
+}
+void fdfd_op_destroy(fdfd_op* op) { op_destroy(op); }
+
+int fdfd_op_assemble_dev(fdfd_op* op, const void* d_eps_r, const void* d_eps_nl, int averaging) {
+    return op_assemble_dev(op, (const cplx*)d_eps_r, (const cplx*)d_eps_nl, averaging);
+}
+int fdfd_op_assemble_host(fdfd_op* op, const double* eps_r, const double* eps_nl, int averaging) {
+    size_t n = op->n();
+    FDFD_CHECK(cudaMemcpyAsync(op->eps_r, eps_r, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
+    if (eps_nl) FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, eps_nl, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
+    if (op_assemble_dev(op, op->eps_r, eps_nl ? op->eps_nl : nullptr, averaging)) return -1;
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+int fdfd_op_get_sfactors_host(fdfd_op* op, double* isxf, double* isxb, double* isyf, double* isyb) {
+    FDFD_CHECK(cudaMemcpy(isxf, op->isxf, sizeof(cplx) * op->nx, cudaMemcpyDeviceToHost));
+    FDFD_CHECK(cudaMemcpy(isxb, op->isxb, sizeof(cplx) * op->nx, cudaMemcpyDeviceToHost));
+    FDFD_CHECK(cudaMemcpy(isyf, op->isyf, sizeof(cplx) * op->ny, cudaMemcpyDeviceToHost));
+    FDFD_CHECK(cudaMemcpy(isyb, op->isyb, sizeof(cplx) * op->ny, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int fdfd_op_get_planes_host(fdfd_op* op, double* planes) {
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    FDFD_CHECK(cudaMemcpy(planes, op->planes, sizeof(cplx) * op->n() * 5, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int fdfd_op_apply_dev(fdfd_op* op, const void* d_x, void* d_y, int nvec, int fused) {
+    return fused ? op_apply_fused(op, (const cplx*)d_x, (cplx*)d_y, nvec)
+                 : op_apply_planes(op, (const cplx*)d_x, (cplx*)d_y, nvec);
+}
+int fdfd_op_apply_host(fdfd_op* op, const double* x, double* y, int nvec, int fused) {
+    size_t cnt = op->n() * nvec;
+    DevBuf dx, dy;
+    if (dx.alloc(cnt) || dy.alloc(cnt)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(dx.p, x, sizeof(cplx) * cnt, cudaMemcpyHostToDevice, op->stream));
+    if (fdfd_op_apply_dev(op, dx.p, dy.p, nvec, fused)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(y, dy.p, sizeof(cplx) * cnt, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2) {
+    return op_derive_fields(op, (const cplx*)d_x, (cplx*)d_f1, (cplx*)d_f2);
+}
+int fdfd_op_derive_fields_host(fdfd_op* op, const double* x, double* f1, double* f2) {
+    size_t n = op->n();
+    DevBuf buf;
+    if (buf.alloc(3 * n)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(buf.p, x, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
+    if (op_derive_fields(op, buf.p, buf.p + n, buf.p + 2 * n)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(f1, buf.p + n, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(f2, buf.p + 2 * n, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+
+int fdfd_direct_create(fdfd_direct** out, int nx, int ny, int tile) { return nd_create(out, nx, ny, tile); }
+int fdfd_direct_add_level(fdfd_direct* s, const fdfd_level_desc* d) {
+    NdLevelDesc x;
+    x.kind = d->kind; x.nb = d->nb; x.kmax = d->kmax; x.mmax = d->mmax; x.ncls = d->ncls;
+    x.child_mmax = d->child_mmax; x.cls = d->cls; x.k_cls = d->k_cls; x.ch1 = d->ch1; x.ch2 = d->ch2;
+    x.c1map = d->c1map; x.c2map = d->c2map; x.x0 = d->x0; x.y0 = d->y0; x.slot_lx = d->slot_lx;
+    x.slot_ly = d->slot_ly; x.slot_right = d->slot_right; x.slot_up = d->slot_up;
+    return nd_add_level(s, &x);
+}
+void fdfd_direct_destroy(fdfd_direct* s) { nd_destroy(s); }
+int fdfd_direct_factor(fdfd_direct* s, fdfd_op* op) { return nd_factor(s, op); }
+int fdfd_direct_stats(fdfd_direct* s, double* factor_bytes, double* factor_flops) {
+    *factor_bytes = (double)s->factor_bytes;
+    *factor_flops = s->factor_flops;
+    return 0;
+}
+int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_x, int nrhs, int max_refine,
+                          double tol, double* relres, int* refine_steps) {
+    double rr = -1.0;
+    int steps = 0;
+    if (max_refine < 0) {          // plain substitution, no residual evaluation
+        if (nd_solve(s, op, (const cplx*)d_b, (cplx*)d_x, nrhs)) return -1;
+    } else if (refine_solve(s, op, (const cplx*)d_b, (cplx*)d_x, nrhs, max_refine, tol, &rr, &steps)) {
+        return -1;
+    }
+    if (relres) *relres = rr;
+    if (refine_steps) *refine_steps = steps;
+    return 0;
+}
+int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b, double* x, int nrhs, int max_refine,
+                           double tol, double* relres, int* refine_steps) {
+    size_t cnt = op->n() * nrhs;
+    DevBuf db, dx;
+    if (db.alloc(cnt) || dx.alloc(cnt)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(db.p, b, sizeof(cplx) * cnt, cudaMemcpyHostToDevice, op->stream));
+    if (fdfd_direct_solve_dev(s, op, db.p, dx.p, nrhs, max_refine, tol, relres, refine_steps)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(x, dx.p, sizeof(cplx) * cnt, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+
+int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, void* d_x, int method, double tol,
+                          int maxiter, int fused, int check_every, int* iters, double* relres, int* converged) {
+    KrylovResult r;
+    int rc;
+    if (method == 0) rc = krylov_bicgstab(op, precond, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every, &r);
+    else if (method == 1) {
+        if (precond) FDFD_FAIL("COCG does not take a preconditioner");
+        rc = krylov_cocg(op, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every, &r);
+    } else FDFD_FAIL("unknown Krylov method %d", method);
+    if (rc) return -1;
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    if (iters) *iters = r.iters;
+    if (relres) *relres = r.relres;
+    if (converged) *converged = r.converged;
+    return 0;
+}
+int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b, double* x, int method, double tol,
+                           int maxiter, int fused, int check_every, int* iters, double* relres, int* converged) {
+    size_t n = op->n();
+    DevBuf db, dx;
+    if (db.alloc(n) || dx.alloc(n)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(db.p, b, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(dx.p, x, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));   // initial guess
+    if (fdfd_krylov_solve_dev(op, precond, db.p, dx.p, method, tol, maxiter, fused, check_every, iters, relres,
+                              converged))
+        return -1;
+    FDFD_CHECK(cudaMemcpy(x, dx.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M, int N, int K, int batch, int mode) {
+    // test hook: C[b] = A[b] B[b] (mode 0) or C[b] -= A[b] B[b] (mode 1), dense row-major, packed batches
+    DevBuf a, b, c;
+    size_t sa = (size_t)M * K, sb = (size_t)K * N, sc = (size_t)M * N;
+    if (a.alloc(sa * batch) || b.alloc(sb * batch) || c.alloc(sc * batch)) return -1;
+    FDFD_CHECK(cudaMemcpy(a.p, A, sizeof(cplx) * sa * batch, cudaMemcpyHostToDevice));
+    FDFD_CHECK(cudaMemcpy(b.p, B, sizeof(cplx) * sb * batch, cudaMemcpyHostToDevice));
+    FDFD_CHECK(cudaMemcpy(c.p, Cm, sizeof(cplx) * sc * batch, cudaMemcpyHostToDevice));
+    GemmBatch g;
+    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = N; g.C = c.p; g.sC = sc; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode;
+    if (zgemm_batched(g, 0)) return -1;
+    FDFD_CHECK(cudaDeviceSynchronize());
+    FDFD_CHECK(cudaMemcpy(Cm, c.p, sizeof(cplx) * sc * batch, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl, int pol, double L0, double neff,
+                         int order, int averaged, double* vals, double* vecs) {
+    return mode_solve(eps_line, n, omega, dl, pol, L0, neff, order, averaged, vals, vecs);
+}
+
+}  // extern "C"

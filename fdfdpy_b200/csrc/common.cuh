@@ -1,0 +1,60 @@
+// Shared device helpers for the fdfdpy_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+typedef double2 cplx;   // (re, im), layout-compatible with numpy complex128
+
+extern thread_local char g_fdfd_err[512];
+
+#define FDFD_CHECK(call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            snprintf(g_fdfd_err, sizeof(g_fdfd_err), "%s:%d: %s -> %s", __FILE__, __LINE__, \
+                     #call, cudaGetErrorString(e__));                                     \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+#define FDFD_FAIL(...)                                                 \
+    do {                                                               \
+        snprintf(g_fdfd_err, sizeof(g_fdfd_err), __VA_ARGS__);         \
+        return -1;                                                     \
+    } while (0)
+
+__host__ __device__ __forceinline__ cplx cmake(double r, double i) { return make_double2(r, i); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ cplx cneg(cplx a) { return make_double2(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+// a += b*c
+__host__ __device__ __forceinline__ void cfma(cplx& a, cplx b, cplx c) {
+    a.x = fma(b.x, c.x, a.x);
+    a.x = fma(-b.y, c.y, a.x);
+    a.y = fma(b.x, c.y, a.y);
+    a.y = fma(b.y, c.x, a.y);
+}
+__host__ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    // Smith's algorithm (no spurious overflow for the huge |S| values deep in the PML)
+    if (fabs(b.x) >= fabs(b.y)) {
+        double r = b.y / b.x, d = b.x + b.y * r;
+        return make_double2((a.x + a.y * r) / d, (a.y - a.x * r) / d);
+    } else {
+        double r = b.x / b.y, d = b.x * r + b.y;
+        return make_double2((a.x * r + a.y) / d, (a.y * r - a.x) / d);
+    }
+}
+__host__ __device__ __forceinline__ cplx crecip(cplx b) { return cdiv(make_double2(1.0, 0.0), b); }
+
+__device__ __forceinline__ cplx ldg_c(const cplx* p) { return __ldg(p); }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

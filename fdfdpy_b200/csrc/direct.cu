@@ -1,0 +1,614 @@
+// Batched multifrontal nested-dissection solver for the 5-point Maxwell stencil on a torus.
+//
+// Replaces the general sparse LU the reference calls in solver_direct (linalg.py:123-149).
+// Every level of the elimination tree is ONE batch of equally padded dense fronts
+//        F = [ F_EE  F_ER ]      E: unknowns eliminated at this level (leaf interiors / shared lines)
+//            [ F_RE  F_RR ]      R: the box ring handed to the parent
+// A blocked Gauss-Jordan sweep over the E pivots turns F in place into
+//        [  F_EE^-1        F_EE^-1 F_ER ]
+//        [ -F_RE F_EE^-1   S            ]   S = F_RR - F_RE F_EE^-1 F_ER  (Schur complement)
+// so the triangular solves of a classic multifrontal code become plain batched matrix-vector
+// products in the solve phase.  The rank-T updates of the sweep are complex GEMMs on the FP64
+// tensor pipe (zgemm.cuh); pivot tiles are inverted in shared memory with partial pivoting.
+#include "direct.cuh"
+#include "zgemm.cuh"
+
+// ------------------------------------------------------------------------------------------
+// assembly
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, const int* __restrict__ cls,
+                     const int* __restrict__ k_cls, const int* __restrict__ x0, const int* __restrict__ y0,
+                     const int* __restrict__ slot_lx, const int* __restrict__ slot_ly,
+                     const int* __restrict__ slot_right, const int* __restrict__ slot_up, int kmax, int nmax,
+                     int nx, int ny) {
+    const long long b = blockIdx.x;
+    const int c = cls[b];
+    cplx* Fb = F + b * (long long)nmax * nmax;
+    const size_t n = (size_t)nx * ny;
+    for (int e = threadIdx.x; e < nmax * nmax; e += blockDim.x) Fb[e] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const int kc = k_cls[c];
+    for (int s = threadIdx.x; s < nmax; s += blockDim.x) {
+        if (s >= kc && s < kmax) Fb[s * nmax + s] = make_double2(1.0, 0.0);   // padded pivots
+        int r = slot_right[c * nmax + s];
+        if (r < 0) continue;                                                  // not an owner slot
+        int u = slot_up[c * nmax + s];
+        int x = x0[b] + slot_lx[c * nmax + s];
+        int y = y0[b] + slot_ly[c * nmax + s];
+        if (x >= nx) x -= nx;
+        if (y >= ny) y -= ny;
+        int xr = x + 1 == nx ? 0 : x + 1, yu = y + 1 == ny ? 0 : y + 1;
+        size_t node = (size_t)x * ny + y, nr = (size_t)xr * ny + y, nu = (size_t)x * ny + yu;
+        Fb[s * nmax + s] = planes[node];                 // c0
+        Fb[s * nmax + r] = planes[2 * n + node];         // cxp: row node, column right neighbour
+        Fb[r * nmax + s] = planes[n + nr];               // cxm of the right neighbour
+        Fb[s * nmax + u] = planes[4 * n + node];         // cyp
+        Fb[u * nmax + s] = planes[3 * n + nu];           // cym of the upper neighbour
+    }
+}
+
+__global__ void __launch_bounds__(256)
+merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const int* __restrict__ cls,
+                      const int* __restrict__ k_cls, const int* __restrict__ ch1, const int* __restrict__ ch2,
+                      const int* __restrict__ inv1, const int* __restrict__ inv2, int kmax, int nmax,
+                      int kc, int nc, int chunks) {
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    const int c = cls[b];
+    const int* i1 = inv1 + (size_t)c * nmax;
+    const int* i2 = inv2 + (size_t)c * nmax;
+    const cplx* S1 = Fc + (long long)ch1[b] * nc * nc;
+    const cplx* S2 = Fc + (long long)ch2[b] * nc * nc;
+    cplx* Fb = F + b * (long long)nmax * nmax;
+    const int kcls = k_cls[c];
+    const long long total = (long long)nmax * nmax;
+    const long long per = (total + chunks - 1) / chunks;
+    const long long e0 = chunk * per, e1 = min(total, e0 + per);
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        int p = (int)(e / nmax), q = (int)(e % nmax);
+        cplx v = make_double2(0.0, 0.0);
+        int a = i1[p], bq = i1[q];
+        if (a >= 0 && bq >= 0) v = S1[(size_t)(kc + a) * nc + kc + bq];
+        a = i2[p];
+        bq = i2[q];
+        if (a >= 0 && bq >= 0) v = cadd(v, S2[(size_t)(kc + a) * nc + kc + bq]);
+        if (p == q && p >= kcls && p < kmax) v = make_double2(1.0, 0.0);
+        Fb[e] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// blocked Gauss-Jordan sweep pieces
+// ------------------------------------------------------------------------------------------
+// P[b] = inverse of the tw x tw pivot tile F[b][j0:j0+tw, j0:j0+tw]; Gauss-Jordan on [A | I] in
+// shared memory with partial (row) pivoting inside the tile.
+__global__ void pivot_inverse_kernel(const cplx* __restrict__ F, int nmax, int j0, int tw,
+                                     cplx* __restrict__ P, int tcap, int* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);          // [tw][2*tw]
+    cplx* scol = sm + (size_t)tw * 2 * tw;                  // [tw]
+    __shared__ int s_piv;
+    const long long b = blockIdx.x;
+    const cplx* Fb = F + b * (long long)nmax * nmax;
+    const int w2 = 2 * tw;
+    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
+        int r = i / tw, c = i % tw;
+        sm[r * w2 + c] = Fb[(size_t)(j0 + r) * nmax + j0 + c];
+        sm[r * w2 + tw + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+    for (int col = 0; col < tw; ++col) {
+        if (threadIdx.x < 32) {
+            double best = -1.0;
+            int bi = col;
+            for (int r = col + threadIdx.x; r < tw; r += 32) {
+                double v = cabs2(sm[r * w2 + col]);
+                if (v > best) { best = v; bi = r; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_down_sync(0xffffffffu, best, o);
+                int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (threadIdx.x == 0) {
+                s_piv = bi;
+                if (!(best > 1e-300)) atomicExch(info, 1);
+            }
+        }
+        __syncthreads();
+        const int p = s_piv;
+        const cplx ipiv = crecip(sm[p * w2 + col]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < w2; c += blockDim.x) {
+            cplx a = sm[col * w2 + c], bb = sm[p * w2 + c];
+            if (p != col) sm[p * w2 + c] = a;
+            sm[col * w2 + c] = cmul(bb, ipiv);
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < tw; r += blockDim.x) scol[r] = sm[r * w2 + col];
+        __syncthreads();
+        for (int i = threadIdx.x; i < tw * w2; i += blockDim.x) {
+            int r = i / w2, c = i % w2;
+            if (r == col) continue;
+            cplx f = scol[r];
+            cplx pr = sm[col * w2 + c];
+            cplx v = sm[i];
+            v.x -= f.x * pr.x - f.y * pr.y;
+            v.y -= f.x * pr.y + f.y * pr.x;
+            sm[i] = v;
+        }
+        __syncthreads();
+    }
+    cplx* Pb = P + b * (long long)tcap * tcap;
+    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
+        int r = i / tw, c = i % tw;
+        Pb[r * tcap + c] = sm[r * w2 + tw + c];
+    }
+}
+
+// Cbuf[b][r][:] = r in J ? 0 : F[b][r][J];   F[b][r][J] = r in J ? I : 0
+__global__ void __launch_bounds__(256)
+panel_kernel(cplx* __restrict__ F, cplx* __restrict__ Cbuf, int nmax, int j0, int tw, int tcap, int chunks) {
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    cplx* Fb = F + b * (long long)nmax * nmax;
+    cplx* Cb = Cbuf + b * (long long)nmax * tcap;
+    const int total = nmax * tw;
+    const int per = (total + chunks - 1) / chunks;
+    const int e0 = chunk * per, e1 = min(total, e0 + per);
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        int r = e / tw, c = e % tw;
+        bool inJ = r >= j0 && r < j0 + tw;
+        cplx* f = Fb + (size_t)r * nmax + j0 + c;
+        Cb[r * tcap + c] = inJ ? make_double2(0.0, 0.0) : *f;
+        *f = make_double2((inJ && r - j0 == c) ? 1.0 : 0.0, 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(cplx* __restrict__ F, const cplx* __restrict__ Rbuf, int nmax, int j0, int tw, int tcap,
+                 int chunks) {
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    cplx* Fb = F + b * (long long)nmax * nmax + (size_t)j0 * nmax;
+    const cplx* Rb = Rbuf + b * (long long)tcap * nmax;
+    const int total = nmax * tw;
+    const int per = (total + chunks - 1) / chunks;
+    const int e0 = chunk * per, e1 = min(total, e0 + per);
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) Fb[e] = Rb[e];
+}
+
+// EZX[b] = F[b][0:kmax, :],  RW[b] = F[b][kmax:, 0:kmax]
+__global__ void __launch_bounds__(256)
+extract_kernel(const cplx* __restrict__ F, cplx* __restrict__ EZX, cplx* __restrict__ RW, int kmax, int mmax,
+               int nmax, int chunks) {
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    const cplx* Fb = F + b * (long long)nmax * nmax;
+    cplx* Eb = EZX + b * (long long)kmax * nmax;
+    cplx* Rb = RW + b * (long long)mmax * kmax;
+    const long long t1 = (long long)kmax * nmax, t2 = (long long)mmax * kmax;
+    const long long total = t1 + t2;
+    const long long per = (total + chunks - 1) / chunks;
+    const long long e0 = chunk * per, e1 = min(total, e0 + per);
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        if (e < t1) Eb[e] = Fb[e];
+        else {
+            long long q = e - t1;
+            int i = (int)(q / kmax), c = (int)(q % kmax);
+            Rb[q] = Fb[(size_t)(kmax + i) * nmax + c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// solve-phase kernels.  Front vectors are [slot][NR] with the right-hand-side index fastest.
+// ------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(128)
+leaf_gather_kernel(cplx* __restrict__ f, const cplx* __restrict__ rhs, const int* __restrict__ cls,
+                   const int* __restrict__ x0, const int* __restrict__ y0, const int* __restrict__ slot_lx,
+                   const int* __restrict__ slot_ly, const int* __restrict__ slot_right, int nmax, int nx, int ny,
+                   int nr_act, long long nb) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * nmax) return;
+    long long b = gid / nmax;
+    int s = (int)(gid % nmax);
+    int c = cls[b];
+    cplx v[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = make_double2(0.0, 0.0);
+    if (slot_right[c * nmax + s] >= 0) {
+        int x = x0[b] + slot_lx[c * nmax + s], y = y0[b] + slot_ly[c * nmax + s];
+        if (x >= nx) x -= nx;
+        if (y >= ny) y -= ny;
+        size_t node = (size_t)x * ny + y, n = (size_t)nx * ny;
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+            if (j < nr_act) v[j] = rhs[j * n + node];
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) f[gid * NR + j] = v[j];
+}
+
+template <int NR>
+__global__ void __launch_bounds__(128)
+leaf_scatter_kernel(const cplx* __restrict__ u, cplx* __restrict__ out, const int* __restrict__ cls,
+                    const int* __restrict__ x0, const int* __restrict__ y0, const int* __restrict__ slot_lx,
+                    const int* __restrict__ slot_ly, const int* __restrict__ slot_right, int nmax, int nx, int ny,
+                    int nr_act, long long nb) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * nmax) return;
+    long long b = gid / nmax;
+    int s = (int)(gid % nmax);
+    int c = cls[b];
+    if (slot_right[c * nmax + s] < 0) return;
+    int x = x0[b] + slot_lx[c * nmax + s], y = y0[b] + slot_ly[c * nmax + s];
+    if (x >= nx) x -= nx;
+    if (y >= ny) y -= ny;
+    size_t node = (size_t)x * ny + y, n = (size_t)nx * ny;
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+        if (j < nr_act) out[j * n + node] = u[gid * NR + j];
+}
+
+// f[b][p] = ring_child1[inv1[p]] + ring_child2[inv2[p]]
+template <int NR>
+__global__ void __launch_bounds__(128)
+merge_gather_kernel(cplx* __restrict__ f, const cplx* __restrict__ ring_c, const int* __restrict__ cls,
+                    const int* __restrict__ ch1, const int* __restrict__ ch2, const int* __restrict__ inv1,
+                    const int* __restrict__ inv2, int nmax, int mc, long long nb) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * nmax) return;
+    long long b = gid / nmax;
+    int p = (int)(gid % nmax);
+    int c = cls[b];
+    int a1 = inv1[(size_t)c * nmax + p], a2 = inv2[(size_t)c * nmax + p];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        cplx v = make_double2(0.0, 0.0);
+        if (a1 >= 0) v = ring_c[((long long)ch1[b] * mc + a1) * NR + j];
+        if (a2 >= 0) v = cadd(v, ring_c[((long long)ch2[b] * mc + a2) * NR + j]);
+        f[gid * NR + j] = v;
+    }
+}
+
+// children pick their ring values out of the parent's solved front:  u_child[kc+i] = u_par[cmap[i]]
+template <int NR>
+__global__ void __launch_bounds__(128)
+child_scatter_kernel(cplx* __restrict__ uc, const cplx* __restrict__ up, const int* __restrict__ cls,
+                     const int* __restrict__ ch1, const int* __restrict__ ch2, const int* __restrict__ c1map,
+                     const int* __restrict__ c2map, int nmax, int mc, int kc, int nc, long long nb) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * 2 * mc) return;
+    long long b = gid / (2 * mc);
+    int r = (int)(gid % (2 * mc));
+    int which = r / mc, i = r % mc;
+    int c = cls[b];
+    int slot = (which ? c2map : c1map)[(size_t)c * mc + i];
+    if (slot < 0) return;
+    long long ch = which ? ch2[b] : ch1[b];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) uc[(ch * nc + kc + i) * NR + j] = up[(b * nmax + slot) * NR + j];
+}
+
+// forward: yE = Z f_E ; ring = f_R + (-W) f_E.   One warp per output row.
+template <int NR>
+__global__ void __launch_bounds__(256)
+forward_mv_kernel(const cplx* __restrict__ EZX, const cplx* __restrict__ RW, const cplx* __restrict__ f,
+                  cplx* __restrict__ yE, cplx* __restrict__ ring, int kmax, int mmax, int nmax, long long nb) {
+    long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (gw >= nb * nmax) return;
+    long long b = gw / nmax;
+    int r = (int)(gw % nmax);
+    const cplx* row = r < kmax ? EZX + (b * kmax + r) * nmax : RW + (b * mmax + (r - kmax)) * kmax;
+    const cplx* v = f + b * nmax * NR;
+    cplx acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int c = lane; c < kmax; c += 32) {
+        cplx m = ldg_c(row + c);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+        for (int o = 16; o > 0; o >>= 1) {
+            acc[j].x += __shfl_down_sync(0xffffffffu, acc[j].x, o);
+            acc[j].y += __shfl_down_sync(0xffffffffu, acc[j].y, o);
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            if (r < kmax) yE[(b * kmax + r) * NR + j] = acc[j];
+            else ring[(b * mmax + (r - kmax)) * NR + j] = cadd(v[r * NR + j], acc[j]);
+        }
+    }
+}
+
+// backward: u_E = yE - X u_R
+template <int NR>
+__global__ void __launch_bounds__(256)
+backward_mv_kernel(const cplx* __restrict__ EZX, const cplx* __restrict__ yE, cplx* __restrict__ u, int kmax,
+                   int mmax, int nmax, long long nb) {
+    long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (gw >= nb * kmax) return;
+    long long b = gw / kmax;
+    int r = (int)(gw % kmax);
+    const cplx* row = EZX + (b * kmax + r) * nmax + kmax;
+    const cplx* v = u + (b * nmax + kmax) * NR;
+    cplx acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int c = lane; c < mmax; c += 32) {
+        cplx m = ldg_c(row + c);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+        for (int o = 16; o > 0; o >>= 1) {
+            acc[j].x += __shfl_down_sync(0xffffffffu, acc[j].x, o);
+            acc[j].y += __shfl_down_sync(0xffffffffu, acc[j].y, o);
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) u[(b * nmax + r) * NR + j] = csub(yE[(b * kmax + r) * NR + j], acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int upload_i32(int** dst, const int* src, size_t count) {
+    *dst = nullptr;
+    if (!src || count == 0) return 0;
+    FDFD_CHECK(cudaMalloc(dst, count * sizeof(int)));
+    FDFD_CHECK(cudaMemcpy(*dst, src, count * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int nd_create(NdSolver** out, int nx, int ny, int tile) {
+    if (tile < 1 || tile > 64) FDFD_FAIL("tile must be in 1..64");
+    NdSolver* s = new NdSolver();
+    s->nx = nx; s->ny = ny; s->tile = tile; s->factored = false;
+    s->factor_bytes = 0; s->factor_flops = 0;
+    s->ws_a = s->ws_b = s->ws_ring_a = s->ws_ring_b = s->ws_ye = nullptr;
+    s->ws_vec_cap = s->ws_ring_cap = s->ws_ye_cap = 0;
+    s->d_info = nullptr;
+    FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
+    *out = s;
+    return 0;
+}
+
+int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
+    NdLevel L;
+    memset(&L, 0, sizeof(L));
+    L.kind = d->kind; L.nb = d->nb; L.kmax = d->kmax; L.mmax = d->mmax; L.nmax = d->kmax + d->mmax;
+    L.ncls = d->ncls; L.child_mmax = d->child_mmax;
+    if (upload_i32(&L.cls, d->cls, d->nb)) return -1;
+    if (upload_i32(&L.k_cls, d->k_cls, d->ncls)) return -1;
+    if (d->kind == 0) {
+        size_t t = (size_t)d->ncls * L.nmax;
+        if (upload_i32(&L.x0, d->x0, d->nb) || upload_i32(&L.y0, d->y0, d->nb) ||
+            upload_i32(&L.slot_lx, d->slot_lx, t) || upload_i32(&L.slot_ly, d->slot_ly, t) ||
+            upload_i32(&L.slot_right, d->slot_right, t) || upload_i32(&L.slot_up, d->slot_up, t))
+            return -1;
+    } else {
+        if (s->levels.empty()) FDFD_FAIL("merge level before any leaf level");
+        size_t t = (size_t)d->ncls * d->child_mmax;
+        if (upload_i32(&L.ch1, d->ch1, d->nb) || upload_i32(&L.ch2, d->ch2, d->nb) ||
+            upload_i32(&L.c1map, d->c1map, t) || upload_i32(&L.c2map, d->c2map, t))
+            return -1;
+        // inverse maps: front slot -> child ring position
+        std::vector<int> i1((size_t)d->ncls * L.nmax, -1), i2((size_t)d->ncls * L.nmax, -1);
+        for (int c = 0; c < d->ncls; ++c)
+            for (int i = 0; i < d->child_mmax; ++i) {
+                int a = d->c1map[(size_t)c * d->child_mmax + i];
+                int b = d->c2map[(size_t)c * d->child_mmax + i];
+                if (a >= L.nmax || b >= L.nmax) FDFD_FAIL("child map out of range");
+                if (a >= 0) i1[(size_t)c * L.nmax + a] = i;
+                if (b >= 0) i2[(size_t)c * L.nmax + b] = i;
+            }
+        if (upload_i32(&L.inv1, i1.data(), i1.size()) || upload_i32(&L.inv2, i2.data(), i2.size())) return -1;
+    }
+    s->levels.push_back(L);
+    s->factored = false;
+    return 0;
+}
+
+static void free_level_factors(NdLevel& L) {
+    if (L.EZX) cudaFree(L.EZX);
+    if (L.RW) cudaFree(L.RW);
+    L.EZX = L.RW = nullptr;
+}
+
+void nd_destroy(NdSolver* s) {
+    if (!s) return;
+    for (auto& L : s->levels) {
+        free_level_factors(L);
+        int* ptrs[] = {L.cls, L.k_cls, L.ch1, L.ch2, L.c1map, L.c2map, L.inv1, L.inv2,
+                       L.x0, L.y0, L.slot_lx, L.slot_ly, L.slot_right, L.slot_up};
+        for (int* p : ptrs)
+            if (p) cudaFree(p);
+    }
+    cudaFree(s->ws_a); cudaFree(s->ws_b); cudaFree(s->ws_ring_a); cudaFree(s->ws_ring_b); cudaFree(s->ws_ye);
+    cudaFree(s->d_info);
+    delete s;
+}
+
+static int chunks_for(long long per_front_elems, long long nb) {
+    // enough CTAs to fill the machine when there are few big fronts, one CTA per front otherwise
+    long long want = (148LL * 8 + nb - 1) / nb;
+    long long maxc = (per_front_elems + 2047) / 2048;
+    long long c = want < maxc ? want : maxc;
+    return (int)(c < 1 ? 1 : c);
+}
+
+int nd_factor(NdSolver* s, const FdfdOp* op) {
+    if (s->levels.empty()) FDFD_FAIL("no levels in the plan");
+    if (op->nx != s->nx || op->ny != s->ny) FDFD_FAIL("operator / plan shape mismatch");
+    cudaStream_t st = op->stream;
+    FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
+    cplx* Fprev = nullptr;
+    int prev_k = 0, prev_n = 0;
+    s->factor_bytes = 0;
+    s->factor_flops = 0;
+    for (size_t li = 0; li < s->levels.size(); ++li) {
+        NdLevel& L = s->levels[li];
+        free_level_factors(L);
+        const long long nb = L.nb;
+        const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
+        const int tcap = kmax < s->tile ? kmax : s->tile;
+        cplx *F = nullptr, *Pbuf = nullptr, *Cbuf = nullptr, *Rbuf = nullptr;
+        FDFD_CHECK(cudaMalloc(&F, sizeof(cplx) * nb * nmax * nmax));
+        FDFD_CHECK(cudaMalloc(&Pbuf, sizeof(cplx) * nb * tcap * tcap));
+        FDFD_CHECK(cudaMalloc(&Cbuf, sizeof(cplx) * nb * nmax * tcap));
+        FDFD_CHECK(cudaMalloc(&Rbuf, sizeof(cplx) * nb * tcap * nmax));
+        if (L.kind == 0) {
+            leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
+                                                              L.slot_ly, L.slot_right, L.slot_up, kmax, nmax,
+                                                              s->nx, s->ny);
+        } else {
+            int chunks = chunks_for((long long)nmax * nmax, nb);
+            merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
+                                                                           L.inv1, L.inv2, kmax, nmax, prev_k,
+                                                                           prev_n, chunks);
+        }
+        FDFD_CHECK(cudaGetLastError());
+        for (int j0 = 0; j0 < kmax; j0 += tcap) {
+            const int tw = (kmax - j0) < tcap ? (kmax - j0) : tcap;
+            size_t smem = sizeof(cplx) * ((size_t)tw * 2 * tw + tw);
+            int threads = tw * tw >= 512 ? 256 : (tw * tw >= 128 ? 128 : 64);
+            if (smem > 48 * 1024)
+                FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
+            int chunks = chunks_for((long long)nmax * tw, nb);
+            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
+            FDFD_CHECK(cudaGetLastError());
+            GemmBatch g;
+            g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
+            g.B = F + (size_t)j0 * nmax; g.sB = (long long)nmax * nmax; g.ldb = nmax;
+            g.C = Rbuf; g.sC = (long long)tcap * nmax; g.ldc = nmax;
+            g.M = tw; g.N = nmax; g.K = tw; g.batch = (int)nb; g.mode = 0;
+            if (zgemm_batched(g, st)) return -1;
+            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
+            FDFD_CHECK(cudaGetLastError());
+            g.A = Cbuf; g.sA = (long long)nmax * tcap; g.lda = tcap;
+            g.B = Rbuf; g.sB = (long long)tcap * nmax; g.ldb = nmax;
+            g.C = F; g.sC = (long long)nmax * nmax; g.ldc = nmax;
+            g.M = nmax; g.N = nmax; g.K = tw; g.mode = 1;
+            if (zgemm_batched(g, st)) return -1;
+            s->factor_flops += 8.0 * (double)nb * ((double)nmax * nmax * tw + (double)tw * tw * nmax);
+        }
+        FDFD_CHECK(cudaMalloc(&L.EZX, sizeof(cplx) * (size_t)nb * kmax * nmax));
+        if (mmax > 0) FDFD_CHECK(cudaMalloc(&L.RW, sizeof(cplx) * (size_t)nb * mmax * kmax));
+        s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * nmax + (size_t)nb * mmax * kmax);
+        {
+            int chunks = chunks_for((long long)kmax * nmax + (long long)mmax * kmax, nb);
+            extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks);
+            FDFD_CHECK(cudaGetLastError());
+        }
+        FDFD_CHECK(cudaStreamSynchronize(st));
+        cudaFree(Pbuf); cudaFree(Cbuf); cudaFree(Rbuf);
+        if (Fprev) cudaFree(Fprev);
+        Fprev = F;
+        prev_k = kmax;
+        prev_n = nmax;
+    }
+    if (Fprev) cudaFree(Fprev);
+    int info = 0;
+    FDFD_CHECK(cudaMemcpy(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info) FDFD_FAIL("direct solver: a pivot block is numerically singular (no inter-block pivoting)");
+    s->factored = true;
+    return 0;
+}
+
+template <int NR>
+static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nr_act) {
+    cudaStream_t st = op->stream;
+    const size_t nlev = s->levels.size();
+    // workspace sizing
+    size_t vec_need = 0, ring_need = 1, ye_need = 0;
+    for (auto& L : s->levels) {
+        vec_need = std::max(vec_need, (size_t)L.nb * L.nmax * NR);
+        ring_need = std::max(ring_need, (size_t)L.nb * std::max(L.mmax, 1) * NR);
+        L.ye_off = ye_need;
+        ye_need += (size_t)L.nb * L.kmax * NR;
+    }
+    if (vec_need > s->ws_vec_cap) {
+        cudaFree(s->ws_a); cudaFree(s->ws_b);
+        FDFD_CHECK(cudaMalloc(&s->ws_a, sizeof(cplx) * vec_need));
+        FDFD_CHECK(cudaMalloc(&s->ws_b, sizeof(cplx) * vec_need));
+        s->ws_vec_cap = vec_need;
+    }
+    if (ring_need > s->ws_ring_cap) {
+        cudaFree(s->ws_ring_a); cudaFree(s->ws_ring_b);
+        FDFD_CHECK(cudaMalloc(&s->ws_ring_a, sizeof(cplx) * ring_need));
+        FDFD_CHECK(cudaMalloc(&s->ws_ring_b, sizeof(cplx) * ring_need));
+        s->ws_ring_cap = ring_need;
+    }
+    if (ye_need > s->ws_ye_cap) {
+        cudaFree(s->ws_ye);
+        FDFD_CHECK(cudaMalloc(&s->ws_ye, sizeof(cplx) * ye_need));
+        s->ws_ye_cap = ye_need;
+    }
+    cplx *f = s->ws_a, *ring_prev = s->ws_ring_a, *ring_cur = s->ws_ring_b;
+    // ---- forward (leaves -> root)
+    for (size_t li = 0; li < nlev; ++li) {
+        NdLevel& L = s->levels[li];
+        const long long nb = L.nb;
+        long long tot = nb * L.nmax;
+        if (L.kind == 0)
+            leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
+                                                                       L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb);
+        else
+            merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
+                                                                        L.inv2, L.nmax, L.child_mmax, nb);
+        forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.EZX, L.RW, f, s->ws_ye + L.ye_off, ring_cur,
+                                                                       L.kmax, L.mmax, L.nmax, nb);
+        FDFD_CHECK(cudaGetLastError());
+        std::swap(ring_prev, ring_cur);
+    }
+    // ---- backward (root -> leaves)
+    cplx *u = s->ws_a, *u_par = s->ws_b;
+    for (size_t li = nlev; li-- > 0;) {
+        NdLevel& L = s->levels[li];
+        const long long nb = L.nb;
+        FDFD_CHECK(cudaMemsetAsync(u, 0, sizeof(cplx) * (size_t)nb * L.nmax * NR, st));
+        if (li + 1 < nlev) {
+            NdLevel& P = s->levels[li + 1];
+            long long tot = (long long)P.nb * 2 * P.child_mmax;
+            child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
+                                                                         P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb);
+        }
+        backward_mv_kernel<NR><<<ceil_div(nb * L.kmax * 32, 256), 256, 0, st>>>(L.EZX, s->ws_ye + L.ye_off, u, L.kmax,
+                                                                                L.mmax, L.nmax, nb);
+        if (L.kind == 0) {
+            long long tot = nb * L.nmax;
+            leaf_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, d_x, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
+                                                                        L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb);
+        }
+        FDFD_CHECK(cudaGetLastError());
+        std::swap(u, u_par);
+    }
+    return 0;
+}
+
+int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs) {
+    if (!s->factored) FDFD_FAIL("nd_solve called before nd_factor");
+    const size_t n = (size_t)s->nx * s->ny;
+    for (int j0 = 0; j0 < nrhs;) {
+        int rem = nrhs - j0, rc;
+        if (rem >= 8) { rc = 8; if (nd_solve_chunk<8>(s, op, d_b + j0 * n, d_x + j0 * n, 8)) return -1; }
+        else if (rem > 2) { rc = rem < 4 ? rem : 4; if (nd_solve_chunk<4>(s, op, d_b + j0 * n, d_x + j0 * n, rc)) return -1; }
+        else if (rem == 2) { rc = 2; if (nd_solve_chunk<2>(s, op, d_b + j0 * n, d_x + j0 * n, 2)) return -1; }
+        else { rc = 1; if (nd_solve_chunk<1>(s, op, d_b + j0 * n, d_x + j0 * n, 1)) return -1; }
+        j0 += rc;
+    }
+    return 0;
+}

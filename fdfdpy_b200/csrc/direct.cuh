@@ -1,0 +1,52 @@
+// Structured direct solver: batched multifrontal nested dissection on the periodic grid.
+// Plan semantics are documented in fdfdpy_b200/ndplan.py; this side owns the numerics.
+#pragma once
+#include <vector>
+#include "operator.cuh"
+
+struct NdLevelDesc {          // host view handed over the C ABI, all arrays int32 host pointers
+    int kind;                 // 0 leaf, 1 merge
+    int nb, kmax, mmax, ncls, child_mmax;
+    const int* cls;           // [nb]
+    const int* k_cls;         // [ncls]
+    const int* ch1;           // [nb]      (merge)
+    const int* ch2;           // [nb]      (merge)
+    const int* c1map;         // [ncls][child_mmax] (merge)
+    const int* c2map;         // [ncls][child_mmax] (merge)
+    const int* x0;            // [nb]      (leaf)
+    const int* y0;            // [nb]      (leaf)
+    const int* slot_lx;       // [ncls][nmax] (leaf)
+    const int* slot_ly;
+    const int* slot_right;
+    const int* slot_up;
+};
+
+struct NdLevel {
+    int kind, nb, kmax, mmax, nmax, ncls, child_mmax;
+    int *cls, *k_cls, *ch1, *ch2, *c1map, *c2map, *inv1, *inv2;
+    int *x0, *y0, *slot_lx, *slot_ly, *slot_right, *slot_up;
+    cplx* EZX;    // [nb][kmax][nmax]   rows of the swept front:  [ F_EE^-1 | F_EE^-1 F_ER ]
+    cplx* RW;     // [nb][mmax][kmax]   -F_RE F_EE^-1
+    cplx* yE;     // solve workspace [nb][kmax][nrhs]
+    size_t ye_off;
+};
+
+struct NdSolver {
+    int nx, ny;
+    int tile;                         // pivot block width of the blocked sweep
+    std::vector<NdLevel> levels;
+    bool factored;
+    size_t factor_bytes;
+    double factor_flops;              // real flops of the last factorisation (8 per complex MAC)
+    int* d_info;                      // device flag: non-zero if a pivot tile was singular
+    // solve workspace (grown on demand)
+    cplx *ws_a, *ws_b, *ws_ring_a, *ws_ring_b, *ws_ye;
+    size_t ws_vec_cap, ws_ring_cap, ws_ye_cap;
+};
+
+int nd_create(NdSolver** out, int nx, int ny, int tile);
+int nd_add_level(NdSolver* s, const NdLevelDesc* d);
+void nd_destroy(NdSolver* s);
+int nd_factor(NdSolver* s, const FdfdOp* op);
+// d_b, d_x: [nrhs][nx*ny] device vectors
+int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs);

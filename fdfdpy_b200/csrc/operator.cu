@@ -1,0 +1,308 @@
+// Maxwell operator on the device: sc-PML stretch factors (reference pml.py:7-41), the five
+// stencil planes of A (linalg.py:39-114), matrix-free application and the derived in-plane
+// fields (simulation.py:138-176).  All kernels are plain HBM-bound streaming kernels: the y
+// index is the fastest one in memory (derivatives.py:9-11), so threads run along y.
+#include "operator.cuh"
+
+thread_local char g_fdfd_err[512] = {0};
+
+// ------------------------------------------------------------------------------------------
+// PML: inverse stretch factors for one axis.  Restates create_sfactor's index rules
+// (pml.py:29-40): low side i <= npml, high side i > n - npml, 'f' half-cell, 'b' full-cell.
+// ------------------------------------------------------------------------------------------
+__global__ void pml_axis_kernel(cplx* __restrict__ inv_f, cplx* __restrict__ inv_b, int n, int npml,
+                                double hw, double omega, double L0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx sf = cmake(1.0, 0.0), sb = cmake(1.0, 0.0);
+    if (npml >= 1) {
+        const double eta0 = sqrt(FDFD_MU0 / FDFD_EPS0);
+        double dw = npml * hw;
+        double sig_max = -(4 + 1) * (-12.0) / (2 * eta0 * dw);
+        double lf = -1.0, lb = -1.0;
+        if (i <= npml) {
+            lf = hw * (npml - i + 0.5);
+            lb = hw * (npml - i + 1);
+        } else if (i > n - npml) {
+            lf = hw * (i - (n - npml) - 0.5);
+            lb = hw * (i - (n - npml) - 1);
+        }
+        if (lf >= 0.0) {
+            double tf = lf / dw, tb = lb / dw;
+            double den = omega * FDFD_EPS0 * L0;
+            sf = cmake(1.0, -(sig_max * (tf * tf * tf * tf)) / den);
+            sb = cmake(1.0, -(sig_max * (tb * tb * tb * tb)) / den);
+        }
+    }
+    inv_f[i] = crecip(sf);
+    inv_b[i] = crecip(sb);
+}
+
+// ------------------------------------------------------------------------------------------
+// plane assembly: one thread per cell
+// ------------------------------------------------------------------------------------------
+struct AsmParams {
+    int nx, ny, pol, averaging;
+    double omega, dx, dy, e0, m0;
+};
+
+__device__ __forceinline__ cplx edge_weight(const cplx* __restrict__ eps, int ix, int iy, int nx, int ny,
+                                            int axis, const AsmParams& p) {
+    // 1 / (eps0' * edge-averaged eps) on the lower face of cell (ix,iy) along `axis` (Hz), or 1/mu0' (Ez)
+    if (p.pol == 0) return cmake(1.0 / p.m0, 0.0);
+    cplx e = eps[(size_t)ix * ny + iy];
+    if (p.averaging) {
+        int jx = axis == 0 ? (ix == 0 ? nx - 1 : ix - 1) : ix;
+        int jy = axis == 1 ? (iy == 0 ? ny - 1 : iy - 1) : iy;
+        cplx e2 = eps[(size_t)jx * ny + jy];
+        e = cmake((e2.x + e.x) / 2, (e2.y + e.y) / 2);
+    }
+    return crecip(cscale(e, p.e0));
+}
+
+__global__ void assemble_planes_kernel(cplx* __restrict__ planes, const cplx* __restrict__ eps_r,
+                                       const cplx* __restrict__ eps_nl, const cplx* __restrict__ isxf,
+                                       const cplx* __restrict__ isxb, const cplx* __restrict__ isyf,
+                                       const cplx* __restrict__ isyb, AsmParams p) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)p.nx * p.ny;
+    if (idx >= n) return;
+    int ix = (int)(idx / p.ny), iy = (int)(idx % p.ny);
+    int ixp = ix + 1 == p.nx ? 0 : ix + 1, iyp = iy + 1 == p.ny ? 0 : iy + 1;
+    // flux weights on the lower faces: b = S_b^-1 * w / d
+    cplx bx0 = cscale(cmul(isxb[ix], edge_weight(eps_r, ix, iy, p.nx, p.ny, 0, p)), 1.0 / p.dx);
+    cplx bx1 = cscale(cmul(isxb[ixp], edge_weight(eps_r, ixp, iy, p.nx, p.ny, 0, p)), 1.0 / p.dx);
+    cplx by0 = cscale(cmul(isyb[iy], edge_weight(eps_r, ix, iy, p.nx, p.ny, 1, p)), 1.0 / p.dy);
+    cplx by1 = cscale(cmul(isyb[iyp], edge_weight(eps_r, ix, iyp, p.nx, p.ny, 1, p)), 1.0 / p.dy);
+    cplx cxm = cscale(cmul(isxf[ix], bx0), 1.0 / p.dx);
+    cplx cxp = cscale(cmul(isxf[ix], bx1), 1.0 / p.dx);
+    cplx cym = cscale(cmul(isyf[iy], by0), 1.0 / p.dy);
+    cplx cyp = cscale(cmul(isyf[iy], by1), 1.0 / p.dy);
+    cplx shift;
+    if (p.pol == 0) shift = cscale(eps_r[idx], p.omega * p.omega * p.e0);
+    else shift = cmake(p.omega * p.omega * p.m0, 0.0);
+    cplx c0 = csub(csub(shift, cadd(cxm, cxp)), cadd(cym, cyp));
+    if (eps_nl) c0 = cadd(c0, cscale(eps_nl[idx], p.omega * p.omega * p.e0));
+    planes[idx] = c0;
+    planes[n + idx] = cxm;
+    planes[2 * n + idx] = cxp;
+    planes[3 * n + idx] = cym;
+    planes[4 * n + idx] = cyp;
+}
+
+// ------------------------------------------------------------------------------------------
+// stencil application from stored planes:  y = A x   or   r = b - A x
+// ------------------------------------------------------------------------------------------
+template <bool RESID>
+__global__ void __launch_bounds__(256)
+stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ x, const cplx* __restrict__ b,
+                      cplx* __restrict__ y, int nx, int ny) {
+    size_t n = (size_t)nx * ny;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    size_t voff = (size_t)blockIdx.y * n;
+    const cplx* xv = x + voff;
+    int ix = (int)(idx / ny), iy = (int)(idx % ny);
+    size_t xm = (size_t)(ix == 0 ? nx - 1 : ix - 1) * ny + iy;
+    size_t xp = (size_t)(ix + 1 == nx ? 0 : ix + 1) * ny + iy;
+    size_t ym = (size_t)ix * ny + (iy == 0 ? ny - 1 : iy - 1);
+    size_t yp = (size_t)ix * ny + (iy + 1 == ny ? 0 : iy + 1);
+    cplx acc = cmul(ldg_c(planes + idx), ldg_c(xv + idx));
+    cfma(acc, ldg_c(planes + n + idx), ldg_c(xv + xm));
+    cfma(acc, ldg_c(planes + 2 * n + idx), ldg_c(xv + xp));
+    cfma(acc, ldg_c(planes + 3 * n + idx), ldg_c(xv + ym));
+    cfma(acc, ldg_c(planes + 4 * n + idx), ldg_c(xv + yp));
+    if (RESID) acc = csub(ldg_c(b + voff + idx), acc);
+    y[voff + idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused matrix-free Ez stencil: coefficients rebuilt from eps_r (+eps_nl) and 1-D PML products.
+// Algorithmic traffic 48 B/cell (x 16 + eps 16 + y 16) (+16 with eps_nl).  Each thread owns one
+// y column and marches ROWS consecutive rows keeping the x-neighbours in registers.
+// ------------------------------------------------------------------------------------------
+#define FUSED_ROWS 8
+__global__ void __launch_bounds__(128)
+stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__ eps_nl,
+                        const cplx* __restrict__ isxf, const cplx* __restrict__ isxb,
+                        const cplx* __restrict__ isyf, const cplx* __restrict__ isyb,
+                        const cplx* __restrict__ x, cplx* __restrict__ y, int nx, int ny,
+                        double inv_mu_dx2, double inv_mu_dy2, double w2e0) {
+    int iy = blockIdx.x * blockDim.x + threadIdx.x;
+    int ix0 = blockIdx.y * FUSED_ROWS;
+    if (iy >= ny) return;
+    size_t n = (size_t)nx * ny;
+    size_t voff = (size_t)blockIdx.z * n;
+    const cplx* xv = x + voff;
+    int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    cplx aym = cscale(cmul(isyf[iy], isyb[iy]), inv_mu_dy2);
+    cplx ayp = cscale(cmul(isyf[iy], isyb[iyp]), inv_mu_dy2);
+    int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
+    cplx xl = ldg_c(xv + (size_t)ixm * ny + iy);
+    cplx xc = ldg_c(xv + (size_t)ix0 * ny + iy);
+#pragma unroll
+    for (int r = 0; r < FUSED_ROWS; ++r) {
+        int ix = ix0 + r;
+        if (ix >= nx) break;
+        int ixp = ix + 1 == nx ? 0 : ix + 1;
+        size_t row = (size_t)ix * ny;
+        cplx xr = ldg_c(xv + (size_t)ixp * ny + iy);
+        cplx xd = ldg_c(xv + row + iym);
+        cplx xu = ldg_c(xv + row + iyp);
+        cplx e = ldg_c(eps_r + row + iy);
+        if (eps_nl) e = cadd(e, ldg_c(eps_nl + row + iy));
+        cplx axm = cscale(cmul(isxf[ix], isxb[ix]), inv_mu_dx2);
+        cplx axp = cscale(cmul(isxf[ix], isxb[ixp]), inv_mu_dx2);
+        cplx c0 = csub(csub(cscale(e, w2e0), cadd(axm, axp)), cadd(aym, ayp));
+        cplx acc = cmul(c0, xc);
+        cfma(acc, axm, xl);
+        cfma(acc, axp, xr);
+        cfma(acc, aym, xd);
+        cfma(acc, ayp, xu);
+        y[voff + row + iy] = acc;
+        xl = xc;
+        xc = xr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// derived in-plane fields
+// ------------------------------------------------------------------------------------------
+__global__ void derive_fields_kernel(const cplx* __restrict__ X, const cplx* __restrict__ eps_r,
+                                     const cplx* __restrict__ eps_nl, const cplx* __restrict__ isxb,
+                                     const cplx* __restrict__ isyb, cplx* __restrict__ f1,
+                                     cplx* __restrict__ f2, AsmParams p) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)p.nx * p.ny;
+    if (idx >= n) return;
+    int ix = (int)(idx / p.ny), iy = (int)(idx % p.ny);
+    int ixm = ix == 0 ? p.nx - 1 : ix - 1, iym = iy == 0 ? p.ny - 1 : iy - 1;
+    size_t jx = (size_t)ixm * p.ny + iy, jy = (size_t)ix * p.ny + iym;
+    cplx xc = X[idx];
+    cplx dxb = cscale(cmul(isxb[ix], csub(xc, X[jx])), 1.0 / p.dx);
+    cplx dyb = cscale(cmul(isyb[iy], csub(xc, X[jy])), 1.0 / p.dy);
+    if (p.pol == 0) {
+        // Hx = -1/(i w mu0') Dyb Ez = (i/(w mu0')) Dyb Ez ;  Hy = 1/(i w mu0') Dxb Ez
+        double c = 1.0 / p.omega / p.m0;
+        f1[idx] = cmake(-c * dyb.y, c * dyb.x);
+        f2[idx] = cmake(c * dxb.y, -c * dxb.x);
+    } else {
+        cplx e = eps_r[idx], ex = eps_r[jx], ey = eps_r[jy];
+        if (eps_nl) {
+            e = cadd(e, eps_nl[idx]);
+            ex = cadd(ex, eps_nl[jx]);
+            ey = cadd(ey, eps_nl[jy]);
+        }
+        cplx wx = e, wy = e;
+        if (p.averaging) {
+            wx = cmake((ex.x + e.x) / 2, (ex.y + e.y) / 2);
+            wy = cmake((ey.x + e.x) / 2, (ey.y + e.y) / 2);
+        }
+        // Ex = 1/(i w) Dyb Hz / ey_w ;  Ey = -1/(i w) Dxb Hz / ex_w
+        cplx a = cdiv(dyb, cscale(wy, p.e0));
+        cplx b = cdiv(dxb, cscale(wx, p.e0));
+        double c = 1.0 / p.omega;
+        f1[idx] = cmake(c * a.y, -c * a.x);
+        f2[idx] = cmake(-c * b.y, c * b.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static AsmParams make_params(const FdfdOp* op) {
+    AsmParams p;
+    p.nx = op->nx;
+    p.ny = op->ny;
+    p.pol = op->pol;
+    p.averaging = op->averaging;
+    p.omega = op->omega;
+    // grid spacing exactly as the reference derives it: L / N with L = N*dl (simulation.py:33-34, linalg.py:23-32)
+    p.dx = ((double)op->nx * op->dl) / op->nx;
+    p.dy = ((double)op->ny * op->dl) / op->ny;
+    p.e0 = FDFD_EPS0 * op->L0;
+    p.m0 = FDFD_MU0 * op->L0;
+    return p;
+}
+
+int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol,
+              double L0) {
+    if (nx < 2 || ny < 2) FDFD_FAIL("grid must be at least 2x2, got %dx%d", nx, ny);
+    if (pol != 0 && pol != 1) FDFD_FAIL("pol must be 0 (Ez) or 1 (Hz)");
+    FdfdOp* op = new FdfdOp();
+    memset(op, 0, sizeof(*op));
+    op->nx = nx; op->ny = ny; op->omega = omega; op->dl = dl; op->L0 = L0;
+    op->npml_x = npml_x; op->npml_y = npml_y; op->pol = pol; op->averaging = 1;
+    FDFD_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+    size_t n = op->n();
+    FDFD_CHECK(cudaMalloc(&op->isxf, sizeof(cplx) * nx));
+    FDFD_CHECK(cudaMalloc(&op->isxb, sizeof(cplx) * nx));
+    FDFD_CHECK(cudaMalloc(&op->isyf, sizeof(cplx) * ny));
+    FDFD_CHECK(cudaMalloc(&op->isyb, sizeof(cplx) * ny));
+    FDFD_CHECK(cudaMalloc(&op->eps_r, sizeof(cplx) * n));
+    FDFD_CHECK(cudaMalloc(&op->eps_nl, sizeof(cplx) * n));
+    FDFD_CHECK(cudaMalloc(&op->planes, sizeof(cplx) * n * 5));
+    AsmParams p = make_params(op);
+    pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0);
+    pml_axis_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->isyf, op->isyb, ny, npml_y, p.dy, omega, L0);
+    FDFD_CHECK(cudaGetLastError());
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    *out = op;
+    return 0;
+}
+
+void op_destroy(FdfdOp* op) {
+    if (!op) return;
+    cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
+    cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
+    cudaStreamDestroy(op->stream);
+    delete op;
+}
+
+int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging) {
+    size_t n = op->n();
+    op->averaging = averaging;
+    op->has_nl = d_eps_nl != nullptr;
+    if (d_eps_r != op->eps_r)
+        FDFD_CHECK(cudaMemcpyAsync(op->eps_r, d_eps_r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
+    if (d_eps_nl && d_eps_nl != op->eps_nl)
+        FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, d_eps_nl, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
+    AsmParams p = make_params(op);
+    assemble_planes_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(
+        op->planes, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, p);
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
+    dim3 grid(ceil_div(op->n(), 256), nvec);
+    stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny);
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
+    dim3 grid(ceil_div(op->n(), 256), nvec);
+    stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny);
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
+    if (op->pol != 0) return op_apply_planes(op, d_x, d_y, nvec);
+    AsmParams p = make_params(op);
+    dim3 grid(ceil_div(op->ny, 128), ceil_div(op->nx, FUSED_ROWS), nvec);
+    stencil_fused_ez_kernel<<<grid, 128, 0, op->stream>>>(
+        op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, d_x, d_y,
+        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0);
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2) {
+    AsmParams p = make_params(op);
+    derive_fields_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(
+        d_x, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxb, op->isyb, d_f1, d_f2, p);
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,38 @@
+// Device-resident Maxwell operator: sc-PML factors, stencil planes, matrix-free apply.
+#pragma once
+#include "common.cuh"
+
+// fdfdpy/constants.py:3-6
+#define FDFD_EPS0 8.85418782e-12
+#define FDFD_MU0 1.25663706e-6
+
+struct FdfdOp {
+    int nx, ny;
+    double omega, dl, L0;
+    int npml_x, npml_y;
+    int pol;            // 0 = Ez, 1 = Hz
+    int averaging;      // Hz edge averaging (linalg.py:68-73)
+    int has_nl;         // eps_nl present
+    cudaStream_t stream;
+    // 1-D inverse stretch factors 1/s (pml.py:63-76), device
+    cplx *isxf, *isxb, *isyf, *isyb;
+    // permittivity planes (device, nx*ny complex128)
+    cplx *eps_r, *eps_nl;
+    // five stencil planes c0,cxm,cxp,cym,cyp (device, 5*nx*ny)
+    cplx *planes;
+    size_t n() const { return (size_t)nx * ny; }
+};
+
+int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y,
+              int pol, double L0);
+void op_destroy(FdfdOp* op);
+// eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes
+int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging);
+// y = A x using the stored planes (any polarisation, nonlinearity included); nvec vectors back to back
+int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
+// y = A x recomputing the coefficients from eps and the 1-D PML factors (Ez hot path, 48 B/cell)
+int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
+// r = b - A x (planes), returns nothing; used by iterative refinement
+int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec);
+// in-plane fields from the solved transverse field (simulation.py:138-176)
+int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2);

@@ -1,0 +1,147 @@
+// Batched complex128 GEMM on the FP64 tensor pipe (DMMA, mma.sync m8n8k4 f64) for sm_100a.
+//
+//   C[b] (M x N)  =  C[b] - A[b] (M x K) * B[b] (K x N)      (mode 1, the Schur / sweep update)
+//   C[b]          =  A[b] * B[b]                              (mode 0)
+//
+// All matrices are row-major interleaved complex (re, im) with leading dimensions and 64-bit
+// batch strides.  A complex product is four real DMMA products; the tiles are split into real
+// and imaginary planes when they are staged in shared memory so every fragment load is a plain
+// conflict-free LDS.64 (leading dimensions are = 4 mod 16 doubles).
+//
+// Warp tile 16 (M) x 32 (N) complex; CTA = WM x WN warps.
+#pragma once
+#include "common.cuh"
+
+struct GemmBatch {
+    const cplx* A; long long sA; int lda;
+    const cplx* B; long long sB; int ldb;
+    cplx* C; long long sC; int ldc;
+    int M, N, K, batch;
+    int mode;   // 0: C = AB, 1: C -= AB
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32)
+zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
+    constexpr int BM = 16 * WM, BN = 32 * WN, BK = 16, NT = WM * WN * 32;
+    __shared__ double As_r[BM][BK + 4], As_i[BM][BK + 4];
+    __shared__ double Bs_r[BK][BN + 4], Bs_i[BK][BN + 4];
+
+    long long bid = blockIdx.x;
+    const int tn = (int)(bid % tiles_n);
+    bid /= tiles_n;
+    const int tm = (int)(bid % tiles_m);
+    const long long b = bid / tiles_m;
+    const cplx* __restrict__ A = g.A + b * g.sA;
+    const cplx* __restrict__ B = g.B + b * g.sB;
+    cplx* __restrict__ C = g.C + b * g.sC;
+    const int m_base = tm * BM, n_base = tn * BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp / WN, wn = warp % WN;
+    const int gq = lane >> 2, tq = lane & 3;
+
+    double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += NT) {
+            int r = i / BK, c = i % BK;
+            int gm = m_base + r, gk = k0 + c;
+            cplx v = make_double2(0.0, 0.0);
+            if (gm < g.M && gk < g.K) v = A[(size_t)gm * g.lda + gk];
+            As_r[r][c] = v.x;
+            As_i[r][c] = v.y;
+        }
+        for (int i = tid; i < BK * BN; i += NT) {
+            int r = i / BN, c = i % BN;
+            int gk = k0 + r, gn = n_base + c;
+            cplx v = make_double2(0.0, 0.0);
+            if (gk < g.K && gn < g.N) v = B[(size_t)gk * g.ldb + gn];
+            Bs_r[r][c] = v.x;
+            Bs_i[r][c] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double ar[2], ai[2], nai[2], br[4], bi[4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                int row = wm * 16 + mt * 8 + gq;
+                ar[mt] = As_r[row][kk + tq];
+                ai[mt] = As_i[row][kk + tq];
+                nai[mt] = -ai[mt];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int col = wn * 32 + nt * 8 + gq;
+                br[nt] = Bs_r[kk + tq][col];
+                bi[nt] = Bs_i[kk + tq][col];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], ar[mt], br[nt]);
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bi[nt]);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], ar[mt], bi[nt]);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], ai[mt], br[nt]);
+                }
+        }
+        __syncthreads();
+    }
+
+    // epilogue: each thread owns, per (mt, nt), two adjacent complex entries of one row
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        int row = m_base + wm * 16 + mt * 8 + gq;
+        if (row >= g.M) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            int col = n_base + wn * 32 + nt * 8 + 2 * tq;
+            cplx* p = C + (size_t)row * g.ldc + col;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (col + e < g.N) {
+                    cplx v = make_double2(cr[mt][nt][e], ci[mt][nt][e]);
+                    if (g.mode == 1) {
+                        cplx o = p[e];
+                        v = make_double2(o.x - v.x, o.y - v.y);
+                    }
+                    p[e] = v;
+                }
+            }
+        }
+    }
+}
+
+static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
+    if (g.M <= 32 && g.N <= 32) {
+        int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
+        long long blocks = (long long)tm * tn * g.batch;
+        zgemm_dmma_kernel<2, 1><<<(unsigned)blocks, 64, 0, stream>>>(g, tm, tn);
+    } else {
+        int tm = (g.M + 63) / 64, tn = (g.N + 63) / 64;
+        long long blocks = (long long)tm * tn * g.batch;
+        if (blocks > 2147483647LL) {
+            snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
+            return -1;
+        }
+        zgemm_dmma_kernel<4, 2><<<(unsigned)blocks, 256, 0, stream>>>(g, tm, tn);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}

@@ -1,0 +1,208 @@
+"""Host-side plan for the structured direct solver (nested dissection on the periodic grid).
+
+The reference hands ``A x = b`` to a general sparse LU (linalg.py:123-149, MKL Pardiso or
+SuperLU), which re-derives an elimination order from the sparsity pattern on every call.
+Here the pattern is known a priori -- a 5-point stencil on an Nx x Ny torus (the derivative
+operators wrap, derivatives.py:21-33) -- so the elimination tree is built geometrically:
+
+* the torus is cut by 2^ax vertical and 2^ay horizontal grid lines into leaf boxes that SHARE
+  their boundary lines;
+* every stencil entry is owned by exactly one leaf (half-open ownership, see ``leaf tables``),
+  so a box's local matrix is "fully summed" on its interior and partial on its ring;
+* a leaf eliminates its interior; each higher level merges boxes pairwise along x or y and
+  eliminates the shared line(s); the last merge along an axis also closes the periodic wrap.
+
+All boxes of a level have one of <= 4 shapes (interval lengths differ by at most one), so a
+level is ONE batch of equally padded dense fronts  [E | R]  (E = eliminated, R = ring kept).
+The plan only holds small per-shape index tables plus per-box (shape id, children, origin);
+it contains no matrix values and is reusable for every eps_r / omega on the same grid shape.
+
+This module is pure index bookkeeping (numpy, no arithmetic on field values).
+"""
+import numpy as np
+
+WMIN = 3          # smallest leaf interval (cells); leaves are WMIN..2*WMIN-1 cells wide
+
+
+def _halve(n, depth):
+    """Interval lengths after ``depth`` recursive floor/ceil halvings of n (all within 1)."""
+    sizes = [n]
+    for _ in range(depth):
+        nxt = []
+        for s in sizes:
+            nxt += [s // 2, s - s // 2]
+        sizes = nxt
+    return np.array(sizes, dtype=np.int64)
+
+
+def _depth_for(n, wmin):
+    if n < 4:
+        raise ValueError("direct solver needs at least 4 cells per axis, got {}".format(n))
+    d = 1
+    while (n >> (d + 1)) >= wmin:
+        d += 1
+    return d
+
+
+def _ring(w, h, xclosed, yclosed, nx, ny):
+    """Ordered ring node list (lx, ly) of a box w x h cells (closed axes span the whole circle)."""
+    pts = []
+    xs = range(nx) if xclosed else range(w + 1)
+    ys = range(ny) if yclosed else range(h + 1)
+    if not yclosed:
+        pts += [(x, 0) for x in xs]
+        pts += [(x, h) for x in xs]
+    if not xclosed:
+        yy = ys if yclosed else range(1, h)
+        pts += [(0, y) for y in yy]
+        pts += [(w, y) for y in yy]
+    return pts
+
+
+class Level:
+    """One batch of fronts.  Attribute names are the ones the C ABI takes (include/fdfd_b200.h)."""
+    pass
+
+
+def build_plan(nx, ny, wmin=WMIN):
+    """Return the list of levels, leaves first, root last."""
+    ax, ay = _depth_for(nx, wmin), _depth_for(ny, wmin)
+    levels = []
+
+    # ---------------- leaves ----------------
+    xs, ys = _halve(nx, ax), _halve(ny, ay)
+    x0 = np.concatenate([[0], np.cumsum(xs)[:-1]])
+    y0 = np.concatenate([[0], np.cumsum(ys)[:-1]])
+    px, py = len(xs), len(ys)
+    shapes = sorted({(int(w), int(h)) for w in set(xs) for h in set(ys)})
+    sid = {s: i for i, s in enumerate(shapes)}
+    lv = Level()
+    lv.kind = "leaf"
+    lv.px, lv.py, lv.nb = px, py, px * py
+    W, H = np.meshgrid(xs, ys, indexing="ij")
+    X0, Y0 = np.meshgrid(x0, y0, indexing="ij")
+    lv.cls = np.array([sid[(int(w), int(h))] for w, h in zip(W.ravel(), H.ravel())], dtype=np.int32)
+    lv.x0 = X0.ravel().astype(np.int32)
+    lv.y0 = Y0.ravel().astype(np.int32)
+    lv.k_cls = np.array([(w - 1) * (h - 1) for w, h in shapes], dtype=np.int32)
+    lv.m_cls = np.array([2 * w + 2 * h for w, h in shapes], dtype=np.int32)
+    lv.kmax, lv.mmax = int(lv.k_cls.max()), int(lv.m_cls.max())
+    lv.nmax = lv.kmax + lv.mmax
+    ncls = len(shapes)
+    lv.ncls = ncls
+    # leaf tables: per slot local coords, ownership and the slots of the +x / +y neighbours
+    lv.slot_lx = np.full((ncls, lv.nmax), -1, dtype=np.int32)
+    lv.slot_ly = np.full((ncls, lv.nmax), -1, dtype=np.int32)
+    lv.slot_right = np.full((ncls, lv.nmax), -1, dtype=np.int32)   # -1: slot does not own entries
+    lv.slot_up = np.full((ncls, lv.nmax), -1, dtype=np.int32)
+    rings = {}
+    for (w, h), c in sid.items():
+        interior = [(x, y) for x in range(1, w) for y in range(1, h)]
+        ring = _ring(w, h, False, False, nx, ny)
+        rings[(w, h)] = ring
+        pos = {p: i for i, p in enumerate(interior)}
+        pos.update({p: lv.kmax + i for i, p in enumerate(ring)})
+        assert len(pos) == (w + 1) * (h + 1)
+        for (x, y), s in pos.items():
+            lv.slot_lx[c, s], lv.slot_ly[c, s] = x, y
+            if x < w and y < h:                      # half-open ownership
+                lv.slot_right[c, s] = pos[(x + 1, y)]
+                lv.slot_up[c, s] = pos[(x, y + 1)]
+    levels.append(lv)
+
+    # ---------------- merges ----------------
+    dx, dy = ax, ay
+    cur_shapes, cur_sid, cur_rings = shapes, sid, rings      # children description
+    cur_xs, cur_ys = xs, ys
+    xclosed = yclosed = False
+    while dx > 0 or dy > 0:
+        wx = nx if xclosed else int(cur_xs.max())
+        wy = ny if yclosed else int(cur_ys.max())
+        axis = 0 if (dx > 0 and (dy == 0 or wx <= wy)) else 1
+        child_px, child_py = len(cur_xs), len(cur_ys)
+        if axis == 0:
+            dx -= 1
+            new_xs, new_ys = cur_xs[0::2] + cur_xs[1::2], cur_ys
+            closing = dx == 0
+        else:
+            dy -= 1
+            new_xs, new_ys = cur_xs, cur_ys[0::2] + cur_ys[1::2]
+            closing = dy == 0
+        npx, npy = len(new_xs), len(new_ys)
+        new_xclosed = xclosed or (axis == 0 and closing)
+        new_yclosed = yclosed or (axis == 1 and closing)
+
+        lv = Level()
+        lv.kind = "merge"
+        lv.axis = axis
+        lv.px, lv.py, lv.nb = npx, npy, npx * npy
+        I, J = np.meshgrid(np.arange(npx), np.arange(npy), indexing="ij")
+        if axis == 0:
+            c1 = (2 * I) * child_py + J
+            c2 = (2 * I + 1) * child_py + J
+            key = [(int(cur_xs[2 * i]), int(cur_xs[2 * i + 1]), int(cur_ys[j]))
+                   for i, j in zip(I.ravel(), J.ravel())]
+        else:
+            c1 = I * child_py + 2 * J
+            c2 = I * child_py + 2 * J + 1
+            key = [(int(cur_ys[2 * j]), int(cur_ys[2 * j + 1]), int(cur_xs[i]))
+                   for i, j in zip(I.ravel(), J.ravel())]
+        lv.ch1 = c1.ravel().astype(np.int32)
+        lv.ch2 = c2.ravel().astype(np.int32)
+        pshapes = sorted(set(key))
+        psid = {s: i for i, s in enumerate(pshapes)}
+        lv.cls = np.array([psid[k] for k in key], dtype=np.int32)
+        lv.ncls = len(pshapes)
+
+        fronts = []
+        new_rings, new_sid_shapes = {}, []
+        for (a1, a2, other) in pshapes:
+            if axis == 0:
+                s1, s2 = (a1, other), (a2, other)
+                pw, ph = a1 + a2, other
+            else:
+                s1, s2 = (other, a1), (other, a2)
+                pw, ph = other, a1 + a2
+            r1, r2 = cur_rings[s1], cur_rings[s2]
+            if axis == 0:
+                mod = nx if new_xclosed else None
+                p1 = [(x, y) for x, y in r1]
+                p2 = [((x + a1) % mod if mod else x + a1, y) for x, y in r2]
+            else:
+                mod = ny if new_yclosed else None
+                p1 = [(x, y) for x, y in r1]
+                p2 = [(x, (y + a1) % mod if mod else y + a1) for x, y in r2]
+            pring = _ring(pw, ph, new_xclosed, new_yclosed, nx, ny)
+            pset = set(pring)
+            union = set(p1) | set(p2)
+            assert pset <= union
+            elim = sorted(union - pset)
+            fronts.append((elim, pring, p1, p2))
+            new_rings[(pw, ph)] = pring
+        lv.k_cls = np.array([len(f[0]) for f in fronts], dtype=np.int32)
+        lv.m_cls = np.array([len(f[1]) for f in fronts], dtype=np.int32)
+        lv.kmax, lv.mmax = int(lv.k_cls.max()), int(lv.m_cls.max())
+        lv.nmax = lv.kmax + lv.mmax
+        child_mmax = levels[-1].mmax
+        lv.child_mmax = child_mmax
+        lv.c1map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
+        lv.c2map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
+        for c, (elim, pring, p1, p2) in enumerate(fronts):
+            pos = {p: i for i, p in enumerate(elim)}
+            pos.update({p: lv.kmax + i for i, p in enumerate(pring)})
+            lv.c1map[c, :len(p1)] = [pos[p] for p in p1]
+            lv.c2map[c, :len(p2)] = [pos[p] for p in p2]
+        levels.append(lv)
+        cur_rings = new_rings
+        cur_xs, cur_ys = new_xs, new_ys
+        xclosed, yclosed = new_xclosed, new_yclosed
+    assert levels[-1].nb == 1 and levels[-1].mmax == 0
+    return levels
+
+
+def plan_stats(levels):
+    """(stored factor entries, peak transient front entries, complex MACs of the blocked sweep)."""
+    stored = sum(lv.nb * (lv.kmax * lv.nmax + lv.mmax * lv.kmax) for lv in levels)
+    transient = max(lv.nb * lv.nmax * lv.nmax for lv in levels)
+    macs = sum(lv.nb * lv.kmax * lv.nmax * lv.nmax for lv in levels)
+    return stored, transient, macs

@@ -1,0 +1,115 @@
+/* fdfd_b200.h -- C ABI of the B200-native fdfdpy hot path (libfdfd_b200.so).
+ *
+ * Plain pointers and sizes only; complex numbers are interleaved (re, im) doubles, i.e. numpy
+ * complex128 / C99 double _Complex.  Every function returns 0 on success and -1 on failure;
+ * fdfd_last_error() then holds a message (thread local).  "host" pointers are ordinary CPU
+ * memory (copied in/out inside the call); "dev" pointers are CUDA device pointers of the current
+ * device (zero-copy; e.g. torch.Tensor.data_ptr()).  Fields are (Nx, Ny) C-ordered, y fastest.
+ *
+ * Each entry point names the reference interface it replaces (fancompute/fdfdpy, file:line).
+ */
+#ifndef FDFD_B200_H
+#define FDFD_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct FdfdOp fdfd_op;         /* the Maxwell operator A on the device               */
+typedef struct NdSolver fdfd_direct;   /* structured direct solver: plan + cached factorisation */
+
+int fdfd_version(void);
+const char* fdfd_last_error(void);
+/* device bookkeeping helpers used by the Python host and the benchmark */
+int fdfd_device_count(int* count);
+int fdfd_set_device(int device);
+int fdfd_mem_info(double* free_bytes, double* total_bytes);
+int fdfd_malloc(void** dev_ptr, double bytes);
+int fdfd_free(void* dev_ptr);
+int fdfd_memcpy_h2d(void* dev, const void* host, double bytes);
+int fdfd_memcpy_d2h(void* host, const void* dev, double bytes);
+int fdfd_op_sync(fdfd_op* op);
+
+/* ---- operator: replaces linalg.py:39 construct_A, pml.py:44 S_create, derivatives.py:7 createDws.
+ * pol: 0 = 'Ez', 1 = 'Hz'.  The sc-PML inverse stretch factors are computed on the device at
+ * creation; fdfd_op_assemble_* builds the five stencil planes of
+ *   A = Dxf mu^-1 Dxb + Dyf mu^-1 Dyb + w^2 eps            (Ez, linalg.py:61-63)
+ *   A = Dxf ex^-1 Dxb + Dyf ey^-1 Dyb + w^2 mu             (Hz, linalg.py:96-98)
+ * eps_nl (may be NULL) adds the Kerr diagonal Anl of simulation.py:68-70.                         */
+int fdfd_op_create(fdfd_op** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y,
+                   int pol, double L0);
+void fdfd_op_destroy(fdfd_op* op);
+int fdfd_op_assemble_host(fdfd_op* op, const double* eps_r_c128, const double* eps_nl_c128, int averaging);
+int fdfd_op_assemble_dev(fdfd_op* op, const void* d_eps_r, const void* d_eps_nl, int averaging);
+/* inverse stretch factors 1/s as four 1-D complex arrays (lengths nx, nx, ny, ny): pml.py:63-76 */
+int fdfd_op_get_sfactors_host(fdfd_op* op, double* isxf, double* isxb, double* isyf, double* isyb);
+/* the five planes c0,cxm,cxp,cym,cyp (5*nx*ny complex) for export of A as a sparse matrix */
+int fdfd_op_get_planes_host(fdfd_op* op, double* planes_c128);
+/* y = A x (replaces the scipy A.dot(x) calls, e.g. nonlinear_solvers.py:127). fused != 0 selects the
+ * matrix-free Ez kernel that rebuilds the coefficients from eps and the PML factors.            */
+int fdfd_op_apply_host(fdfd_op* op, const double* x_c128, double* y_c128, int nvec, int fused);
+int fdfd_op_apply_dev(fdfd_op* op, const void* d_x, void* d_y, int nvec, int fused);
+/* in-plane fields from the transverse one: simulation.py:138-176 (Hx,Hy | Ex,Ey)               */
+int fdfd_op_derive_fields_host(fdfd_op* op, const double* x_c128, double* f1_c128, double* f2_c128);
+int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2);
+
+/* ---- direct solver: replaces linalg.py:123 solver_direct (pyMKL pardisoSolver factor/solve,
+ * scipy spsolve).  The elimination plan comes from fdfdpy_b200/ndplan.py, one call per level. */
+typedef struct {
+    int kind;              /* 0 leaf, 1 merge */
+    int nb, kmax, mmax, ncls, child_mmax;
+    const int* cls;        /* [nb]   shape class of every front */
+    const int* k_cls;      /* [ncls] number of real pivots per class */
+    const int* ch1;        /* [nb]   merge: first child front  */
+    const int* ch2;        /* [nb]   merge: second child front */
+    const int* c1map;      /* [ncls][child_mmax] merge: child ring position -> front slot (-1 pad) */
+    const int* c2map;
+    const int* x0;         /* [nb]   leaf: box origin */
+    const int* y0;
+    const int* slot_lx;    /* [ncls][kmax+mmax] leaf: slot -> local coordinates (-1 pad) */
+    const int* slot_ly;
+    const int* slot_right; /* leaf: slot of the +x neighbour if this slot owns its entries, else -1 */
+    const int* slot_up;
+} fdfd_level_desc;
+
+int fdfd_direct_create(fdfd_direct** out, int nx, int ny, int tile);
+int fdfd_direct_add_level(fdfd_direct* s, const fdfd_level_desc* level);
+void fdfd_direct_destroy(fdfd_direct* s);
+/* numeric factorisation of the operator's current planes; cached inside the handle and reused by
+ * every later solve (the README "save the factorization of A" to-do).                           */
+int fdfd_direct_factor(fdfd_direct* s, fdfd_op* op);
+int fdfd_direct_stats(fdfd_direct* s, double* factor_bytes, double* factor_flops);
+/* x = A^-1 b for nrhs right-hand sides [nrhs][nx*ny], followed by up to max_refine steps of
+ * iterative refinement with the fp64 stencil residual; relres = max_j ||b_j - A x_j|| / ||b_j||. */
+int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b_c128, double* x_c128, int nrhs,
+                           int max_refine, double tol, double* relres, int* refine_steps);
+int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_x, int nrhs,
+                          int max_refine, double tol, double* relres, int* refine_steps);
+
+/* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
+ * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).
+ * method: 0 = BiCGSTAB, 1 = COCG on the symmetrised operator.  precond may be NULL; when given
+ * (BiCGSTAB only) its cached factorisation is the right preconditioner.                         */
+int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b_c128, double* x_c128,
+                           int method, double tol, int maxiter, int fused, int check_every,
+                           int* iters, double* relres, int* converged);
+int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, void* d_x, int method,
+                          double tol, int maxiter, int fused, int check_every, int* iters,
+                          double* relres, int* converged);
+
+/* ---- modal source: replaces source/mode.py:64-108 insert_mode's eigensolve (linalg.py:104
+ * solver_eigs -> ARPACK shift-invert).  eps_line: n real relative permittivities along the
+ * source plane; averaged != 0 applies the edge average of mode.py:82 (planes normal to y).
+ * Returns the `order` eigenpairs of the 1-D waveguide operator closest to
+ * (omega sqrt(mu0' eps0') neff)^2: vals[order], vecs[order][n] (unit 2-norm, real).              */
+int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl, int pol, double L0,
+                         double neff, int order, int averaged, double* vals, double* vecs);
+
+/* ---- test hook for the batched complex GEMM that carries the factorisation (zgemm.cuh):
+ * C[b] = A[b] B[b] (mode 0) or C[b] -= A[b] B[b] (mode 1); packed row-major batches on the host. */
+int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, int N, int K, int batch,
+                            int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,191 @@
+"""GPU parity tests of the C-ABI building blocks against the CPU oracle and the golden vectors.
+
+Tolerances: the path is fp64; element-wise operator parity is held to 1e-13 relative, solved
+fields to <= 1e-8 relative L2 (north-star bound) -- in practice they land near 1e-12.
+"""
+import numpy as np
+import pytest
+
+from oracle import fdfd_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+OMEGA = 2 * np.pi * 200e12
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def core():
+    from fdfdpy_b200 import core
+    return core
+
+
+def test_zgemm_hook():
+    from fdfdpy_b200 import _lib
+    lib = _lib.load()
+    _lib.require_gpu()
+    rng = np.random.default_rng(0)
+    for (M, N, K, batch) in [(25, 25, 9, 7), (64, 64, 32, 3), (70, 130, 17, 2), (200, 96, 64, 1), (13, 40, 5, 11)]:
+        A = rng.standard_normal((batch, M, K)) + 1j * rng.standard_normal((batch, M, K))
+        B = rng.standard_normal((batch, K, N)) + 1j * rng.standard_normal((batch, K, N))
+        C0 = rng.standard_normal((batch, M, N)) + 1j * rng.standard_normal((batch, M, N))
+        for mode in (0, 1):
+            C = C0.copy()
+            _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, batch, mode))
+            ref = A @ B if mode == 0 else C0 - A @ B
+            assert relerr(C, ref) < 1e-14, (M, N, K, batch, mode)
+
+
+def test_operator_parity_golden(core, golden):
+    g = golden("operator")
+    for tag in "abc":
+        eps = g[tag + "_eps"]
+        omega, dl, L0, npx, npy = g[tag + "_meta"]
+        npml = [int(npx), int(npy)]
+        for pol in ("Ez", "Hz"):
+            op = core.MaxwellOperator(omega, eps, dl, npml, pol, L0)
+            for mine, k in zip(op.sfactors(), ("isxf", "isxb", "isyf", "isyb")):
+                np.testing.assert_allclose(mine, g[f"{tag}_{k}"], rtol=1e-13)
+            planes = op.planes()
+            ref = orc.stencil_planes(omega, eps, dl, npml, pol, L0)
+            for p, r in zip(planes, ref):
+                assert np.abs(p - r).max() <= 1e-13 * np.abs(ref[0]).max(), (tag, pol)
+            # against the reference's own CSR matrix
+            import scipy.sparse as sp
+            n = eps.size
+            Aref = sp.csr_matrix((g[f"{tag}_{pol}_A_data"], g[f"{tag}_{pol}_A_indices"], g[f"{tag}_{pol}_A_indptr"]),
+                                 shape=(n, n))
+            d = op.to_scipy() - Aref
+            assert abs(d).max() <= 1e-13 * abs(Aref).max()
+            u = np.random.default_rng(3).standard_normal(eps.shape) + 1j * np.random.default_rng(4).standard_normal(eps.shape)
+            ref_y = Aref.dot(u.reshape(-1)).reshape(eps.shape)
+            assert relerr(op.dot(u), ref_y) < 1e-14
+            if pol == "Ez":
+                assert relerr(op.dot(u, fused=True), ref_y) < 1e-13
+
+
+def test_apply_multivector_and_nl(core):
+    rng = np.random.default_rng(5)
+    nx, ny = 70, 45
+    eps = 1 + 3 * rng.random((nx, ny))
+    eps_nl = 0.1 * rng.random((nx, ny))
+    op = core.MaxwellOperator(OMEGA, eps, 0.03, [6, 5], "Ez", 1e-6, eps_nl=eps_nl)
+    planes = orc.stencil_planes(OMEGA, eps, 0.03, [6, 5], "Ez", 1e-6, eps_nl=eps_nl)
+    U = rng.standard_normal((3, nx, ny)) + 1j * rng.standard_normal((3, nx, ny))
+    ref = np.stack([orc.apply_planes(planes, u) for u in U])
+    assert relerr(op.dot(U), ref) < 1e-14
+    assert relerr(op.dot(U, fused=True), ref) < 1e-13
+
+
+@pytest.mark.parametrize("shape,npml", [((16, 16), [3, 3]), ((23, 17), [4, 3]), ((64, 48), [8, 6]),
+                                        ((37, 90), [0, 7]), ((130, 75), [10, 10])])
+@pytest.mark.parametrize("pol", ["Ez", "Hz"])
+def test_direct_solver_vs_oracle(core, shape, npml, pol):
+    rng = np.random.default_rng(11)
+    nx, ny = shape
+    eps = 1 + 5 * rng.random((nx, ny))
+    op = core.MaxwellOperator(OMEGA, eps, 0.04, npml, pol, 1e-6)
+    b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+    d = op.direct()
+    x0 = d.solve(b, max_refine=0)                      # raw substitution, no refinement
+    A = orc.construct_A(OMEGA, eps, 0.04, npml, pol, 1e-6)
+    ref = orc.sparse_solve(A, b).reshape(nx, ny)
+    assert relerr(x0, ref) < 1e-9, "unrefined"
+    x = d.solve(b, max_refine=3, tol=1e-13)
+    assert d.last_relres < 1e-11
+    assert relerr(x, ref) < 1e-10
+
+
+def test_direct_multi_rhs_reuses_factorisation(core):
+    rng = np.random.default_rng(12)
+    nx, ny = 48, 52
+    eps = 1 + 5 * rng.random((nx, ny))
+    op = core.MaxwellOperator(OMEGA, eps, 0.04, [6, 6], "Hz", 1e-6)
+    d = op.direct()
+    d.factor()
+    B = rng.standard_normal((11, nx, ny)) + 1j * rng.standard_normal((11, nx, ny))
+    X = d.solve(B)
+    A = orc.construct_A(OMEGA, eps, 0.04, [6, 6], "Hz", 1e-6)
+    for j in range(11):
+        ref = orc.sparse_solve(A, B[j]).reshape(nx, ny)
+        assert relerr(X[j], ref) < 1e-10, j
+    # zero right-hand side gives zeros (linalg.py:129-130)
+    assert not d.solve(np.zeros((nx, ny))).any()
+
+
+def test_config0_dipole_golden(core, golden):
+    g = golden("config0_dipole")
+    omega, dl, L0, npx, npy = g["meta"]
+    op = core.MaxwellOperator(omega, g["eps"], dl, [int(npx), int(npy)], "Ez", L0)
+    src = np.zeros((200, 200))
+    src[100, 100] = 1
+    ez = op.solve(src * 1j * omega).reshape(200, 200)
+    assert relerr(ez, g["ez"]) < 1e-8
+    hx, hy = op.derive_fields(ez)
+    assert relerr(hx[::10, ::10], g["hx_probe"]) < 1e-8
+    assert relerr(hy[::10, ::10], g["hy_probe"]) < 1e-8
+
+
+def test_derived_fields_hz(core, golden):
+    g = golden("linear_small")
+    omega, dl, L0, npx, npy = g["Hz_meta"]
+    op = core.MaxwellOperator(omega, g["Hz_eps"], dl, [int(npx), int(npy)], "Hz", L0)
+    hz = op.solve(g["Hz_src"] * 1j * omega).reshape(g["Hz_eps"].shape)
+    assert relerr(hz, g["Hz_fz"]) < 1e-8
+    ex, ey = op.derive_fields(hz)
+    assert relerr(ex, g["Hz_f1"]) < 1e-8
+    assert relerr(ey, g["Hz_f2"]) < 1e-8
+
+
+def test_krylov_small(core):
+    rng = np.random.default_rng(13)
+    nx, ny = 40, 36
+    eps = 1 + 2 * rng.random((nx, ny))
+    npml = [8, 8]
+    op = core.MaxwellOperator(OMEGA, eps, 0.05, npml, "Ez", 1e-6)
+    b = np.zeros((nx, ny), dtype=complex)
+    b[20, 18] = 1j * OMEGA
+    A = orc.construct_A(OMEGA, eps, 0.05, npml, "Ez", 1e-6)
+    ref = orc.sparse_solve(A, b).reshape(nx, ny)
+    x, info = op.krylov(b, method="bicgstab", tol=1e-11, maxiter=20000, check_every=20)
+    assert info["relres"] < 1e-9, info
+    assert relerr(x, ref) < 1e-6
+    x, info = op.krylov(b, method="cocg", tol=1e-11, maxiter=20000, check_every=20)
+    assert info["relres"] < 1e-8, info
+    assert relerr(x, ref) < 1e-6
+    # preconditioned by the cached factorisation of a PERTURBED operator: few iterations
+    op2 = core.MaxwellOperator(OMEGA, eps, 0.05, npml, "Ez", 1e-6)
+    op2.direct().factor()
+    op2_lib_handle = op2.direct()
+    eps_pert = eps * (1 + 1e-3 * rng.random((nx, ny)))
+    # keep the old factors, change only the planes
+    from fdfdpy_b200._lib import check, ptr, as_c128
+    check(op2.lib.fdfd_op_assemble_host(op2.h, ptr(as_c128(eps_pert)), None, 1))
+    op2_lib_handle.factored = True
+    x, info = op2.krylov(b, method="bicgstab", tol=1e-12, maxiter=50, check_every=1, precondition=True)
+    A2 = orc.construct_A(OMEGA, eps_pert, 0.05, npml, "Ez", 1e-6)
+    ref2 = orc.sparse_solve(A2, b).reshape(nx, ny)
+    assert info["iters"] <= 10, info
+    assert relerr(x, ref2) < 1e-9
+
+
+def test_mode_solve_golden(core, golden):
+    g = golden("mode_source")
+    omega, dl, L0, npx, npy = g["meta"]
+    eps, epsT = g["eps"], g["epsT"]
+
+    def up_to_sign(a, b):
+        return min(relerr(a, b), relerr(-a, b))
+
+    for pol in ("Ez", "Hz"):
+        vals, vecs = core.mode_solve(eps[15, 10:40], omega, dl, pol, L0, 3.5, order=1, averaged=False)
+        ref, refval = orc.mode_profile(eps[15, 10:40], omega, dl, pol, L0, 3.5, direction_normal='x')
+        assert abs(vals[0] - refval.real) < 1e-10 * abs(refval), pol
+        assert up_to_sign(vecs[0], ref) < 1e-8, pol
+        assert up_to_sign(vecs[0], g[pol + "_src"][15, 10:40]) < 1e-8, pol
+        vals, vecs = core.mode_solve(epsT[8:52, 15], omega, dl, pol, L0, 3.5, order=2, averaged=True)
+        assert up_to_sign(2 * vecs[1], g[pol + "_srcT"][8:52, 15]) < 1e-8, pol
