@@ -47,8 +47,8 @@ SIGNATURES = {
     "fdfd_op_get_planes_host": (C.c_int, [_vp, _vp]),
     "fdfd_op_apply_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "fdfd_op_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
-    "fdfd_op_derive_fields_host": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "fdfd_op_derive_fields_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fdfd_op_derive_fields_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "fdfd_op_derive_fields_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "fdfd_direct_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
     "fdfd_direct_add_level": (C.c_int, [_vp, C.POINTER(LevelDesc)]),
     "fdfd_direct_destroy": (None, [_vp]),
@@ -57,9 +57,9 @@ SIGNATURES = {
     "fdfd_direct_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
     "fdfd_direct_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
     "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
-                                         _ip, _dp, _ip]),
+                                         _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
-                                        _ip, _dp, _ip]),
+                                        _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fdfd_mode_solve_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                        C.c_int, C.c_int, _vp, _vp]),

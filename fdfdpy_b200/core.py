@@ -46,6 +46,7 @@ class MaxwellOperator:
         check(self.lib.fdfd_op_create(C.byref(self.h), self.nx, self.ny, self.omega, self.dl, self.NPML[0],
                                       self.NPML[1], POL[pol], self.L0))
         self._direct = None
+        self.preconditioner = None      # optional DirectSolver of a nearby operator (same grid)
         self.assemble(eps_r, eps_nl, averaging)
 
     def assemble(self, eps_r, eps_nl=None, averaging=True):
@@ -97,10 +98,12 @@ class MaxwellOperator:
         A = sp.coo_matrix((vals, (np.tile(row, 5), np.concatenate(cols))), shape=self.shape)
         return A.asformat(matrix_format)
 
-    def derive_fields(self, X):
+    def derive_fields(self, X, averaging=None):
+        """In-plane fields; ``averaging`` overrides the operator's Hz edge-averaging flag."""
         X = as_c128(X)
         f1, f2 = np.empty_like(X), np.empty_like(X)
-        check(self.lib.fdfd_op_derive_fields_host(self.h, ptr(X), ptr(f1), ptr(f2)))
+        av = -1 if averaging is None else int(bool(averaging))
+        check(self.lib.fdfd_op_derive_fields_host(self.h, ptr(X), ptr(f1), ptr(f2), av))
         return f1.reshape(self.nx, self.ny), f2.reshape(self.nx, self.ny)
 
     # ---- solvers
@@ -114,19 +117,24 @@ class MaxwellOperator:
         return self.direct().solve(b, max_refine=max_refine, tol=tol)
 
     def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10,
-               precondition=False):
+               precondition=False, c12=None, real_inner=False):
+        """Krylov solve of A x (+ c12 conj(x)) = b.  ``precondition=True`` uses whatever factorisation
+        the direct-solver handle currently caches (it may belong to a nearby operator)."""
         b = as_c128(b)
         x = np.zeros_like(b) if x0 is None else as_c128(x0).copy()
         it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
         pre = None
         if precondition:
-            d = self.direct()
-            if not d.factored:
+            d = self.preconditioner if self.preconditioner is not None else self.direct()
+            if not d.has_factors:
                 d.factor()
             pre = d.h
+        c12a = None if c12 is None else as_c128(c12)
+        if self.has_nl and fused and self.pol != "Ez":
+            fused = False
         check(self.lib.fdfd_krylov_solve_host(self.h, pre, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
-                                              float(tol), int(maxiter), int(fused), int(check_every),
-                                              C.byref(it), C.byref(rr), C.byref(conv)))
+                                              float(tol), int(maxiter), int(fused), int(check_every), ptr(c12a),
+                                              int(bool(real_inner)), C.byref(it), C.byref(rr), C.byref(conv)))
         return x.reshape(b.shape), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
 
 
@@ -153,7 +161,8 @@ class DirectSolver:
                 setattr(d, nme, arr.ctypes.data_as(C.POINTER(C.c_int)))
             check(self.lib.fdfd_direct_add_level(self.h, C.byref(d)))
         del keep
-        self.factored = False
+        self.factored = False       # cached factors belong to the operator's CURRENT planes
+        self.has_factors = False    # some factorisation is cached (possibly of an earlier operator state)
         self.last_relres = None
         self.last_refine_steps = None
 
@@ -168,6 +177,7 @@ class DirectSolver:
     def factor(self):
         check(self.lib.fdfd_direct_factor(self.h, self.op.h))
         self.factored = True
+        self.has_factors = True
 
     def stats(self):
         fb, ff = C.c_double(0), C.c_double(0)

@@ -88,15 +88,15 @@ int fdfd_op_apply_host(fdfd_op* op, const double* x, double* y, int nvec, int fu
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     return 0;
 }
-int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2) {
-    return op_derive_fields(op, (const cplx*)d_x, (cplx*)d_f1, (cplx*)d_f2);
+int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2, int averaging) {
+    return op_derive_fields(op, (const cplx*)d_x, (cplx*)d_f1, (cplx*)d_f2, averaging);
 }
-int fdfd_op_derive_fields_host(fdfd_op* op, const double* x, double* f1, double* f2) {
+int fdfd_op_derive_fields_host(fdfd_op* op, const double* x, double* f1, double* f2, int averaging) {
     size_t n = op->n();
     DevBuf buf;
     if (buf.alloc(3 * n)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(buf.p, x, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
-    if (op_derive_fields(op, buf.p, buf.p + n, buf.p + 2 * n)) return -1;
+    if (op_derive_fields(op, buf.p, buf.p + n, buf.p + 2 * n, averaging)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(f1, buf.p + n, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
     FDFD_CHECK(cudaMemcpyAsync(f2, buf.p + 2 * n, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
@@ -145,12 +145,15 @@ int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b, double*
 }
 
 int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, void* d_x, int method, double tol,
-                          int maxiter, int fused, int check_every, int* iters, double* relres, int* converged) {
+                          int maxiter, int fused, int check_every, const void* d_c12, int real_inner, int* iters,
+                          double* relres, int* converged) {
     KrylovResult r;
     int rc;
-    if (method == 0) rc = krylov_bicgstab(op, precond, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every, &r);
+    if (method == 0)
+        rc = krylov_bicgstab(op, precond, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every,
+                             (const cplx*)d_c12, real_inner, &r);
     else if (method == 1) {
-        if (precond) FDFD_FAIL("COCG does not take a preconditioner");
+        if (precond || d_c12) FDFD_FAIL("COCG takes neither a preconditioner nor an anti-linear term");
         rc = krylov_cocg(op, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every, &r);
     } else FDFD_FAIL("unknown Krylov method %d", method);
     if (rc) return -1;
@@ -161,14 +164,19 @@ int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, vo
     return 0;
 }
 int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b, double* x, int method, double tol,
-                           int maxiter, int fused, int check_every, int* iters, double* relres, int* converged) {
+                           int maxiter, int fused, int check_every, const double* c12, int real_inner, int* iters,
+                           double* relres, int* converged) {
     size_t n = op->n();
-    DevBuf db, dx;
+    DevBuf db, dx, dc;
     if (db.alloc(n) || dx.alloc(n)) return -1;
+    if (c12) {
+        if (dc.alloc(n)) return -1;
+        FDFD_CHECK(cudaMemcpyAsync(dc.p, c12, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
+    }
     FDFD_CHECK(cudaMemcpyAsync(db.p, b, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
     FDFD_CHECK(cudaMemcpyAsync(dx.p, x, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));   // initial guess
-    if (fdfd_krylov_solve_dev(op, precond, db.p, dx.p, method, tol, maxiter, fused, check_every, iters, relres,
-                              converged))
+    if (fdfd_krylov_solve_dev(op, precond, db.p, dx.p, method, tol, maxiter, fused, check_every, dc.p, real_inner,
+                              iters, relres, converged))
         return -1;
     FDFD_CHECK(cudaMemcpy(x, dx.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost));
     return 0;

@@ -34,7 +34,7 @@ dot_partial_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, size_
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__ out) {
+dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__ out, int real_only) {
     __shared__ double sx[RED_THREADS], sy[RED_THREADS];
     double ax = 0, ay = 0;
     for (int i = threadIdx.x; i < count; i += blockDim.x) { ax += partial[i].x; ay += partial[i].y; }
@@ -44,13 +44,14 @@ dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__
         if (threadIdx.x < s) { sx[threadIdx.x] += sx[threadIdx.x + s]; sy[threadIdx.x] += sy[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = make_double2(sx[0], sy[0]);
+    if (threadIdx.x == 0) *out = make_double2(sx[0], real_only ? 0.0 : sy[0]);
 }
 
-int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out) {
+int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
+            int real_only) {
     if (conj_a) dot_partial_kernel<true><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial);
     else dot_partial_kernel<false><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial);
-    dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out);
+    dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out, real_only);
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
@@ -141,12 +142,36 @@ static int host_scalar(cudaStream_t st, const cplx* d, cplx* h) {
     return 0;
 }
 
-static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused) {
-    return fused ? op_apply_fused(op, x, y, 1) : op_apply_planes(op, x, y, 1);
+// y (+)= c12 .* conj(x): the anti-linear part of the Newton Jacobian (nonlinear_solvers.py:134-135, Jac12)
+__global__ void conj_couple_kernel(cplx* __restrict__ y, const cplx* __restrict__ c12, const cplx* __restrict__ x,
+                                   size_t n, int subtract) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx t = cmul(c12[i], cconj(x[i]));
+    y[i] = subtract ? csub(y[i], t) : cadd(y[i], t);
+}
+
+static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cplx* c12) {
+    if (fused ? op_apply_fused(op, x, y, 1) : op_apply_planes(op, x, y, 1)) return -1;
+    if (c12) {
+        conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), 0);
+        FDFD_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int residual_A(const FdfdOp* op, const cplx* b, const cplx* x, cplx* r, const cplx* c12) {
+    if (op_residual(op, b, x, r, 1)) return -1;
+    if (c12) {
+        conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(r, c12, x, op->n(), 1);
+        FDFD_CHECK(cudaGetLastError());
+    }
+    return 0;
 }
 
 int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
-                    int fused, int check_every, KrylovResult* res) {
+                    int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
+    const int RI = (real_inner || c12) ? 1 : 0;   // an R-linear operator needs the real inner product
     const size_t n = op->n();
     cudaStream_t st = op->stream;
     const int nvec = precond ? 8 : 6;
@@ -160,14 +185,14 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
     cplx h;
     if (check_every < 1) check_every = 1;
     // r = b - A x
-    if (op_residual(op, d_b, d_x, r, 1)) return -1;
+    if (residual_A(op, d_b, d_x, r, c12)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(r0, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
     FDFD_CHECK(cudaMemsetAsync(p, 0, sizeof(cplx) * n, st));
     FDFD_CHECK(cudaMemsetAsync(v, 0, sizeof(cplx) * n, st));
     cplx init[S_COUNT];
     for (int i = 0; i < S_COUNT; ++i) init[i] = make_double2(1.0, 0.0);
     FDFD_CHECK(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR)) return -1;
+    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, RI)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
@@ -176,29 +201,29 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     if (res->relres <= tol) { res->converged = 1; return 0; }
     for (int it = 1; it <= maxiter; ++it) {
-        if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO)) return -1;
+        if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO, RI)) return -1;
         bicg_beta_kernel<<<1, 1, 0, st>>>(sc);
         bicg_p_kernel<<<nblk, 256, 0, st>>>(p, r, v, sc, n);
         if (precond) { if (nd_solve(precond, op, p, ph, 1)) return -1; }
-        if (apply_A(op, ph, v, fused)) return -1;
-        if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V)) return -1;
+        if (apply_A(op, ph, v, fused, c12)) return -1;
+        if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V, RI)) return -1;
         bicg_alpha_kernel<<<1, 1, 0, st>>>(sc);
         bicg_s_kernel<<<nblk, 256, 0, st>>>(s, r, v, sc, n);
         if (precond) { if (nd_solve(precond, op, s, sh, 1)) return -1; }
-        if (apply_A(op, sh, t, fused)) return -1;
-        if (dev_dot(st, t, s, n, true, partial, sc + S_TS)) return -1;
-        if (dev_dot(st, t, t, n, true, partial, sc + S_TT)) return -1;
+        if (apply_A(op, sh, t, fused, c12)) return -1;
+        if (dev_dot(st, t, s, n, true, partial, sc + S_TS, RI)) return -1;
+        if (dev_dot(st, t, t, n, true, partial, sc + S_TT, RI)) return -1;
         bicg_omega_kernel<<<1, 1, 0, st>>>(sc);
         bicg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, ph, sh, s, t, sc, n);
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_RR)) return -1;
+            if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
             if (host_scalar(st, sc + S_RR, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;           // NaN: breakdown
@@ -206,8 +231,8 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
         }
     }
     // report the TRUE residual of the returned iterate
-    if (op_residual(op, d_b, d_x, r, 1)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR)) return -1;
+    if (residual_A(op, d_b, d_x, r, c12)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     res->converged = res->relres <= tol * 10 ? res->converged : 0;
@@ -232,7 +257,7 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
     if (op_residual(op, d_b, d_x, r, 1)) return -1;
     sym_scale_kernel<<<nblk, 256, 0, st>>>(r, op->isxf, op->isyf, op->nx, op->ny);
     FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR)) return -1;
+    if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR, 0)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
@@ -241,20 +266,20 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, false, partial, sc + S_RHO)) return -1;
+    if (dev_dot(st, r, r, n, false, partial, sc + S_RHO, 0)) return -1;
     for (int it = 1; it <= maxiter; ++it) {
-        if (apply_A(op, p, q, fused)) return -1;
+        if (apply_A(op, p, q, fused, nullptr)) return -1;
         sym_scale_kernel<<<nblk, 256, 0, st>>>(q, op->isxf, op->isyf, op->nx, op->ny);
-        if (dev_dot(st, p, q, n, false, partial, sc + S_PQ)) return -1;
+        if (dev_dot(st, p, q, n, false, partial, sc + S_PQ, 0)) return -1;
         cocg_alpha_kernel<<<1, 1, 0, st>>>(sc);
         cocg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, p, q, sc, n);
-        if (dev_dot(st, r, r, n, false, partial, sc + S_RR)) return -1;
+        if (dev_dot(st, r, r, n, false, partial, sc + S_RR, 0)) return -1;
         cocg_beta_kernel<<<1, 1, 0, st>>>(sc);
         cocg_p_kernel<<<nblk, 256, 0, st>>>(p, r, sc, n);
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_TT)) return -1;
+            if (dev_dot(st, r, r, n, true, partial, sc + S_TT, 0)) return -1;
             if (host_scalar(st, sc + S_TT, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;
@@ -263,10 +288,10 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
     }
     // true residual in the ORIGINAL (unscaled) system
     if (op_residual(op, d_b, d_x, r, 1)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, 0)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     double rn = sqrt(h.x);
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR)) return -1;
+    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, 0)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = rn / sqrt(h.x);
     return 0;
@@ -282,7 +307,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
     std::vector<double> bn(nrhs);
     cplx h;
     for (int j = 0; j < nrhs; ++j) {
-        if (dev_dot(st, d_b + j * n, d_b + j * n, n, true, partial, sc)) return -1;
+        if (dev_dot(st, d_b + j * n, d_b + j * n, n, true, partial, sc, 0)) return -1;
         if (host_scalar(st, sc, &h)) return -1;
         bn[j] = sqrt(h.x);
     }
@@ -293,7 +318,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
         if (op_residual(op, d_b, d_x, r, nrhs)) return -1;
         worst = 0.0;
         for (int j = 0; j < nrhs; ++j) {
-            if (dev_dot(st, r + j * n, r + j * n, n, true, partial, sc)) return -1;
+            if (dev_dot(st, r + j * n, r + j * n, n, true, partial, sc, 0)) return -1;
             if (host_scalar(st, sc, &h)) return -1;
             double rel = bn[j] > 0 ? sqrt(h.x) / bn[j] : 0.0;
             if (!(rel == rel)) rel = 1e300;

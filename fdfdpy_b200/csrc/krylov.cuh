@@ -9,9 +9,10 @@ struct KrylovResult {
     double relres;     // ||b - A x|| / ||b|| of the returned iterate (true residual)
 };
 
-int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out);
+int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
+            int real_only);
 int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
-                    int fused, int check_every, KrylovResult* res);
+                    int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res);
 int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,
                 KrylovResult* res);
 int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs, int max_refine, double tol,

@@ -299,8 +299,9 @@ int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
     return 0;
 }
 
-int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2) {
+int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2, int averaging) {
     AsmParams p = make_params(op);
+    if (averaging >= 0) p.averaging = averaging;
     derive_fields_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(
         d_x, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxb, op->isyb, d_f1, d_f2, p);
     FDFD_CHECK(cudaGetLastError());

@@ -35,4 +35,4 @@ int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
 // r = b - A x (planes), returns nothing; used by iterative refinement
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec);
 // in-plane fields from the solved transverse field (simulation.py:138-176)
-int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2);
+int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2, int averaging);

@@ -48,9 +48,11 @@ int fdfd_op_get_planes_host(fdfd_op* op, double* planes_c128);
  * matrix-free Ez kernel that rebuilds the coefficients from eps and the PML factors.            */
 int fdfd_op_apply_host(fdfd_op* op, const double* x_c128, double* y_c128, int nvec, int fused);
 int fdfd_op_apply_dev(fdfd_op* op, const void* d_x, void* d_y, int nvec, int fused);
-/* in-plane fields from the transverse one: simulation.py:138-176 (Hx,Hy | Ex,Ey)               */
-int fdfd_op_derive_fields_host(fdfd_op* op, const double* x_c128, double* f1_c128, double* f2_c128);
-int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2);
+/* in-plane fields from the transverse one: simulation.py:138-176 (Hx,Hy | Ex,Ey).
+ * averaging: 1/0 = Hz edge averaging on/off (solve_fields' argument), -1 = as assembled.          */
+int fdfd_op_derive_fields_host(fdfd_op* op, const double* x_c128, double* f1_c128, double* f2_c128,
+                               int averaging);
+int fdfd_op_derive_fields_dev(fdfd_op* op, const void* d_x, void* d_f1, void* d_f2, int averaging);
 
 /* ---- direct solver: replaces linalg.py:123 solver_direct (pyMKL pardisoSolver factor/solve,
  * scipy spsolve).  The elimination plan comes from fdfdpy_b200/ndplan.py, one call per level. */
@@ -88,13 +90,18 @@ int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).
  * method: 0 = BiCGSTAB, 1 = COCG on the symmetrised operator.  precond may be NULL; when given
- * (BiCGSTAB only) its cached factorisation is the right preconditioner.                         */
+ * (BiCGSTAB only) its cached factorisation is the right preconditioner -- it may belong to a
+ * nearby operator (previous Born iterate, linear part of the Newton Jacobian).  c12 (may be NULL)
+ * adds the anti-linear term  c12 .* conj(x)  of the Newton Jacobian (nonlinear_solvers.py:134-135;
+ * replaces linalg.py:152 solver_complex2real): the system is then only R-linear and is solved with
+ * the real inner product, which real_inner != 0 also forces.  x holds the initial guess on entry. */
 int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b_c128, double* x_c128,
                            int method, double tol, int maxiter, int fused, int check_every,
-                           int* iters, double* relres, int* converged);
+                           const double* c12_c128, int real_inner, int* iters, double* relres,
+                           int* converged);
 int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, void* d_x, int method,
-                          double tol, int maxiter, int fused, int check_every, int* iters,
-                          double* relres, int* converged);
+                          double tol, int maxiter, int fused, int check_every, const void* d_c12,
+                          int real_inner, int* iters, double* relres, int* converged);
 
 /* ---- modal source: replaces source/mode.py:64-108 insert_mode's eigensolve (linalg.py:104
  * solver_eigs -> ARPACK shift-invert).  eps_line: n real relative permittivities along the

@@ -1,0 +1,92 @@
+"""CPU tests: input validation of the public API, the elimination plan (executed by a numpy model
+of the GPU algorithm against the oracle), the C-ABI symbol table, and the loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import fdfd_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_constructor_rejects_bad_inputs():
+    """tests/test_simulation.py of the reference, verbatim in intent: every bad argument -> ValueError."""
+    from fdfdpy_b200 import Simulation
+    good = dict(omega=100, eps_r=np.ones((100, 50)), dl=0.001, NPML=[10, 10], pol='Hz')
+
+    def build(**kw):
+        a = dict(good, **kw)
+        return Simulation(a['omega'], a['eps_r'], a['dl'], a['NPML'], a['pol'])
+
+    for bad in (dict(omega=-100), dict(omega=[100, 200, 300]), dict(eps_r=-np.ones((100, 50))),
+                dict(eps_r=list(np.ones((100, 50)))), dict(dl=-0.001), dict(dl=[1e-4, 1e-5]),
+                dict(NPML=10), dict(NPML=[10, 10, 10]), dict(NPML=[200, 200]), dict(pol=5),
+                dict(pol='WrongPolarization')):
+        with pytest.raises(ValueError):
+            build(**bad)
+    # the reference raises AssertionError for some of these (simulation.py:258-265): also accepted
+    with pytest.raises(AssertionError):
+        build(pol='TE')
+
+
+def test_no_gpu_fails_loudly():
+    from fdfdpy_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_int(0)
+    if lib.fdfd_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    from fdfdpy_b200 import Simulation
+    with pytest.raises(_lib.FdfdError):
+        Simulation(100, np.ones((20, 20)), 0.001, [3, 3], 'Ez')
+
+
+def test_cabi_exports_every_declared_symbol():
+    from fdfdpy_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "fdfd_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fdfd_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, "binding missing for " + name
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.fdfd_version() >= 100
+
+
+@pytest.mark.parametrize("shape,npml", [((16, 16), [3, 3]), ((23, 17), [4, 3]), ((37, 52), [0, 6]), ((8, 64), [2, 9])])
+@pytest.mark.parametrize("pol", ["Ez", "Hz"])
+def test_elimination_plan_numpy_model(shape, npml, pol):
+    """The plan executed the way the kernels do (padded fronts, blocked sweep, level-wise solve)."""
+    from fdfdpy_b200.ndplan import build_plan
+    from tests.nd_model import factor, solve
+    nx, ny = shape
+    rng = np.random.default_rng(0)
+    eps = 1 + 5 * rng.random((nx, ny))
+    omega = 2 * np.pi * 200e12
+    planes = orc.stencil_planes(omega, eps, 0.04, npml, pol, 1e-6)
+    levels = build_plan(nx, ny)
+    store = factor(levels, planes, nx, ny, tile=8)
+    b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+    u = solve(levels, store, b, nx, ny)
+    ref = orc.sparse_solve(orc.planes_to_csr(planes), b).reshape(nx, ny)
+    assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-11
+
+
+def test_plan_structure_invariants():
+    from fdfdpy_b200.ndplan import build_plan, plan_stats
+    for nx, ny in [(200, 200), (300, 100), (125, 87), (64, 1000)]:
+        levels = build_plan(nx, ny)
+        assert levels[0].kind == "leaf" and levels[-1].nb == 1 and levels[-1].mmax == 0
+        # every grid node is eliminated exactly once
+        total = sum(int(lv.k_cls[c]) for lv in levels for c in lv.cls)
+        assert total == nx * ny
+        for lv in levels[1:]:
+            assert lv.c1map.max() < lv.nmax and lv.c2map.max() < lv.nmax
+        stored, transient, macs = plan_stats(levels)
+        assert stored > 0 and transient > 0 and macs > 0
+    with pytest.raises(ValueError):
+        build_plan(3, 50)
