@@ -38,6 +38,14 @@ SIGNATURES = {
     "fdfd_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_double]),
     "fdfd_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_double]),
     "fdfd_op_sync": (C.c_int, [_vp]),
+    "fdfd_launch_count": (C.c_double, [C.c_int]),
+    "fdfd_timer_start": (C.c_int, [_vp]),
+    "fdfd_timer_stop": (C.c_int, [_vp, _dp]),
+    "fdfd_gemm_timing": (C.c_int, [C.c_int]),
+    "fdfd_gemm_timing_read": (C.c_int, [_vp]),
+    "fdfd_dmma_peak": (C.c_int, [_dp]),
+    "fdfd_host_register": (C.c_int, [_vp, C.c_double]),
+    "fdfd_host_unregister": (C.c_int, [_vp]),
     "fdfd_op_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.c_int, C.c_double]),
     "fdfd_op_destroy": (None, [_vp]),

@@ -16,7 +16,83 @@ struct DevBuf {
 };
 }  // namespace
 
+ZgemmTiming g_zgemm_timing;
+
+// register-resident DMMA loop: the practical FP64 tensor-pipe ceiling at the clocks the board runs at
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
 extern "C" {
+
+int fdfd_dmma_peak(double* tflops) {
+    double* d = nullptr;
+    FDFD_CHECK(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    const int iters = 4000, blocks = 148 * 4;
+    dmma_peak_kernel<<<blocks, 256>>>(d, 100);
+    FDFD_CHECK(cudaDeviceSynchronize());
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        FDFD_CHECK(cudaEventRecord(e0));
+        dmma_peak_kernel<<<blocks, 256>>>(d, iters);
+        FDFD_CHECK(cudaEventRecord(e1));
+        FDFD_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = (double)blocks * 8 /*warps*/ * iters * 16.0 * 512.0;   // 8x8x4 MACs x 2 per DMMA
+        best = fmax(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return 0;
+}
+
+int fdfd_gemm_timing(int enable) {
+    for (cudaEvent_t e : g_zgemm_timing.ev) cudaEventDestroy(e);
+    g_zgemm_timing.ev.clear(); g_zgemm_timing.flops.clear(); g_zgemm_timing.big.clear();
+    g_zgemm_timing.on = enable != 0;
+    return 0;
+}
+/* totals since fdfd_gemm_timing(1): out[0..2] = ms, real flops, launches of the 64x64-tile kernel;
+ * out[3..5] the same for the 32x32-tile kernel.  Synchronises the device. */
+int fdfd_gemm_timing_read(double* out) {
+    FDFD_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < 6; ++i) out[i] = 0;
+    for (size_t i = 0; i < g_zgemm_timing.flops.size(); ++i) {
+        float ms = 0;
+        FDFD_CHECK(cudaEventElapsedTime(&ms, g_zgemm_timing.ev[2 * i], g_zgemm_timing.ev[2 * i + 1]));
+        int o = g_zgemm_timing.big[i] ? 0 : 3;
+        out[o] += ms; out[o + 1] += g_zgemm_timing.flops[i]; out[o + 2] += 1;
+    }
+    return 0;
+}
+int fdfd_timer_start(fdfd_op* op) {
+    if (!op->ev0) { FDFD_CHECK(cudaEventCreate(&op->ev0)); FDFD_CHECK(cudaEventCreate(&op->ev1)); }
+    FDFD_CHECK(cudaEventRecord(op->ev0, op->stream));
+    return 0;
+}
+int fdfd_timer_stop(fdfd_op* op, double* ms) {
+    FDFD_CHECK(cudaEventRecord(op->ev1, op->stream));
+    FDFD_CHECK(cudaEventSynchronize(op->ev1));
+    float t = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&t, op->ev0, op->ev1));
+    *ms = t;
+    return 0;
+}
 
 int fdfd_version(void) { return 100; }
 const char* fdfd_last_error(void) { return g_fdfd_err; }
@@ -39,6 +115,16 @@ int fdfd_memcpy_d2h(void* host, const void* dev, double bytes) {
     FDFD_CHECK(cudaMemcpy(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
+double fdfd_launch_count(int reset) {
+    double v = (double)g_fdfd_launches;
+    if (reset) g_fdfd_launches = 0;
+    return v;
+}
+int fdfd_host_register(void* host, double bytes) {
+    FDFD_CHECK(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int fdfd_host_unregister(void* host) { FDFD_CHECK(cudaHostUnregister(host)); return 0; }
 int fdfd_op_sync(fdfd_op* op) { FDFD_CHECK(cudaStreamSynchronize(op->stream)); return 0; }
 
 int fdfd_op_create(fdfd_op** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol,

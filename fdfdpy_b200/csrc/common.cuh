@@ -9,6 +9,7 @@
 typedef double2 cplx;   // (re, im), layout-compatible with numpy complex128
 
 extern thread_local char g_fdfd_err[512];
+extern unsigned long long g_fdfd_launches;   // kernels launched by this library (bench bookkeeping)
 
 #define FDFD_CHECK(call)                                                                  \
     do {                                                                                  \

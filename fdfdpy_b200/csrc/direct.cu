@@ -469,14 +469,14 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         FDFD_CHECK(cudaMalloc(&Cbuf, sizeof(cplx) * nb * nmax * tcap));
         FDFD_CHECK(cudaMalloc(&Rbuf, sizeof(cplx) * nb * tcap * nmax));
         if (L.kind == 0) {
-            leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
+            { leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
                                                               L.slot_ly, L.slot_right, L.slot_up, kmax, nmax,
-                                                              s->nx, s->ny);
+                                                              s->nx, s->ny); ++g_fdfd_launches; }
         } else {
             int chunks = chunks_for((long long)nmax * nmax, nb);
-            merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
+            { merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
                                                                            L.inv1, L.inv2, kmax, nmax, prev_k,
-                                                                           prev_n, chunks);
+                                                                           prev_n, chunks); ++g_fdfd_launches; }
         }
         FDFD_CHECK(cudaGetLastError());
         for (int j0 = 0; j0 < kmax; j0 += tcap) {
@@ -486,9 +486,9 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
-            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
+            { pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info); ++g_fdfd_launches; }
             int chunks = chunks_for((long long)nmax * tw, nb);
-            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
+            { panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks); ++g_fdfd_launches; }
             FDFD_CHECK(cudaGetLastError());
             GemmBatch g;
             g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
@@ -496,7 +496,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             g.C = Rbuf; g.sC = (long long)tcap * nmax; g.ldc = nmax;
             g.M = tw; g.N = nmax; g.K = tw; g.batch = (int)nb; g.mode = 0;
             if (zgemm_batched(g, st)) return -1;
-            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
+            { copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks); ++g_fdfd_launches; }
             FDFD_CHECK(cudaGetLastError());
             g.A = Cbuf; g.sA = (long long)nmax * tcap; g.lda = tcap;
             g.B = Rbuf; g.sB = (long long)tcap * nmax; g.ldb = nmax;
@@ -510,7 +510,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * nmax + (size_t)nb * mmax * kmax);
         {
             int chunks = chunks_for((long long)kmax * nmax + (long long)mmax * kmax, nb);
-            extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks);
+            { extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks); ++g_fdfd_launches; }
             FDFD_CHECK(cudaGetLastError());
         }
         FDFD_CHECK(cudaStreamSynchronize(st));
@@ -564,13 +564,13 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         const long long nb = L.nb;
         long long tot = nb * L.nmax;
         if (L.kind == 0)
-            leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
-                                                                       L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb);
+            { leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
+                                                                       L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb); ++g_fdfd_launches; }
         else
-            merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
-                                                                        L.inv2, L.nmax, L.child_mmax, nb);
-        forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.EZX, L.RW, f, s->ws_ye + L.ye_off, ring_cur,
-                                                                       L.kmax, L.mmax, L.nmax, nb);
+            { merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
+                                                                        L.inv2, L.nmax, L.child_mmax, nb); ++g_fdfd_launches; }
+        { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.EZX, L.RW, f, s->ws_ye + L.ye_off, ring_cur,
+                                                                       L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         std::swap(ring_prev, ring_cur);
     }
@@ -583,15 +583,15 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         if (li + 1 < nlev) {
             NdLevel& P = s->levels[li + 1];
             long long tot = (long long)P.nb * 2 * P.child_mmax;
-            child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
-                                                                         P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb);
+            { child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
+                                                                         P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb); ++g_fdfd_launches; }
         }
-        backward_mv_kernel<NR><<<ceil_div(nb * L.kmax * 32, 256), 256, 0, st>>>(L.EZX, s->ws_ye + L.ye_off, u, L.kmax,
-                                                                                L.mmax, L.nmax, nb);
+        { backward_mv_kernel<NR><<<ceil_div(nb * L.kmax * 32, 256), 256, 0, st>>>(L.EZX, s->ws_ye + L.ye_off, u, L.kmax,
+                                                                                L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         if (L.kind == 0) {
             long long tot = nb * L.nmax;
-            leaf_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, d_x, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
-                                                                        L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb);
+            { leaf_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, d_x, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
+                                                                        L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb); ++g_fdfd_launches; }
         }
         FDFD_CHECK(cudaGetLastError());
         std::swap(u, u_par);

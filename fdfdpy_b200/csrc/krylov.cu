@@ -49,9 +49,9 @@ dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__
 
 int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
             int real_only) {
-    if (conj_a) dot_partial_kernel<true><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial);
-    else dot_partial_kernel<false><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial);
-    dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out, real_only);
+    if (conj_a) { dot_partial_kernel<true><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
+    else { dot_partial_kernel<false><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
+    { dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out, real_only); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
@@ -154,7 +154,7 @@ __global__ void conj_couple_kernel(cplx* __restrict__ y, const cplx* __restrict_
 static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cplx* c12) {
     if (fused ? op_apply_fused(op, x, y, 1) : op_apply_planes(op, x, y, 1)) return -1;
     if (c12) {
-        conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), 0);
+        { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), 0); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
     }
     return 0;
@@ -163,7 +163,7 @@ static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cp
 static int residual_A(const FdfdOp* op, const cplx* b, const cplx* x, cplx* r, const cplx* c12) {
     if (op_residual(op, b, x, r, 1)) return -1;
     if (c12) {
-        conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(r, c12, x, op->n(), 1);
+        { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(r, c12, x, op->n(), 1); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
     }
     return 0;
@@ -207,19 +207,19 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
     if (res->relres <= tol) { res->converged = 1; return 0; }
     for (int it = 1; it <= maxiter; ++it) {
         if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO, RI)) return -1;
-        bicg_beta_kernel<<<1, 1, 0, st>>>(sc);
-        bicg_p_kernel<<<nblk, 256, 0, st>>>(p, r, v, sc, n);
+        { bicg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
+        { bicg_p_kernel<<<nblk, 256, 0, st>>>(p, r, v, sc, n); ++g_fdfd_launches; }
         if (precond) { if (nd_solve(precond, op, p, ph, 1)) return -1; }
         if (apply_A(op, ph, v, fused, c12)) return -1;
         if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V, RI)) return -1;
-        bicg_alpha_kernel<<<1, 1, 0, st>>>(sc);
-        bicg_s_kernel<<<nblk, 256, 0, st>>>(s, r, v, sc, n);
+        { bicg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
+        { bicg_s_kernel<<<nblk, 256, 0, st>>>(s, r, v, sc, n); ++g_fdfd_launches; }
         if (precond) { if (nd_solve(precond, op, s, sh, 1)) return -1; }
         if (apply_A(op, sh, t, fused, c12)) return -1;
         if (dev_dot(st, t, s, n, true, partial, sc + S_TS, RI)) return -1;
         if (dev_dot(st, t, t, n, true, partial, sc + S_TT, RI)) return -1;
-        bicg_omega_kernel<<<1, 1, 0, st>>>(sc);
-        bicg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, ph, sh, s, t, sc, n);
+        { bicg_omega_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
+        { bicg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, ph, sh, s, t, sc, n); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
@@ -253,9 +253,9 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
     if (check_every < 1) check_every = 1;
     // symmetrised system  D A x = D b,  D = diag(sxf[ix] syf[iy])
     FDFD_CHECK(cudaMemcpyAsync(bs, d_b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    sym_scale_kernel<<<nblk, 256, 0, st>>>(bs, op->isxf, op->isyf, op->nx, op->ny);
+    { sym_scale_kernel<<<nblk, 256, 0, st>>>(bs, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
     if (op_residual(op, d_b, d_x, r, 1)) return -1;
-    sym_scale_kernel<<<nblk, 256, 0, st>>>(r, op->isxf, op->isyf, op->nx, op->ny);
+    { sym_scale_kernel<<<nblk, 256, 0, st>>>(r, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
     if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR, 0)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
@@ -269,13 +269,13 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
     if (dev_dot(st, r, r, n, false, partial, sc + S_RHO, 0)) return -1;
     for (int it = 1; it <= maxiter; ++it) {
         if (apply_A(op, p, q, fused, nullptr)) return -1;
-        sym_scale_kernel<<<nblk, 256, 0, st>>>(q, op->isxf, op->isyf, op->nx, op->ny);
+        { sym_scale_kernel<<<nblk, 256, 0, st>>>(q, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
         if (dev_dot(st, p, q, n, false, partial, sc + S_PQ, 0)) return -1;
-        cocg_alpha_kernel<<<1, 1, 0, st>>>(sc);
-        cocg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, p, q, sc, n);
+        { cocg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
+        { cocg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, p, q, sc, n); ++g_fdfd_launches; }
         if (dev_dot(st, r, r, n, false, partial, sc + S_RR, 0)) return -1;
-        cocg_beta_kernel<<<1, 1, 0, st>>>(sc);
-        cocg_p_kernel<<<nblk, 256, 0, st>>>(p, r, sc, n);
+        { cocg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
+        { cocg_p_kernel<<<nblk, 256, 0, st>>>(p, r, sc, n); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
@@ -326,7 +326,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
         }
         if (worst <= tol || step >= max_refine) break;
         if (nd_solve(nd, op, r, d, nrhs)) return -1;
-        axpy_one_kernel<<<ceil_div(n * nrhs, 256), 256, 0, st>>>(d_x, d, n * nrhs);
+        { axpy_one_kernel<<<ceil_div(n * nrhs, 256), 256, 0, st>>>(d_x, d, n * nrhs); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
     }
     *relres_out = worst;

@@ -325,8 +325,8 @@ int mode_solve(const double* eps_line, int n, double omega, double dl, int pol, 
     cudaError_t e = cudaMemcpy(eps, eps_line, sizeof(double) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(info, 0, sizeof(int));
     if (e == cudaSuccess) {
-        mode_kernel<<<1, MODE_THREADS>>>(eps, n, omega, dl, pol, L0, neff, order, averaged, p, M, piv, d, off, sq, X, Y,
-                                         BY, dvals, dvecs, info);
+        { mode_kernel<<<1, MODE_THREADS>>>(eps, n, omega, dl, pol, L0, neff, order, averaged, p, M, piv, d, off, sq, X, Y,
+                                         BY, dvals, dvecs, info); ++g_fdfd_launches; }
         e = cudaGetLastError();
     }
     int h_info = 0;

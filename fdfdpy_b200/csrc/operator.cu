@@ -5,6 +5,7 @@
 #include "operator.cuh"
 
 thread_local char g_fdfd_err[512] = {0};
+unsigned long long g_fdfd_launches = 0;
 
 // ------------------------------------------------------------------------------------------
 // PML: inverse stretch factors for one axis.  Restates create_sfactor's index rules
@@ -243,8 +244,8 @@ int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x,
     FDFD_CHECK(cudaMalloc(&op->eps_nl, sizeof(cplx) * n));
     FDFD_CHECK(cudaMalloc(&op->planes, sizeof(cplx) * n * 5));
     AsmParams p = make_params(op);
-    pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0);
-    pml_axis_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->isyf, op->isyb, ny, npml_y, p.dy, omega, L0);
+    { pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0); ++g_fdfd_launches; }
+    { pml_axis_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->isyf, op->isyb, ny, npml_y, p.dy, omega, L0); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     *out = op;
@@ -255,6 +256,7 @@ void op_destroy(FdfdOp* op) {
     if (!op) return;
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
+    if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
     cudaStreamDestroy(op->stream);
     delete op;
 }
@@ -268,22 +270,22 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     if (d_eps_nl && d_eps_nl != op->eps_nl)
         FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, d_eps_nl, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
     AsmParams p = make_params(op);
-    assemble_planes_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(
-        op->planes, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, p);
+    { assemble_planes_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(
+        op->planes, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, p); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
 
 int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
     dim3 grid(ceil_div(op->n(), 256), nvec);
-    stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny);
+    { stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
 
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
     dim3 grid(ceil_div(op->n(), 256), nvec);
-    stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny);
+    { stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
@@ -292,9 +294,9 @@ int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
     if (op->pol != 0) return op_apply_planes(op, d_x, d_y, nvec);
     AsmParams p = make_params(op);
     dim3 grid(ceil_div(op->ny, 128), ceil_div(op->nx, FUSED_ROWS), nvec);
-    stencil_fused_ez_kernel<<<grid, 128, 0, op->stream>>>(
+    { stencil_fused_ez_kernel<<<grid, 128, 0, op->stream>>>(
         op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, d_x, d_y,
-        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0);
+        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
@@ -302,8 +304,8 @@ int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
 int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2, int averaging) {
     AsmParams p = make_params(op);
     if (averaging >= 0) p.averaging = averaging;
-    derive_fields_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(
-        d_x, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxb, op->isyb, d_f1, d_f2, p);
+    { derive_fields_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(
+        d_x, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxb, op->isyb, d_f1, d_f2, p); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }

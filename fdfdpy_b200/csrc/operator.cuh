@@ -14,6 +14,7 @@ struct FdfdOp {
     int averaging;      // Hz edge averaging (linalg.py:68-73)
     int has_nl;         // eps_nl present
     cudaStream_t stream;
+    cudaEvent_t ev0, ev1;   // fdfd_timer_start/stop
     // 1-D inverse stretch factors 1/s (pml.py:63-76), device
     cplx *isxf, *isxb, *isyf, *isyb;
     // permittivity planes (device, nx*ny complex128)

@@ -10,6 +10,7 @@
 //
 // Warp tile 16 (M) x 32 (N) complex; CTA = WM x WN warps.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 struct GemmBatch {
@@ -123,12 +124,27 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     }
 }
 
+// optional live timing of every GEMM launch (CUDA events on the launching stream); see capi.cu
+struct ZgemmTiming {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;      // start/stop pairs
+    std::vector<double> flops;        // real flops of each launch (8 per complex MAC)
+    std::vector<int> big;             // 1: 64x64-tile kernel, 0: 32x32-tile kernel
+};
+extern ZgemmTiming g_zgemm_timing;
+
 static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_zgemm_timing.on) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+    }
     if (g.M <= 32 && g.N <= 32) {
         int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
         long long blocks = (long long)tm * tn * g.batch;
-        zgemm_dmma_kernel<2, 1><<<(unsigned)blocks, 64, 0, stream>>>(g, tm, tn);
+        { zgemm_dmma_kernel<2, 1><<<(unsigned)blocks, 64, 0, stream>>>(g, tm, tn); ++g_fdfd_launches; }
     } else {
         int tm = (g.M + 63) / 64, tn = (g.N + 63) / 64;
         long long blocks = (long long)tm * tn * g.batch;
@@ -136,7 +152,14 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
             snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
             return -1;
         }
-        zgemm_dmma_kernel<4, 2><<<(unsigned)blocks, 256, 0, stream>>>(g, tm, tn);
+        { zgemm_dmma_kernel<4, 2><<<(unsigned)blocks, 256, 0, stream>>>(g, tm, tn); ++g_fdfd_launches; }
+    }
+    if (g_zgemm_timing.on) {
+        cudaEventRecord(e1, stream);
+        g_zgemm_timing.ev.push_back(e0);
+        g_zgemm_timing.ev.push_back(e1);
+        g_zgemm_timing.flops.push_back(8.0 * g.M * (double)g.N * g.K * g.batch);
+        g_zgemm_timing.big.push_back((g.M <= 32 && g.N <= 32) ? 0 : 1);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -28,6 +28,19 @@ int fdfd_free(void* dev_ptr);
 int fdfd_memcpy_h2d(void* dev, const void* host, double bytes);
 int fdfd_memcpy_d2h(void* host, const void* dev, double bytes);
 int fdfd_op_sync(fdfd_op* op);
+/* number of CUDA kernels this library has launched so far (reset != 0 zeroes the counter) */
+double fdfd_launch_count(int reset);
+/* measurement helpers (bench.py): CUDA-event timer on the operator's stream; live per-launch timing
+ * of the GEMM kernels (totals: ms, real flops, launches for the 64x64- and the 32x32-tile kernel);
+ * and a register-resident DMMA loop that measures the FP64 tensor-pipe ceiling of this board. */
+int fdfd_timer_start(fdfd_op* op);
+int fdfd_timer_stop(fdfd_op* op, double* ms);
+int fdfd_gemm_timing(int enable);
+int fdfd_gemm_timing_read(double* out6);
+int fdfd_dmma_peak(double* tflops);
+/* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
+int fdfd_host_register(void* host, double bytes);
+int fdfd_host_unregister(void* host);
 
 /* ---- operator: replaces linalg.py:39 construct_A, pml.py:44 S_create, derivatives.py:7 createDws.
  * pol: 0 = 'Ez', 1 = 'Hz'.  The sc-PML inverse stretch factors are computed on the device at

@@ -136,6 +136,20 @@ def gold_mode():
     out["eps"] = eps
     out["epsT"] = epsT
     out["meta"] = np.array([omega, dl, 1e-6, 10, 10])
+    # tests/test_flux.py workload at full size: the upstream assertion (flux1 == flux2) does not
+    # hold for the reference itself because the unit-norm mode profile is not rescaled with dl;
+    # record what the reference actually returns (flux, W_in) for both resolutions.
+    rows = []
+    for (dl2, shape, wg, c, w, p) in [(0.01, (300, 100), (40, 60), [20, 50], 60, [150, 50]),
+                                      (0.005, (600, 200), (80, 120), [20, 100], 120, [300, 100])]:
+        e = np.ones(shape)
+        e[:, wg[0]:wg[1]] = 12.25
+        sim = Simulation(omega, e, dl2, [15, 15], 'Ez')
+        sim.add_mode(3.5, 'x', c, w, scale=1)
+        sim.setup_modes()
+        sim.solve_fields()
+        rows.append([sim.flux_probe('x', p, w), sim.W_in])
+    out["flux_test"] = np.array(rows)
     save("mode_source", **out)
 
 
