@@ -107,7 +107,7 @@ class MaxwellOperator:
         return f1.reshape(self.nx, self.ny), f2.reshape(self.nx, self.ny)
 
     # ---- solvers
-    def direct(self, tile=32):
+    def direct(self, tile=64):
         if self._direct is None:
             self._direct = DirectSolver(self, tile=tile)
         return self._direct
@@ -141,7 +141,7 @@ class MaxwellOperator:
 class DirectSolver:
     """Structured direct solver handle (reference: linalg.py:123 solver_direct / pardisoSolver)."""
 
-    def __init__(self, op, tile=32):
+    def __init__(self, op, tile=64):
         self.op = op
         self.lib = op.lib
         self.h = C.c_void_p()

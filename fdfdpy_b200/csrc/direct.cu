@@ -10,6 +10,7 @@
 // so the triangular solves of a classic multifrontal code become plain batched matrix-vector
 // products in the solve phase.  The rank-T updates of the sweep are complex GEMMs on the FP64
 // tensor pipe (zgemm.cuh); pivot tiles are inverted in shared memory with partial pivoting.
+#include <algorithm>
 #include "direct.cuh"
 #include "zgemm.cuh"
 
@@ -379,6 +380,8 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->ws_a = s->ws_b = s->ws_ring_a = s->ws_ring_b = s->ws_ye = nullptr;
     s->ws_vec_cap = s->ws_ring_cap = s->ws_ye_cap = 0;
     s->d_info = nullptr;
+    s->fws = nullptr;
+    s->fws_cap = 0;
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
     *out = s;
     return 0;
@@ -437,6 +440,7 @@ void nd_destroy(NdSolver* s) {
     }
     cudaFree(s->ws_a); cudaFree(s->ws_b); cudaFree(s->ws_ring_a); cudaFree(s->ws_ring_b); cudaFree(s->ws_ye);
     cudaFree(s->d_info);
+    if (s->fws) cudaFree(s->fws);
     delete s;
 }
 
@@ -448,10 +452,39 @@ static int chunks_for(long long per_front_elems, long long nb) {
     return (int)(c < 1 ? 1 : c);
 }
 
+// one arena for all transient factorisation buffers: two ping-pong front batches plus the pivot /
+// column-panel / row-panel scratch, sized for the largest level; allocated once and kept
+static int ensure_factor_workspace(NdSolver* s) {
+    size_t maxF = 0, maxP = 0, maxC = 0;
+    for (auto& L : s->levels) {
+        const size_t nb = L.nb, nmax = L.nmax;
+        const size_t tcap = L.kmax < s->tile ? L.kmax : s->tile;
+        maxF = std::max(maxF, nb * nmax * nmax);
+        maxP = std::max(maxP, nb * tcap * tcap);
+        maxC = std::max(maxC, nb * nmax * tcap);
+    }
+    size_t need = 2 * maxF + maxP + 2 * maxC;
+    if (need > s->fws_cap) {
+        if (s->fws) cudaFree(s->fws);
+        s->fws = nullptr;
+        s->fws_cap = 0;
+        FDFD_CHECK(cudaMalloc(&s->fws, sizeof(cplx) * need));
+        s->fws_cap = need;
+    }
+    s->fws_F[0] = s->fws;
+    s->fws_F[1] = s->fws + maxF;
+    s->fws_P = s->fws + 2 * maxF;
+    s->fws_C = s->fws_P + maxP;
+    s->fws_R = s->fws_C + maxC;
+    return 0;
+}
+
 int nd_factor(NdSolver* s, const FdfdOp* op) {
     if (s->levels.empty()) FDFD_FAIL("no levels in the plan");
     if (op->nx != s->nx || op->ny != s->ny) FDFD_FAIL("operator / plan shape mismatch");
     cudaStream_t st = op->stream;
+    s->factored = false;
+    if (ensure_factor_workspace(s)) return -1;
     FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
     cplx* Fprev = nullptr;
     int prev_k = 0, prev_n = 0;
@@ -459,24 +492,24 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     s->factor_flops = 0;
     for (size_t li = 0; li < s->levels.size(); ++li) {
         NdLevel& L = s->levels[li];
-        free_level_factors(L);
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
         const int tcap = kmax < s->tile ? kmax : s->tile;
-        cplx *F = nullptr, *Pbuf = nullptr, *Cbuf = nullptr, *Rbuf = nullptr;
-        FDFD_CHECK(cudaMalloc(&F, sizeof(cplx) * nb * nmax * nmax));
-        FDFD_CHECK(cudaMalloc(&Pbuf, sizeof(cplx) * nb * tcap * tcap));
-        FDFD_CHECK(cudaMalloc(&Cbuf, sizeof(cplx) * nb * nmax * tcap));
-        FDFD_CHECK(cudaMalloc(&Rbuf, sizeof(cplx) * nb * tcap * nmax));
+        cplx *F = s->fws_F[li & 1], *Pbuf = s->fws_P, *Cbuf = s->fws_C, *Rbuf = s->fws_R;
+        // factor storage is allocated on the first factorisation and reused afterwards
+        if (!L.EZX) FDFD_CHECK(cudaMalloc(&L.EZX, sizeof(cplx) * (size_t)nb * kmax * nmax));
+        if (mmax > 0 && !L.RW) FDFD_CHECK(cudaMalloc(&L.RW, sizeof(cplx) * (size_t)nb * mmax * kmax));
         if (L.kind == 0) {
-            { leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
+            leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
                                                               L.slot_ly, L.slot_right, L.slot_up, kmax, nmax,
-                                                              s->nx, s->ny); ++g_fdfd_launches; }
+                                                              s->nx, s->ny);
+            ++g_fdfd_launches;
         } else {
             int chunks = chunks_for((long long)nmax * nmax, nb);
-            { merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
+            merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
                                                                            L.inv1, L.inv2, kmax, nmax, prev_k,
-                                                                           prev_n, chunks); ++g_fdfd_launches; }
+                                                                           prev_n, chunks);
+            ++g_fdfd_launches;
         }
         FDFD_CHECK(cudaGetLastError());
         for (int j0 = 0; j0 < kmax; j0 += tcap) {
@@ -486,9 +519,11 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
-            { pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info); ++g_fdfd_launches; }
+            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
+            ++g_fdfd_launches;
             int chunks = chunks_for((long long)nmax * tw, nb);
-            { panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks); ++g_fdfd_launches; }
+            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
+            ++g_fdfd_launches;
             FDFD_CHECK(cudaGetLastError());
             GemmBatch g;
             g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
@@ -496,7 +531,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             g.C = Rbuf; g.sC = (long long)tcap * nmax; g.ldc = nmax;
             g.M = tw; g.N = nmax; g.K = tw; g.batch = (int)nb; g.mode = 0;
             if (zgemm_batched(g, st)) return -1;
-            { copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks); ++g_fdfd_launches; }
+            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
+            ++g_fdfd_launches;
             FDFD_CHECK(cudaGetLastError());
             g.A = Cbuf; g.sA = (long long)nmax * tcap; g.lda = tcap;
             g.B = Rbuf; g.sB = (long long)tcap * nmax; g.ldb = nmax;
@@ -505,24 +541,20 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             if (zgemm_batched(g, st)) return -1;
             s->factor_flops += 8.0 * (double)nb * ((double)nmax * nmax * tw + (double)tw * tw * nmax);
         }
-        FDFD_CHECK(cudaMalloc(&L.EZX, sizeof(cplx) * (size_t)nb * kmax * nmax));
-        if (mmax > 0) FDFD_CHECK(cudaMalloc(&L.RW, sizeof(cplx) * (size_t)nb * mmax * kmax));
         s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * nmax + (size_t)nb * mmax * kmax);
         {
             int chunks = chunks_for((long long)kmax * nmax + (long long)mmax * kmax, nb);
-            { extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks); ++g_fdfd_launches; }
+            extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks);
+            ++g_fdfd_launches;
             FDFD_CHECK(cudaGetLastError());
         }
-        FDFD_CHECK(cudaStreamSynchronize(st));
-        cudaFree(Pbuf); cudaFree(Cbuf); cudaFree(Rbuf);
-        if (Fprev) cudaFree(Fprev);
         Fprev = F;
         prev_k = kmax;
         prev_n = nmax;
     }
-    if (Fprev) cudaFree(Fprev);
     int info = 0;
-    FDFD_CHECK(cudaMemcpy(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+    FDFD_CHECK(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FDFD_CHECK(cudaStreamSynchronize(st));
     if (info) FDFD_FAIL("direct solver: a pivot block is numerically singular (no inter-block pivoting)");
     s->factored = true;
     return 0;

@@ -39,6 +39,9 @@ struct NdSolver {
     size_t factor_bytes;
     double factor_flops;              // real flops of the last factorisation (8 per complex MAC)
     int* d_info;                      // device flag: non-zero if a pivot tile was singular
+    // factorisation arena (allocated once): ping-pong front batches + pivot / panel scratch
+    cplx *fws, *fws_F[2], *fws_P, *fws_C, *fws_R;
+    size_t fws_cap;
     // solve workspace (grown on demand)
     cplx *ws_a, *ws_b, *ws_ring_a, *ws_ring_b, *ws_ye;
     size_t ws_vec_cap, ws_ring_cap, ws_ye_cap;

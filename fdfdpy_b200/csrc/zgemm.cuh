@@ -27,12 +27,27 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
         : "d"(a), "d"(b));
 }
 
-template <int WM, int WN>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;     // src-size 0 -> the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// Tiles are staged interleaved (re, im) by cp.async (LDGSTS) into a STAGES-deep ring; fragment loads
+// are LDS.128.  Leading dimensions LDA = 4 mod 8 and LDB = 2 mod 8 complex make every 8-lane phase of
+// those loads hit eight different 16-byte bank groups.
+template <int WM, int WN, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     constexpr int BM = 16 * WM, BN = 32 * WN, BK = 16, NT = WM * WN * 32;
-    __shared__ double As_r[BM][BK + 4], As_i[BM][BK + 4];
-    __shared__ double Bs_r[BK][BN + 4], Bs_i[BK][BN + 4];
+    constexpr int LDA = BK + 4, LDB = BN + 2;
+    constexpr int A_ELEMS = BM * LDA, B_ELEMS = BK * LDB;
+    extern __shared__ __align__(16) unsigned char zg_smem[];
+    cplx* As = reinterpret_cast<cplx*>(zg_smem);            // [STAGES][BM][LDA]
+    cplx* Bs = As + STAGES * A_ELEMS;                        // [STAGES][BK][LDB]
 
     long long bid = blockIdx.x;
     const int tn = (int)(bid % tiles_n);
@@ -53,52 +68,62 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
 
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
+    auto load_tile = [&](int stage, int kt) {
+        const int k0 = kt * BK;
+        cplx* as = As + stage * A_ELEMS;
+        cplx* bs = Bs + stage * B_ELEMS;
+#pragma unroll
         for (int i = tid; i < BM * BK; i += NT) {
             int r = i / BK, c = i % BK;
             int gm = m_base + r, gk = k0 + c;
-            cplx v = make_double2(0.0, 0.0);
-            if (gm < g.M && gk < g.K) v = A[(size_t)gm * g.lda + gk];
-            As_r[r][c] = v.x;
-            As_i[r][c] = v.y;
+            bool ok = gm < g.M && gk < g.K;
+            cp_async16(as + r * LDA + c, ok ? A + (size_t)gm * g.lda + gk : A, ok);
         }
+#pragma unroll
         for (int i = tid; i < BK * BN; i += NT) {
             int r = i / BN, c = i % BN;
             int gk = k0 + r, gn = n_base + c;
-            cplx v = make_double2(0.0, 0.0);
-            if (gk < g.K && gn < g.N) v = B[(size_t)gk * g.ldb + gn];
-            Bs_r[r][c] = v.x;
-            Bs_i[r][c] = v.y;
+            bool ok = gk < g.K && gn < g.N;
+            cp_async16(bs + r * LDB + c, ok ? B + (size_t)gk * g.ldb + gn : B, ok);
         }
+    };
+
+    const int KT = (g.K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
+        if (kt + STAGES - 1 < KT) load_tile((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+        cp_async_commit();
+        const cplx* as = As + (kt % STAGES) * A_ELEMS;
+        const cplx* bs = Bs + (kt % STAGES) * B_ELEMS;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double ar[2], ai[2], nai[2], br[4], bi[4];
+            cplx a[2], bq[4];
+            double nai[2];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                int row = wm * 16 + mt * 8 + gq;
-                ar[mt] = As_r[row][kk + tq];
-                ai[mt] = As_i[row][kk + tq];
-                nai[mt] = -ai[mt];
+                a[mt] = as[(wm * 16 + mt * 8 + gq) * LDA + kk + tq];
+                nai[mt] = -a[mt].y;
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                int col = wn * 32 + nt * 8 + gq;
-                br[nt] = Bs_r[kk + tq][col];
-                bi[nt] = Bs_i[kk + tq][col];
-            }
+            for (int nt = 0; nt < 4; ++nt) bq[nt] = bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], ar[mt], br[nt]);
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bi[nt]);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], ar[mt], bi[nt]);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], ai[mt], br[nt]);
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
                 }
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
 
     // epilogue: each thread owns, per (mt, nt), two adjacent complex entries of one row
 #pragma unroll
@@ -124,6 +149,11 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     }
 }
 
+template <int WM, int WN, int STAGES>
+constexpr size_t zgemm_smem_bytes() {
+    return sizeof(cplx) * STAGES * ((16 * WM) * (16 + 4) + 16 * (32 * WN + 2));
+}
+
 // optional live timing of every GEMM launch (CUDA events on the launching stream); see capi.cu
 struct ZgemmTiming {
     bool on = false;
@@ -144,7 +174,9 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
     if (g.M <= 32 && g.N <= 32) {
         int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
         long long blocks = (long long)tm * tn * g.batch;
-        { zgemm_dmma_kernel<2, 1><<<(unsigned)blocks, 64, 0, stream>>>(g, tm, tn); ++g_fdfd_launches; }
+        constexpr size_t sm = zgemm_smem_bytes<2, 1, 2>();
+        zgemm_dmma_kernel<2, 1, 2><<<(unsigned)blocks, 64, sm, stream>>>(g, tm, tn);
+        ++g_fdfd_launches;
     } else {
         int tm = (g.M + 63) / 64, tn = (g.N + 63) / 64;
         long long blocks = (long long)tm * tn * g.batch;
@@ -152,7 +184,14 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
             snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
             return -1;
         }
-        { zgemm_dmma_kernel<4, 2><<<(unsigned)blocks, 256, 0, stream>>>(g, tm, tn); ++g_fdfd_launches; }
+        constexpr size_t sm = zgemm_smem_bytes<4, 2, 3>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            attr_set = true;
+        }
+        zgemm_dmma_kernel<4, 2, 3><<<(unsigned)blocks, 256, sm, stream>>>(g, tm, tn);
+        ++g_fdfd_launches;
     }
     if (g_zgemm_timing.on) {
         cudaEventRecord(e1, stream);

@@ -9,7 +9,8 @@ from fdfdpy_b200 import core  # noqa: E402
 
 OMEGA = 2 * np.pi * 200e12
 sizes = [int(a) for a in sys.argv[1:]] or [512, 1024]
-tile = 32
+import os
+tile = int(os.environ.get("FDFD_TILE", "32"))
 for n in sizes:
     rng = np.random.default_rng(0)
     eps = 1 + 11 * (rng.random((n, n)) > 0.5)
