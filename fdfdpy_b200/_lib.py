@@ -44,6 +44,9 @@ SIGNATURES = {
     "fdfd_gemm_timing": (C.c_int, [C.c_int]),
     "fdfd_gemm_timing_read": (C.c_int, [_vp]),
     "fdfd_dmma_peak": (C.c_int, [_dp]),
+    "fdfd_phase_timing": (C.c_int, [C.c_int]),
+    "fdfd_phase_timing_read": (C.c_int, [_vp]),
+    "fdfd_dmma_probe": (C.c_int, [C.c_int, C.c_int, _dp]),
     "fdfd_host_register": (C.c_int, [_vp, C.c_double]),
     "fdfd_host_unregister": (C.c_int, [_vp]),
     "fdfd_op_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -69,6 +72,8 @@ SIGNATURES = {
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                         _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fdfd_zgemm_set_variant": (C.c_int, [C.c_int]),
+    "fdfd_zgemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "fdfd_mode_solve_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                        C.c_int, C.c_int, _vp, _vp]),
 }

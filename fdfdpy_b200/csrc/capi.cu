@@ -17,6 +17,7 @@ struct DevBuf {
 }  // namespace
 
 ZgemmTiming g_zgemm_timing;
+int g_zgemm_variant = 0;
 
 // register-resident DMMA loop: the practical FP64 tensor-pipe ceiling at the clocks the board runs at
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
@@ -34,6 +35,21 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
     if (s == 123.456) out[0] = s;
 }
 
+template <int NACC>
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
 extern "C" {
 
 int fdfd_dmma_peak(double* tflops) {
@@ -61,6 +77,35 @@ int fdfd_dmma_peak(double* tflops) {
     return 0;
 }
 
+/* DMMA issue-rate probe: `warps` warps per SM (one CTA per SM), `nacc` independent accumulators */
+int fdfd_dmma_probe(int warps, int nacc, double* tflops) {
+    double* d = nullptr;
+    FDFD_CHECK(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    const int iters = 20000 / nacc;
+    auto launch = [&](int it) {
+        if (nacc == 1) dmma_probe_kernel<1><<<148, warps * 32>>>(d, it);
+        else if (nacc == 2) dmma_probe_kernel<2><<<148, warps * 32>>>(d, it);
+        else if (nacc == 4) dmma_probe_kernel<4><<<148, warps * 32>>>(d, it);
+        else if (nacc == 8) dmma_probe_kernel<8><<<148, warps * 32>>>(d, it);
+        else dmma_probe_kernel<16><<<148, warps * 32>>>(d, it);
+    };
+    launch(10);
+    FDFD_CHECK(cudaDeviceSynchronize());
+    FDFD_CHECK(cudaEventRecord(e0));
+    launch(iters);
+    FDFD_CHECK(cudaEventRecord(e1));
+    FDFD_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    int na = nacc >= 16 ? 16 : nacc;
+    *tflops = 148.0 * warps * iters * na * 512.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
 int fdfd_gemm_timing(int enable) {
     for (cudaEvent_t e : g_zgemm_timing.ev) cudaEventDestroy(e);
     g_zgemm_timing.ev.clear(); g_zgemm_timing.flops.clear(); g_zgemm_timing.big.clear();
@@ -77,6 +122,24 @@ int fdfd_gemm_timing_read(double* out) {
         FDFD_CHECK(cudaEventElapsedTime(&ms, g_zgemm_timing.ev[2 * i], g_zgemm_timing.ev[2 * i + 1]));
         int o = g_zgemm_timing.big[i] ? 0 : 3;
         out[o] += ms; out[o + 1] += g_zgemm_timing.flops[i]; out[o + 2] += 1;
+    }
+    return 0;
+}
+int fdfd_phase_timing(int enable) {
+    for (cudaEvent_t e : g_phase_timing.ev) cudaEventDestroy(e);
+    g_phase_timing.ev.clear(); g_phase_timing.cat.clear();
+    g_phase_timing.on = enable != 0;
+    return 0;
+}
+/* per-phase totals in ms since fdfd_phase_timing(1): assemble, pivot, panel, rowgemm, copy, update,
+ * extract, solve_fwd, solve_bwd, stencil (10 doubles). Synchronises the device. */
+int fdfd_phase_timing_read(double* out10) {
+    FDFD_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < PH_COUNT; ++i) out10[i] = 0;
+    for (size_t i = 0; i < g_phase_timing.cat.size(); ++i) {
+        float ms = 0;
+        FDFD_CHECK(cudaEventElapsedTime(&ms, g_phase_timing.ev[2 * i], g_phase_timing.ev[2 * i + 1]));
+        out10[g_phase_timing.cat[i]] += ms;
     }
     return 0;
 }
@@ -282,6 +345,34 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
     if (zgemm_batched(g, 0)) return -1;
     FDFD_CHECK(cudaDeviceSynchronize());
     FDFD_CHECK(cudaMemcpy(Cm, c.p, sizeof(cplx) * sc * batch, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }
+
+int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int iters, double* ms_per_launch) {
+    // device-only timing of one GEMM shape (uninitialised-but-finite operands), CUDA events
+    DevBuf a, b, c;
+    size_t sa = (size_t)M * K, sb = (size_t)K * N, sc = (size_t)M * N;
+    if (a.alloc(sa * batch) || b.alloc(sb * batch) || c.alloc(sc * batch)) return -1;
+    FDFD_CHECK(cudaMemset(a.p, 0, sizeof(cplx) * sa * batch));
+    FDFD_CHECK(cudaMemset(b.p, 0, sizeof(cplx) * sb * batch));
+    FDFD_CHECK(cudaMemset(c.p, 0, sizeof(cplx) * sc * batch));
+    GemmBatch g;
+    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = N; g.C = c.p; g.sC = sc; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode;
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) if (zgemm_batched(g, 0)) return -1;
+    FDFD_CHECK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) if (zgemm_batched(g, 0)) return -1;
+    FDFD_CHECK(cudaEventRecord(e1, 0));
+    FDFD_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_launch = ms / iters;
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 typedef double2 cplx;   // (re, im), layout-compatible with numpy complex128
 
@@ -57,5 +58,32 @@ __host__ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
 __host__ __device__ __forceinline__ cplx crecip(cplx b) { return cdiv(make_double2(1.0, 0.0), b); }
 
 __device__ __forceinline__ cplx ldg_c(const cplx* p) { return __ldg(p); }
+
+// ---- optional live phase timing (CUDA events on the launching stream), read by bench.py ----
+enum FdfdPhase { PH_ASSEMBLE = 0, PH_PIVOT, PH_PANEL, PH_ROWGEMM, PH_COPY, PH_UPDATE, PH_EXTRACT, PH_SOLVE_FWD,
+                 PH_SOLVE_BWD, PH_STENCIL, PH_COUNT };
+struct PhaseTiming {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cat;
+};
+extern PhaseTiming g_phase_timing;
+struct PhaseScope {
+    cudaStream_t st;
+    bool active;
+    PhaseScope(int cat, cudaStream_t s) : st(s), active(g_phase_timing.on) {
+        if (!active) return;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        g_phase_timing.ev.push_back(e0);
+        g_phase_timing.ev.push_back(e1);
+        g_phase_timing.cat.push_back(cat);
+    }
+    ~PhaseScope() {
+        if (active) cudaEventRecord(g_phase_timing.ev.back(), st);
+    }
+};
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

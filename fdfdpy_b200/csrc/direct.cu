@@ -499,6 +499,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         // factor storage is allocated on the first factorisation and reused afterwards
         if (!L.EZX) FDFD_CHECK(cudaMalloc(&L.EZX, sizeof(cplx) * (size_t)nb * kmax * nmax));
         if (mmax > 0 && !L.RW) FDFD_CHECK(cudaMalloc(&L.RW, sizeof(cplx) * (size_t)nb * mmax * kmax));
+        {
+        PhaseScope ph(PH_ASSEMBLE, st);
         if (L.kind == 0) {
             leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
                                                               L.slot_ly, L.slot_right, L.slot_up, kmax, nmax,
@@ -511,6 +513,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                                                                            prev_n, chunks);
             ++g_fdfd_launches;
         }
+        }
         FDFD_CHECK(cudaGetLastError());
         for (int j0 = 0; j0 < kmax; j0 += tcap) {
             const int tw = (kmax - j0) < tcap ? (kmax - j0) : tcap;
@@ -519,30 +522,46 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
-            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
-            ++g_fdfd_launches;
+            {
+                PhaseScope ph(PH_PIVOT, st);
+                pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
+                ++g_fdfd_launches;
+            }
             int chunks = chunks_for((long long)nmax * tw, nb);
-            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
-            ++g_fdfd_launches;
+            {
+                PhaseScope ph(PH_PANEL, st);
+                panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
+                ++g_fdfd_launches;
+            }
             FDFD_CHECK(cudaGetLastError());
             GemmBatch g;
             g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
             g.B = F + (size_t)j0 * nmax; g.sB = (long long)nmax * nmax; g.ldb = nmax;
             g.C = Rbuf; g.sC = (long long)tcap * nmax; g.ldc = nmax;
             g.M = tw; g.N = nmax; g.K = tw; g.batch = (int)nb; g.mode = 0;
-            if (zgemm_batched(g, st)) return -1;
-            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
-            ++g_fdfd_launches;
+            {
+                PhaseScope ph(PH_ROWGEMM, st);
+                if (zgemm_batched(g, st)) return -1;
+            }
+            {
+                PhaseScope ph(PH_COPY, st);
+                copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
+                ++g_fdfd_launches;
+            }
             FDFD_CHECK(cudaGetLastError());
             g.A = Cbuf; g.sA = (long long)nmax * tcap; g.lda = tcap;
             g.B = Rbuf; g.sB = (long long)tcap * nmax; g.ldb = nmax;
             g.C = F; g.sC = (long long)nmax * nmax; g.ldc = nmax;
             g.M = nmax; g.N = nmax; g.K = tw; g.mode = 1;
-            if (zgemm_batched(g, st)) return -1;
+            {
+                PhaseScope ph(PH_UPDATE, st);
+                if (zgemm_batched(g, st)) return -1;
+            }
             s->factor_flops += 8.0 * (double)nb * ((double)nmax * nmax * tw + (double)tw * tw * nmax);
         }
         s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * nmax + (size_t)nb * mmax * kmax);
         {
+            PhaseScope ph(PH_EXTRACT, st);
             int chunks = chunks_for((long long)kmax * nmax + (long long)mmax * kmax, nb);
             extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks);
             ++g_fdfd_launches;
@@ -591,6 +610,8 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
     }
     cplx *f = s->ws_a, *ring_prev = s->ws_ring_a, *ring_cur = s->ws_ring_b;
     // ---- forward (leaves -> root)
+    {
+    PhaseScope phf(PH_SOLVE_FWD, st);
     for (size_t li = 0; li < nlev; ++li) {
         NdLevel& L = s->levels[li];
         const long long nb = L.nb;
@@ -606,7 +627,9 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         FDFD_CHECK(cudaGetLastError());
         std::swap(ring_prev, ring_cur);
     }
+    }
     // ---- backward (root -> leaves)
+    PhaseScope phb(PH_SOLVE_BWD, st);
     cplx *u = s->ws_a, *u_par = s->ws_b;
     for (size_t li = nlev; li-- > 0;) {
         NdLevel& L = s->levels[li];

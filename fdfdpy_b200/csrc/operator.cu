@@ -6,6 +6,7 @@
 
 thread_local char g_fdfd_err[512] = {0};
 unsigned long long g_fdfd_launches = 0;
+PhaseTiming g_phase_timing;
 
 // ------------------------------------------------------------------------------------------
 // PML: inverse stretch factors for one axis.  Restates create_sfactor's index rules

@@ -39,6 +39,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Tiles are staged interleaved (re, im) by cp.async (LDGSTS) into a STAGES-deep ring; fragment loads
 // are LDS.128.  Leading dimensions LDA = 4 mod 8 and LDB = 2 mod 8 complex make every 8-lane phase of
 // those loads hit eight different 16-byte bank groups.
+// (mma.sync m16n8k16 f64 was tried: ptxas lowers it to eight DMMA.8x8x4 on sm_100a and it ran ~6 % slower.)
 template <int WM, int WN, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
@@ -149,6 +150,158 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     }
 }
 
+// Persistent variant for the large sweep updates: one CTA per SM walks its share of the 64x64
+// output tiles; the cp.async ring runs ACROSS tiles (no pipeline refill per tile) and the C tile of
+// a mode-1 update is prefetched into registers under the last k-tile's DMMAs, so neither the
+// operand nor the accumulator-read latency is exposed.
+template <int STAGES>
+__global__ void __launch_bounds__(256, 1)
+zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long total_tiles) {
+    constexpr int WN = 2, BM = 64, BN = 64, BK = 16, NT = 256;
+    constexpr int LDA = BK + 4, LDB = BN + 2;
+    constexpr int A_ELEMS = BM * LDA, B_ELEMS = BK * LDB;
+    extern __shared__ __align__(16) unsigned char zg_smem[];
+    cplx* As = reinterpret_cast<cplx*>(zg_smem);
+    cplx* Bs = As + STAGES * A_ELEMS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp / WN, wn = warp % WN;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int KT = (g.K + BK - 1) / BK;
+    const unsigned ntiles = (unsigned)total_tiles;
+    if (blockIdx.x >= ntiles) return;
+    const unsigned tiles_per_batch = (unsigned)tiles_m * (unsigned)tiles_n;
+
+    // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor); no divisions in the hot loop
+    unsigned ld_tile = blockIdx.x;
+    int ld_kt = 0, ld_stage = 0, ld_m = 0, ld_n = 0;
+    const cplx *ld_A = g.A, *ld_B = g.B;
+    auto decode_load = [&]() {
+        unsigned b = ld_tile / tiles_per_batch, r = ld_tile - b * tiles_per_batch;
+        unsigned tm = r / (unsigned)tiles_n, tn = r - tm * (unsigned)tiles_n;
+        ld_m = (int)tm * BM;
+        ld_n = (int)tn * BN;
+        ld_A = g.A + (long long)b * g.sA;
+        ld_B = g.B + (long long)b * g.sB;
+    };
+    decode_load();
+    auto issue_load = [&]() {
+        const int k0 = ld_kt * BK;
+        cplx* as = As + ld_stage * A_ELEMS;
+        cplx* bs = Bs + ld_stage * B_ELEMS;
+#pragma unroll
+        for (int i = tid; i < BM * BK; i += NT) {
+            int r = i / BK, c = i % BK;
+            int gm = ld_m + r, gk = k0 + c;
+            bool ok = gm < g.M && gk < g.K;
+            cp_async16(as + r * LDA + c, ok ? ld_A + (size_t)gm * g.lda + gk : ld_A, ok);
+        }
+#pragma unroll
+        for (int i = tid; i < BK * BN; i += NT) {
+            int r = i / BN, c = i % BN;
+            int gk = k0 + r, gn = ld_n + c;
+            bool ok = gk < g.K && gn < g.N;
+            cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gk * g.ldb + gn : ld_B, ok);
+        }
+        ld_stage = ld_stage + 1 == STAGES ? 0 : ld_stage + 1;
+        if (++ld_kt == KT) {
+            ld_kt = 0;
+            ld_tile += gridDim.x;
+            if (ld_tile < ntiles) decode_load();
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (ld_tile < ntiles) issue_load();
+        cp_async_commit();
+    }
+    double cr[2][4][2], ci[2][4][2];
+    cplx cpre[2][4][2];
+    int stage = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        unsigned b = tile / tiles_per_batch, rr = tile - b * tiles_per_batch;
+        unsigned tm = rr / (unsigned)tiles_n, tn = rr - tm * (unsigned)tiles_n;
+        cplx* __restrict__ C = g.C + (long long)b * g.sC;
+        const int m_base = (int)tm * BM, n_base = (int)tn * BN;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+      for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (ld_tile < ntiles) issue_load();
+        cp_async_commit();
+        const bool last = kt == KT - 1;
+        if (last && g.mode == 1) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                int row = m_base + wm * 16 + mt * 8 + gq;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    int col = n_base + wn * 32 + nt * 8 + 2 * tq;
+                    const cplx* p = C + (size_t)row * g.ldc + col;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        cpre[mt][nt][e] = (row < g.M && col + e < g.N) ? p[e] : make_double2(0.0, 0.0);
+                }
+            }
+        }
+        const cplx* as = As + stage * A_ELEMS;
+        const cplx* bs = Bs + stage * B_ELEMS;
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            cplx a[2], bq[4];
+            double nai[2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                a[mt] = as[(wm * 16 + mt * 8 + gq) * LDA + kk + tq];
+                nai[mt] = -a[mt].y;
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) bq[nt] = bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
+                }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
+                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
+                }
+        }
+        if (last) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                int row = m_base + wm * 16 + mt * 8 + gq;
+                if (row >= g.M) continue;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    int col = n_base + wn * 32 + nt * 8 + 2 * tq;
+                    cplx* p = C + (size_t)row * g.ldc + col;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (col + e < g.N) {
+                            cplx v = make_double2(cr[mt][nt][e], ci[mt][nt][e]);
+                            if (g.mode == 1) v = make_double2(cpre[mt][nt][e].x - v.x, cpre[mt][nt][e].y - v.y);
+                            p[e] = v;
+                        }
+                    }
+                }
+            }
+        }
+      }
+    }
+    cp_async_wait<0>();
+}
+
 template <int WM, int WN, int STAGES>
 constexpr size_t zgemm_smem_bytes() {
     return sizeof(cplx) * STAGES * ((16 * WM) * (16 + 4) + 16 * (32 * WN + 2));
@@ -162,6 +315,7 @@ struct ZgemmTiming {
     std::vector<int> big;             // 1: 64x64-tile kernel, 0: 32x32-tile kernel
 };
 extern ZgemmTiming g_zgemm_timing;
+extern int g_zgemm_variant;   // 0: persistent kernel for large problems, 1: always the tiled kernel
 
 static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
@@ -184,14 +338,27 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
             snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
             return -1;
         }
-        constexpr size_t sm = zgemm_smem_bytes<4, 2, 3>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            attr_set = true;
+        if (g_zgemm_variant == 0 && blocks >= 148) {
+            constexpr int ST = 4;
+            constexpr size_t sm = sizeof(cplx) * ST * (64 * 20 + 16 * 66);
+            static bool attr_p = false;
+            if (!attr_p) {
+                cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sm);
+                attr_p = true;
+            }
+            zgemm_dmma_persistent_kernel<ST><<<148, 256, sm, stream>>>(g, tm, tn, blocks);
+            ++g_fdfd_launches;
+        } else {
+            constexpr size_t sm = zgemm_smem_bytes<4, 2, 3>();
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                attr_set = true;
+            }
+            zgemm_dmma_kernel<4, 2, 3><<<(unsigned)blocks, 256, sm, stream>>>(g, tm, tn);
+            ++g_fdfd_launches;
         }
-        zgemm_dmma_kernel<4, 2, 3><<<(unsigned)blocks, 256, sm, stream>>>(g, tm, tn);
-        ++g_fdfd_launches;
     }
     if (g_zgemm_timing.on) {
         cudaEventRecord(e1, stream);

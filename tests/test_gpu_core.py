@@ -29,7 +29,7 @@ def test_zgemm_hook():
     lib = _lib.load()
     _lib.require_gpu()
     rng = np.random.default_rng(0)
-    for (M, N, K, batch) in [(25, 25, 9, 7), (64, 64, 32, 3), (70, 130, 17, 2), (200, 96, 64, 1), (13, 40, 5, 11)]:
+    for (M, N, K, batch) in [(25, 25, 9, 7), (64, 64, 32, 3), (70, 130, 17, 2), (200, 96, 64, 1), (13, 40, 5, 11), (520, 530, 70, 2), (1000, 700, 64, 1)]:
         A = rng.standard_normal((batch, M, K)) + 1j * rng.standard_normal((batch, M, K))
         B = rng.standard_normal((batch, K, N)) + 1j * rng.standard_normal((batch, K, N))
         C0 = rng.standard_normal((batch, M, N)) + 1j * rng.standard_normal((batch, M, N))

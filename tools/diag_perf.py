@@ -21,8 +21,16 @@ for n in sizes:
     t2 = time.time()
     d.factor()
     t3 = time.time()
+    import ctypes as C
+    from fdfdpy_b200 import _lib
+    op.lib.fdfd_phase_timing(1)
     d.factor()
     t4 = time.time()
+    ph = np.zeros(10)
+    op.lib.fdfd_phase_timing_read(_lib.ptr(ph))
+    op.lib.fdfd_phase_timing(0)
+    names = "assemble pivot panel rowgemm copy update extract solve_fwd solve_bwd stencil".split()
+    print("   phases ms:", " ".join(f"{k}={v:.1f}" for k, v in zip(names, ph)), "sum=%.1f" % ph.sum(), flush=True)
     b = np.zeros((n, n), dtype=complex)
     b[n // 2, n // 2] = 1j * OMEGA
     x = d.solve(b, max_refine=0)
