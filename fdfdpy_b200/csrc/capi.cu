@@ -132,14 +132,14 @@ int fdfd_phase_timing(int enable) {
     return 0;
 }
 /* per-phase totals in ms since fdfd_phase_timing(1): assemble, pivot, panel, rowgemm, copy, update,
- * extract, solve_fwd, solve_bwd, stencil (10 doubles). Synchronises the device. */
-int fdfd_phase_timing_read(double* out10) {
+ * expand, solve_fwd, solve_bwd, stencil, ggemm, schur (12 doubles). Synchronises the device. */
+int fdfd_phase_timing_read(double* out12) {
     FDFD_CHECK(cudaDeviceSynchronize());
-    for (int i = 0; i < PH_COUNT; ++i) out10[i] = 0;
+    for (int i = 0; i < PH_COUNT; ++i) out12[i] = 0;
     for (size_t i = 0; i < g_phase_timing.cat.size(); ++i) {
         float ms = 0;
         FDFD_CHECK(cudaEventElapsedTime(&ms, g_phase_timing.ev[2 * i], g_phase_timing.ev[2 * i + 1]));
-        out10[g_phase_timing.cat[i]] += ms;
+        out12[g_phase_timing.cat[i]] += ms;
     }
     return 0;
 }
@@ -331,8 +331,9 @@ int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b, d
     return 0;
 }
 
-int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M, int N, int K, int batch, int mode) {
-    // test hook: C[b] = A[b] B[b] (mode 0) or C[b] -= A[b] B[b] (mode 1), dense row-major, packed batches
+int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M, int N, int K, int batch, int mode,
+                            int transb, int lower) {
+    // test hook: C[b] = A[b] op(B[b]) (mode 0) or C[b] -= A[b] op(B[b]) (mode 1), dense row-major, packed batches
     DevBuf a, b, c;
     size_t sa = (size_t)M * K, sb = (size_t)K * N, sc = (size_t)M * N;
     if (a.alloc(sa * batch) || b.alloc(sb * batch) || c.alloc(sc * batch)) return -1;
@@ -340,8 +341,8 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
     FDFD_CHECK(cudaMemcpy(b.p, B, sizeof(cplx) * sb * batch, cudaMemcpyHostToDevice));
     FDFD_CHECK(cudaMemcpy(c.p, Cm, sizeof(cplx) * sc * batch, cudaMemcpyHostToDevice));
     GemmBatch g;
-    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = N; g.C = c.p; g.sC = sc; g.ldc = N;
-    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode;
+    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = transb ? K : N; g.C = c.p; g.sC = sc; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode; g.transb = transb; g.lower = lower;
     if (zgemm_batched(g, 0)) return -1;
     FDFD_CHECK(cudaDeviceSynchronize());
     FDFD_CHECK(cudaMemcpy(Cm, c.p, sizeof(cplx) * sc * batch, cudaMemcpyDeviceToHost));
@@ -350,7 +351,8 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
 
 int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }
 
-int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int iters, double* ms_per_launch) {
+int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int transb, int lower, int iters,
+                     double* ms_per_launch) {
     // device-only timing of one GEMM shape (uninitialised-but-finite operands), CUDA events
     DevBuf a, b, c;
     size_t sa = (size_t)M * K, sb = (size_t)K * N, sc = (size_t)M * N;
@@ -359,8 +361,8 @@ int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int iters, double
     FDFD_CHECK(cudaMemset(b.p, 0, sizeof(cplx) * sb * batch));
     FDFD_CHECK(cudaMemset(c.p, 0, sizeof(cplx) * sc * batch));
     GemmBatch g;
-    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = N; g.C = c.p; g.sC = sc; g.ldc = N;
-    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode;
+    g.A = a.p; g.sA = sa; g.lda = K; g.B = b.p; g.sB = sb; g.ldb = transb ? K : N; g.C = c.p; g.sC = sc; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.batch = batch; g.mode = mode; g.transb = transb; g.lower = lower;
     cudaEvent_t e0, e1;
     FDFD_CHECK(cudaEventCreate(&e0));
     FDFD_CHECK(cudaEventCreate(&e1));

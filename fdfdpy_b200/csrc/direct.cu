@@ -1,15 +1,18 @@
 // Batched multifrontal nested-dissection solver for the 5-point Maxwell stencil on a torus.
 //
 // Replaces the general sparse LU the reference calls in solver_direct (linalg.py:123-149).
-// Every level of the elimination tree is ONE batch of equally padded dense fronts
-//        F = [ F_EE  F_ER ]      E: unknowns eliminated at this level (leaf interiors / shared lines)
+// The operator is row-scaled by D = diag(sxf[ix] syf[iy]) on the fly: D A is complex SYMMETRIC (the
+// forward stretch factors are the only asymmetry of the sc-PML operator, linalg.py:61-63 / 96-98),
+// so every front keeps only its lower triangle.  Every level of the elimination tree is ONE batch
+// of equally padded dense fronts
+//        F = [ F_EE   .   ]      E: unknowns eliminated at this level (leaf interiors / shared lines)
 //            [ F_RE  F_RR ]      R: the box ring handed to the parent
-// A blocked Gauss-Jordan sweep over the E pivots turns F in place into
-//        [  F_EE^-1        F_EE^-1 F_ER ]
-//        [ -F_RE F_EE^-1   S            ]   S = F_RR - F_RE F_EE^-1 F_ER  (Schur complement)
-// so the triangular solves of a classic multifrontal code become plain batched matrix-vector
-// products in the solve phase.  The rank-T updates of the sweep are complex GEMMs on the FP64
-// tensor pipe (zgemm.cuh); pivot tiles are inverted in shared memory with partial pivoting.
+// and computes, with complex GEMMs on the FP64 tensor pipe (zgemm.cuh),
+//        Einv = F_EE^-1                    blocked Gauss-Jordan, pivoting inside 64-wide tiles
+//        G    = F_RE Einv                  (m x k) = (m x k)(k x k),       K = k
+//        S    = F_RR - G F_RE^T            lower tiles only,               K = k
+// Einv and G are the stored factors; the triangular solves of a classic multifrontal code become
+// plain batched matrix-vector products:  ring = f_R - G f_E,  u_E = Einv f_E - G^T u_R.
 #include <algorithm>
 #include "direct.cuh"
 #include "zgemm.cuh"
@@ -17,8 +20,13 @@
 // ------------------------------------------------------------------------------------------
 // assembly
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx row_scale(const cplx* __restrict__ isxf, const cplx* __restrict__ isyf, int x, int y) {
+    return crecip(cmul(isxf[x], isyf[y]));      // sxf[x] * syf[y]
+}
+
 __global__ void __launch_bounds__(64)
-leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, const int* __restrict__ cls,
+leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, const cplx* __restrict__ isxf,
+                     const cplx* __restrict__ isyf, const int* __restrict__ cls,
                      const int* __restrict__ k_cls, const int* __restrict__ x0, const int* __restrict__ y0,
                      const int* __restrict__ slot_lx, const int* __restrict__ slot_ly,
                      const int* __restrict__ slot_right, const int* __restrict__ slot_up, int kmax, int nmax,
@@ -27,7 +35,8 @@ leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, cons
     const int c = cls[b];
     cplx* Fb = F + b * (long long)nmax * nmax;
     const size_t n = (size_t)nx * ny;
-    for (int e = threadIdx.x; e < nmax * nmax; e += blockDim.x) Fb[e] = make_double2(0.0, 0.0);
+    for (int e = threadIdx.x; e < nmax * nmax; e += blockDim.x)
+        if (e % nmax <= e / nmax) Fb[e] = make_double2(0.0, 0.0);
     __syncthreads();
     const int kc = k_cls[c];
     for (int s = threadIdx.x; s < nmax; s += blockDim.x) {
@@ -39,13 +48,12 @@ leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, cons
         int y = y0[b] + slot_ly[c * nmax + s];
         if (x >= nx) x -= nx;
         if (y >= ny) y -= ny;
-        int xr = x + 1 == nx ? 0 : x + 1, yu = y + 1 == ny ? 0 : y + 1;
-        size_t node = (size_t)x * ny + y, nr = (size_t)xr * ny + y, nu = (size_t)x * ny + yu;
-        Fb[s * nmax + s] = planes[node];                 // c0
-        Fb[s * nmax + r] = planes[2 * n + node];         // cxp: row node, column right neighbour
-        Fb[r * nmax + s] = planes[n + nr];               // cxm of the right neighbour
-        Fb[s * nmax + u] = planes[4 * n + node];         // cyp
-        Fb[u * nmax + s] = planes[3 * n + nu];           // cym of the upper neighbour
+        size_t node = (size_t)x * ny + y;
+        const cplx d = row_scale(isxf, isyf, x, y);
+        // scaled row `node`: its +x / +y couplings equal the scaled -x / -y couplings of the neighbours
+        Fb[s * nmax + s] = cmul(planes[node], d);                                   // c0
+        Fb[max(s, r) * nmax + min(s, r)] = cmul(planes[2 * n + node], d);           // cxp
+        Fb[max(s, u) * nmax + min(s, u)] = cmul(planes[4 * n + node], d);           // cyp
     }
 }
 
@@ -68,12 +76,13 @@ merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const i
     const long long e0 = chunk * per, e1 = min(total, e0 + per);
     for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         int p = (int)(e / nmax), q = (int)(e % nmax);
+        if (q > p) continue;                       // lower triangle only
         cplx v = make_double2(0.0, 0.0);
         int a = i1[p], bq = i1[q];
-        if (a >= 0 && bq >= 0) v = S1[(size_t)(kc + a) * nc + kc + bq];
+        if (a >= 0 && bq >= 0) v = S1[(size_t)(kc + max(a, bq)) * nc + kc + min(a, bq)];
         a = i2[p];
         bq = i2[q];
-        if (a >= 0 && bq >= 0) v = cadd(v, S2[(size_t)(kc + a) * nc + kc + bq]);
+        if (a >= 0 && bq >= 0) v = cadd(v, S2[(size_t)(kc + max(a, bq)) * nc + kc + min(a, bq)]);
         if (p == q && p >= kcls && p < kmax) v = make_double2(1.0, 0.0);
         Fb[e] = v;
     }
@@ -84,8 +93,9 @@ merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const i
 // ------------------------------------------------------------------------------------------
 // P[b] = inverse of the tw x tw pivot tile F[b][j0:j0+tw, j0:j0+tw]; Gauss-Jordan on [A | I] in
 // shared memory with partial (row) pivoting inside the tile.
+// sym != 0: F holds only the lower triangle of a symmetric matrix.
 __global__ void pivot_inverse_kernel(const cplx* __restrict__ F, int nmax, int j0, int tw,
-                                     cplx* __restrict__ P, int tcap, int* __restrict__ info) {
+                                     cplx* __restrict__ P, int tcap, int* __restrict__ info, int sym) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(smem_raw);          // [tw][2*tw]
     cplx* scol = sm + (size_t)tw * 2 * tw;                  // [tw]
@@ -95,7 +105,7 @@ __global__ void pivot_inverse_kernel(const cplx* __restrict__ F, int nmax, int j
     const int w2 = 2 * tw;
     for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
         int r = i / tw, c = i % tw;
-        sm[r * w2 + c] = Fb[(size_t)(j0 + r) * nmax + j0 + c];
+        sm[r * w2 + c] = (sym && c > r) ? Fb[(size_t)(j0 + c) * nmax + j0 + r] : Fb[(size_t)(j0 + r) * nmax + j0 + c];
         sm[r * w2 + tw + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
     }
     __syncthreads();
@@ -180,26 +190,19 @@ copy_rows_kernel(cplx* __restrict__ F, const cplx* __restrict__ Rbuf, int nmax, 
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) Fb[e] = Rb[e];
 }
 
-// EZX[b] = F[b][0:kmax, :],  RW[b] = F[b][kmax:, 0:kmax]
+// Einv[b] (kmax x kmax, full) = symmetric expansion of the lower triangle of F[b][0:kmax, 0:kmax]
 __global__ void __launch_bounds__(256)
-extract_kernel(const cplx* __restrict__ F, cplx* __restrict__ EZX, cplx* __restrict__ RW, int kmax, int mmax,
-               int nmax, int chunks) {
+sym_expand_kernel(const cplx* __restrict__ F, cplx* __restrict__ E, int kmax, int nmax, int chunks) {
     const long long b = blockIdx.x / chunks;
     const int chunk = blockIdx.x % chunks;
     const cplx* Fb = F + b * (long long)nmax * nmax;
-    cplx* Eb = EZX + b * (long long)kmax * nmax;
-    cplx* Rb = RW + b * (long long)mmax * kmax;
-    const long long t1 = (long long)kmax * nmax, t2 = (long long)mmax * kmax;
-    const long long total = t1 + t2;
+    cplx* Eb = E + b * (long long)kmax * kmax;
+    const long long total = (long long)kmax * kmax;
     const long long per = (total + chunks - 1) / chunks;
     const long long e0 = chunk * per, e1 = min(total, e0 + per);
     for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        if (e < t1) Eb[e] = Fb[e];
-        else {
-            long long q = e - t1;
-            int i = (int)(q / kmax), c = (int)(q % kmax);
-            Rb[q] = Fb[(size_t)(kmax + i) * nmax + c];
-        }
+        int p = (int)(e / kmax), q = (int)(e % kmax);
+        Eb[e] = Fb[(size_t)max(p, q) * nmax + min(p, q)];
     }
 }
 
@@ -208,7 +211,8 @@ extract_kernel(const cplx* __restrict__ F, cplx* __restrict__ EZX, cplx* __restr
 // ------------------------------------------------------------------------------------------
 template <int NR>
 __global__ void __launch_bounds__(128)
-leaf_gather_kernel(cplx* __restrict__ f, const cplx* __restrict__ rhs, const int* __restrict__ cls,
+leaf_gather_kernel(cplx* __restrict__ f, const cplx* __restrict__ rhs, const cplx* __restrict__ isxf,
+                   const cplx* __restrict__ isyf, const int* __restrict__ cls,
                    const int* __restrict__ x0, const int* __restrict__ y0, const int* __restrict__ slot_lx,
                    const int* __restrict__ slot_ly, const int* __restrict__ slot_right, int nmax, int nx, int ny,
                    int nr_act, long long nb) {
@@ -225,9 +229,10 @@ leaf_gather_kernel(cplx* __restrict__ f, const cplx* __restrict__ rhs, const int
         if (x >= nx) x -= nx;
         if (y >= ny) y -= ny;
         size_t node = (size_t)x * ny + y, n = (size_t)nx * ny;
+        const cplx d = row_scale(isxf, isyf, x, y);       // the factors belong to D A: solve D A x = D b
 #pragma unroll
         for (int j = 0; j < NR; ++j)
-            if (j < nr_act) v[j] = rhs[j * n + node];
+            if (j < nr_act) v[j] = cmul(rhs[j * n + node], d);
     }
 #pragma unroll
     for (int j = 0; j < NR; ++j) f[gid * NR + j] = v[j];
@@ -294,17 +299,17 @@ child_scatter_kernel(cplx* __restrict__ uc, const cplx* __restrict__ up, const i
     for (int j = 0; j < NR; ++j) uc[(ch * nc + kc + i) * NR + j] = up[(b * nmax + slot) * NR + j];
 }
 
-// forward: yE = Z f_E ; ring = f_R + (-W) f_E.   One warp per output row.
+// forward: yE = Einv f_E ; ring = f_R - G f_E.   One warp per output row.
 template <int NR>
 __global__ void __launch_bounds__(256)
-forward_mv_kernel(const cplx* __restrict__ EZX, const cplx* __restrict__ RW, const cplx* __restrict__ f,
+forward_mv_kernel(const cplx* __restrict__ Einv, const cplx* __restrict__ G, const cplx* __restrict__ f,
                   cplx* __restrict__ yE, cplx* __restrict__ ring, int kmax, int mmax, int nmax, long long nb) {
     long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (gw >= nb * nmax) return;
     long long b = gw / nmax;
     int r = (int)(gw % nmax);
-    const cplx* row = r < kmax ? EZX + (b * kmax + r) * nmax : RW + (b * mmax + (r - kmax)) * kmax;
+    const cplx* row = r < kmax ? Einv + (b * kmax + r) * kmax : G + (b * mmax + (r - kmax)) * kmax;
     const cplx* v = f + b * nmax * NR;
     cplx acc[NR];
 #pragma unroll
@@ -324,40 +329,47 @@ forward_mv_kernel(const cplx* __restrict__ EZX, const cplx* __restrict__ RW, con
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             if (r < kmax) yE[(b * kmax + r) * NR + j] = acc[j];
-            else ring[(b * mmax + (r - kmax)) * NR + j] = cadd(v[r * NR + j], acc[j]);
+            else ring[(b * mmax + (r - kmax)) * NR + j] = csub(v[r * NR + j], acc[j]);
         }
     }
 }
 
-// backward: u_E = yE - X u_R
+// backward: u_E = yE - G^T u_R.  Lanes run along the E index (the contiguous one of G), the 8 warps
+// of a CTA split the ring rows and reduce through shared memory (fixed order: deterministic).
 template <int NR>
 __global__ void __launch_bounds__(256)
-backward_mv_kernel(const cplx* __restrict__ EZX, const cplx* __restrict__ yE, cplx* __restrict__ u, int kmax,
-                   int mmax, int nmax, long long nb) {
-    long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (gw >= nb * kmax) return;
-    long long b = gw / kmax;
-    int r = (int)(gw % kmax);
-    const cplx* row = EZX + (b * kmax + r) * nmax + kmax;
-    const cplx* v = u + (b * nmax + kmax) * NR;
+backward_mvt_kernel(const cplx* __restrict__ G, const cplx* __restrict__ yE, cplx* __restrict__ u, int kmax,
+                    int mmax, int nmax, long long nb) {
+    __shared__ cplx part[8][32][NR];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long gid = (long long)blockIdx.x * 32 + lane;       // (front, E slot)
+    const bool ok = gid < nb * kmax;
+    const long long b = ok ? gid / kmax : 0;
+    const int r = ok ? (int)(gid % kmax) : 0;
     cplx acc[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
-    for (int c = lane; c < mmax; c += 32) {
-        cplx m = ldg_c(row + c);
+    if (ok) {
+        const cplx* col = G + b * (long long)mmax * kmax + r;
+        const cplx* v = u + (b * nmax + kmax) * NR;
+#pragma unroll 4
+        for (int c = w; c < mmax; c += 8) {
+            cplx m = ldg_c(col + (size_t)c * kmax);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+            for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+        }
     }
 #pragma unroll
-    for (int j = 0; j < NR; ++j)
-        for (int o = 16; o > 0; o >>= 1) {
-            acc[j].x += __shfl_down_sync(0xffffffffu, acc[j].x, o);
-            acc[j].y += __shfl_down_sync(0xffffffffu, acc[j].y, o);
-        }
-    if (lane == 0) {
+    for (int j = 0; j < NR; ++j) part[w][lane][j] = acc[j];
+    __syncthreads();
+    if (w == 0 && ok) {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) u[(b * nmax + r) * NR + j] = csub(yE[(b * kmax + r) * NR + j], acc[j]);
+        for (int j = 0; j < NR; ++j) {
+            cplx t = part[0][lane][j];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) t = cadd(t, part[q][lane][j]);
+            u[(b * nmax + r) * NR + j] = csub(yE[(b * kmax + r) * NR + j], t);
+        }
     }
 }
 
@@ -424,9 +436,9 @@ int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
 }
 
 static void free_level_factors(NdLevel& L) {
-    if (L.EZX) cudaFree(L.EZX);
-    if (L.RW) cudaFree(L.RW);
-    L.EZX = L.RW = nullptr;
+    if (L.Einv) cudaFree(L.Einv);
+    if (L.G) cudaFree(L.G);
+    L.Einv = L.G = nullptr;
 }
 
 void nd_destroy(NdSolver* s) {
@@ -453,15 +465,17 @@ static int chunks_for(long long per_front_elems, long long nb) {
 }
 
 // one arena for all transient factorisation buffers: two ping-pong front batches plus the pivot /
-// column-panel / row-panel scratch, sized for the largest level; allocated once and kept
+// column-panel / row-panel scratch of the blocked inversion, sized for the largest level; allocated
+// once and kept
 static int ensure_factor_workspace(NdSolver* s) {
     size_t maxF = 0, maxP = 0, maxC = 0;
     for (auto& L : s->levels) {
-        const size_t nb = L.nb, nmax = L.nmax;
-        const size_t tcap = L.kmax < s->tile ? L.kmax : s->tile;
+        const size_t nb = L.nb, nmax = L.nmax, kmax = L.kmax;
         maxF = std::max(maxF, nb * nmax * nmax);
-        maxP = std::max(maxP, nb * tcap * tcap);
-        maxC = std::max(maxC, nb * nmax * tcap);
+        if (L.kmax > s->tile) {
+            maxP = std::max(maxP, nb * (size_t)s->tile * s->tile);
+            maxC = std::max(maxC, nb * kmax * s->tile);
+        }
     }
     size_t need = 2 * maxF + maxP + 2 * maxC;
     if (need > s->fws_cap) {
@@ -476,6 +490,60 @@ static int ensure_factor_workspace(NdSolver* s) {
     s->fws_P = s->fws + 2 * maxF;
     s->fws_C = s->fws_P + maxP;
     s->fws_R = s->fws_C + maxC;
+    return 0;
+}
+
+// In-place blocked Gauss-Jordan inversion of a batch of full n x n matrices (n > tile):
+// per 64-wide pivot tile J:  P = E_JJ^-1 (shared memory, partial pivoting inside the tile),
+// column panel saved / zeroed, R = P E_J,: , rank-T update E -= C R.
+static int gj_invert_batch(NdSolver* s, cplx* E, int n, long long nb, cudaStream_t st) {
+    const int tcap = s->tile;
+    cplx *Pbuf = s->fws_P, *Cbuf = s->fws_C, *Rbuf = s->fws_R;
+    for (int j0 = 0; j0 < n; j0 += tcap) {
+        const int tw = (n - j0) < tcap ? (n - j0) : tcap;
+        size_t smem = sizeof(cplx) * ((size_t)tw * 2 * tw + tw);
+        int threads = tw * tw >= 512 ? 256 : (tw * tw >= 128 ? 128 : 64);
+        if (smem > 48 * 1024)
+            FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        {
+            PhaseScope ph(PH_PIVOT, st);
+            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(E, n, j0, tw, Pbuf, tcap, s->d_info, 0);
+            ++g_fdfd_launches;
+        }
+        int chunks = chunks_for((long long)n * tw, nb);
+        {
+            PhaseScope ph(PH_PANEL, st);
+            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(E, Cbuf, n, j0, tw, tcap, chunks);
+            ++g_fdfd_launches;
+        }
+        FDFD_CHECK(cudaGetLastError());
+        GemmBatch g;
+        g.transb = 0; g.lower = 0;
+        g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
+        g.B = E + (size_t)j0 * n; g.sB = (long long)n * n; g.ldb = n;
+        g.C = Rbuf; g.sC = (long long)tcap * n; g.ldc = n;
+        g.M = tw; g.N = n; g.K = tw; g.batch = (int)nb; g.mode = 0;
+        {
+            PhaseScope ph(PH_ROWGEMM, st);
+            if (zgemm_batched(g, st)) return -1;
+        }
+        {
+            PhaseScope ph(PH_COPY, st);
+            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(E, Rbuf, n, j0, tw, tcap, chunks);
+            ++g_fdfd_launches;
+        }
+        FDFD_CHECK(cudaGetLastError());
+        g.A = Cbuf; g.sA = (long long)n * tcap; g.lda = tcap;
+        g.B = Rbuf; g.sB = (long long)tcap * n; g.ldb = n;
+        g.C = E; g.sC = (long long)n * n; g.ldc = n;
+        g.M = n; g.N = n; g.K = tw; g.mode = 1;
+        {
+            PhaseScope ph(PH_UPDATE, st);
+            if (zgemm_batched(g, st)) return -1;
+        }
+        s->factor_flops += 8.0 * (double)nb * ((double)n * n * tw + (double)tw * tw * n);
+    }
     return 0;
 }
 
@@ -494,79 +562,70 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         NdLevel& L = s->levels[li];
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
-        const int tcap = kmax < s->tile ? kmax : s->tile;
-        cplx *F = s->fws_F[li & 1], *Pbuf = s->fws_P, *Cbuf = s->fws_C, *Rbuf = s->fws_R;
+        cplx* F = s->fws_F[li & 1];
         // factor storage is allocated on the first factorisation and reused afterwards
-        if (!L.EZX) FDFD_CHECK(cudaMalloc(&L.EZX, sizeof(cplx) * (size_t)nb * kmax * nmax));
-        if (mmax > 0 && !L.RW) FDFD_CHECK(cudaMalloc(&L.RW, sizeof(cplx) * (size_t)nb * mmax * kmax));
+        if (!L.Einv) FDFD_CHECK(cudaMalloc(&L.Einv, sizeof(cplx) * (size_t)nb * kmax * kmax));
+        if (mmax > 0 && !L.G) FDFD_CHECK(cudaMalloc(&L.G, sizeof(cplx) * (size_t)nb * mmax * kmax));
         {
-        PhaseScope ph(PH_ASSEMBLE, st);
-        if (L.kind == 0) {
-            leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, L.cls, L.k_cls, L.x0, L.y0, L.slot_lx,
-                                                              L.slot_ly, L.slot_right, L.slot_up, kmax, nmax,
-                                                              s->nx, s->ny);
+            PhaseScope ph(PH_ASSEMBLE, st);
+            if (L.kind == 0) {
+                leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, op->isxf, op->isyf, L.cls, L.k_cls,
+                                                                  L.x0, L.y0, L.slot_lx, L.slot_ly, L.slot_right,
+                                                                  L.slot_up, kmax, nmax, s->nx, s->ny);
+            } else {
+                int chunks = chunks_for((long long)nmax * nmax, nb);
+                merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
+                                                                               L.inv1, L.inv2, kmax, nmax, prev_k,
+                                                                               prev_n, chunks);
+            }
             ++g_fdfd_launches;
-        } else {
-            int chunks = chunks_for((long long)nmax * nmax, nb);
-            merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
-                                                                           L.inv1, L.inv2, kmax, nmax, prev_k,
-                                                                           prev_n, chunks);
-            ++g_fdfd_launches;
-        }
         }
         FDFD_CHECK(cudaGetLastError());
-        for (int j0 = 0; j0 < kmax; j0 += tcap) {
-            const int tw = (kmax - j0) < tcap ? (kmax - j0) : tcap;
-            size_t smem = sizeof(cplx) * ((size_t)tw * 2 * tw + tw);
-            int threads = tw * tw >= 512 ? 256 : (tw * tw >= 128 ? 128 : 64);
+        // ---- Einv = F_EE^-1
+        if (kmax <= s->tile) {
+            size_t smem = sizeof(cplx) * ((size_t)kmax * 2 * kmax + kmax);
+            int threads = kmax * kmax >= 512 ? 256 : (kmax * kmax >= 128 ? 128 : 64);
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
-            {
-                PhaseScope ph(PH_PIVOT, st);
-                pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, j0, tw, Pbuf, tcap, s->d_info);
-                ++g_fdfd_launches;
-            }
-            int chunks = chunks_for((long long)nmax * tw, nb);
-            {
-                PhaseScope ph(PH_PANEL, st);
-                panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Cbuf, nmax, j0, tw, tcap, chunks);
-                ++g_fdfd_launches;
-            }
-            FDFD_CHECK(cudaGetLastError());
-            GemmBatch g;
-            g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
-            g.B = F + (size_t)j0 * nmax; g.sB = (long long)nmax * nmax; g.ldb = nmax;
-            g.C = Rbuf; g.sC = (long long)tcap * nmax; g.ldc = nmax;
-            g.M = tw; g.N = nmax; g.K = tw; g.batch = (int)nb; g.mode = 0;
-            {
-                PhaseScope ph(PH_ROWGEMM, st);
-                if (zgemm_batched(g, st)) return -1;
-            }
-            {
-                PhaseScope ph(PH_COPY, st);
-                copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Rbuf, nmax, j0, tw, tcap, chunks);
-                ++g_fdfd_launches;
-            }
-            FDFD_CHECK(cudaGetLastError());
-            g.A = Cbuf; g.sA = (long long)nmax * tcap; g.lda = tcap;
-            g.B = Rbuf; g.sB = (long long)tcap * nmax; g.ldb = nmax;
-            g.C = F; g.sC = (long long)nmax * nmax; g.ldc = nmax;
-            g.M = nmax; g.N = nmax; g.K = tw; g.mode = 1;
-            {
-                PhaseScope ph(PH_UPDATE, st);
-                if (zgemm_batched(g, st)) return -1;
-            }
-            s->factor_flops += 8.0 * (double)nb * ((double)nmax * nmax * tw + (double)tw * tw * nmax);
-        }
-        s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * nmax + (size_t)nb * mmax * kmax);
-        {
-            PhaseScope ph(PH_EXTRACT, st);
-            int chunks = chunks_for((long long)kmax * nmax + (long long)mmax * kmax, nb);
-            extract_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.EZX, L.RW, kmax, mmax, nmax, chunks);
+            PhaseScope ph(PH_PIVOT, st);
+            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, 0, kmax, L.Einv, kmax, s->d_info, 1);
             ++g_fdfd_launches;
-            FDFD_CHECK(cudaGetLastError());
+        } else {
+            {
+                PhaseScope ph(PH_EXTRACT, st);
+                int chunks = chunks_for((long long)kmax * kmax, nb);
+                sym_expand_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.Einv, kmax, nmax, chunks);
+                ++g_fdfd_launches;
+            }
+            if (gj_invert_batch(s, L.Einv, kmax, nb, st)) return -1;
         }
+        FDFD_CHECK(cudaGetLastError());
+        if (mmax > 0) {
+            GemmBatch g;
+            // ---- G = F_RE Einv = F_RE Einv^T (Einv is symmetric: both operands k-contiguous)
+            g.transb = 1; g.lower = 0; g.mode = 0; g.batch = (int)nb;
+            g.A = F + (size_t)kmax * nmax; g.sA = (long long)nmax * nmax; g.lda = nmax;
+            g.B = L.Einv; g.sB = (long long)kmax * kmax; g.ldb = kmax;
+            g.C = L.G; g.sC = (long long)mmax * kmax; g.ldc = kmax;
+            g.M = mmax; g.N = kmax; g.K = kmax;
+            {
+                PhaseScope ph(PH_GGEMM, st);
+                if (zgemm_batched(g, st)) return -1;
+            }
+            // ---- S = F_RR - G F_RE^T, lower tiles only, in place (the parent assembles from it)
+            g.transb = 1; g.lower = 1; g.mode = 1;
+            g.A = L.G; g.sA = (long long)mmax * kmax; g.lda = kmax;
+            g.B = F + (size_t)kmax * nmax; g.sB = (long long)nmax * nmax; g.ldb = nmax;
+            g.C = F + (size_t)kmax * nmax + kmax; g.sC = (long long)nmax * nmax; g.ldc = nmax;
+            g.M = mmax; g.N = mmax; g.K = kmax;
+            {
+                PhaseScope ph(PH_SCHUR, st);
+                if (zgemm_batched(g, st)) return -1;
+            }
+            s->factor_flops += 8.0 * (double)nb * ((double)mmax * kmax * kmax + 0.5 * (double)mmax * mmax * kmax);
+        }
+        s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * kmax + (size_t)nb * mmax * kmax);
         Fprev = F;
         prev_k = kmax;
         prev_n = nmax;
@@ -617,12 +676,12 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         const long long nb = L.nb;
         long long tot = nb * L.nmax;
         if (L.kind == 0)
-            { leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
+            { leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, op->isxf, op->isyf, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
                                                                        L.slot_right, L.nmax, s->nx, s->ny, nr_act, nb); ++g_fdfd_launches; }
         else
             { merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
                                                                         L.inv2, L.nmax, L.child_mmax, nb); ++g_fdfd_launches; }
-        { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.EZX, L.RW, f, s->ws_ye + L.ye_off, ring_cur,
+        { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
                                                                        L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         std::swap(ring_prev, ring_cur);
@@ -641,8 +700,8 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
             { child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
                                                                          P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb); ++g_fdfd_launches; }
         }
-        { backward_mv_kernel<NR><<<ceil_div(nb * L.kmax * 32, 256), 256, 0, st>>>(L.EZX, s->ws_ye + L.ye_off, u, L.kmax,
-                                                                                L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        { backward_mvt_kernel<NR><<<ceil_div(nb * L.kmax, 32), 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
+                                                                           L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         if (L.kind == 0) {
             long long tot = nb * L.nmax;
             { leaf_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, d_x, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,

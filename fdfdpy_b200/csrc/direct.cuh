@@ -25,8 +25,8 @@ struct NdLevel {
     int kind, nb, kmax, mmax, nmax, ncls, child_mmax;
     int *cls, *k_cls, *ch1, *ch2, *c1map, *c2map, *inv1, *inv2;
     int *x0, *y0, *slot_lx, *slot_ly, *slot_right, *slot_up;
-    cplx* EZX;    // [nb][kmax][nmax]   rows of the swept front:  [ F_EE^-1 | F_EE^-1 F_ER ]
-    cplx* RW;     // [nb][mmax][kmax]   -F_RE F_EE^-1
+    cplx* Einv;   // [nb][kmax][kmax]   F_EE^-1 of the row-scaled (symmetric) front, full storage
+    cplx* G;      // [nb][mmax][kmax]   F_RE F_EE^-1
     cplx* yE;     // solve workspace [nb][kmax][nrhs]
     size_t ye_off;
 };

@@ -1,7 +1,11 @@
 // Batched complex128 GEMM on the FP64 tensor pipe (DMMA, mma.sync m8n8k4 f64) for sm_100a.
 //
-//   C[b] (M x N)  =  C[b] - A[b] (M x K) * B[b] (K x N)      (mode 1, the Schur / sweep update)
-//   C[b]          =  A[b] * B[b]                              (mode 0)
+//   C[b] (M x N)  =  C[b] - A[b] (M x K) * op(B[b])          (mode 1, the Schur / sweep update)
+//   C[b]          =  A[b] * op(B[b])                          (mode 0)
+// op(B) = B (K x N, transb 0) or B^T with B stored N x K (transb 1: both operands have k contiguous,
+// the natural form of the symmetric Schur update  S -= G F_RE^T).  lower != 0 computes only the
+// 64x64 tiles on or below the diagonal (M == N; the strict upper triangle of C is never touched
+// outside diagonal tiles).
 //
 // All matrices are row-major interleaved complex (re, im) with leading dimensions and 64-bit
 // batch strides.  A complex product is four real DMMA products; the tiles are split into real
@@ -19,6 +23,8 @@ struct GemmBatch {
     cplx* C; long long sC; int ldc;
     int M, N, K, batch;
     int mode;   // 0: C = AB, 1: C -= AB
+    int transb; // 0: B is K x N, 1: B is N x K (C = A B^T)
+    int lower;  // 1: only tiles with tile_row >= tile_col
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -40,12 +46,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // are LDS.128.  Leading dimensions LDA = 4 mod 8 and LDB = 2 mod 8 complex make every 8-lane phase of
 // those loads hit eight different 16-byte bank groups.
 // (mma.sync m16n8k16 f64 was tried: ptxas lowers it to eight DMMA.8x8x4 on sm_100a and it ran ~6 % slower.)
-template <int WM, int WN, int STAGES>
+template <int WM, int WN, int STAGES, bool TB>
 __global__ void __launch_bounds__(WM * WN * 32)
 zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     constexpr int BM = 16 * WM, BN = 32 * WN, BK = 16, NT = WM * WN * 32;
-    constexpr int LDA = BK + 4, LDB = BN + 2;
-    constexpr int A_ELEMS = BM * LDA, B_ELEMS = BK * LDB;
+    constexpr int LDA = BK + 4, LDB = TB ? BK + 4 : BN + 2;
+    constexpr int A_ELEMS = BM * LDA, B_ELEMS = TB ? BN * LDB : BK * LDB;
     extern __shared__ __align__(16) unsigned char zg_smem[];
     cplx* As = reinterpret_cast<cplx*>(zg_smem);            // [STAGES][BM][LDA]
     cplx* Bs = As + STAGES * A_ELEMS;                        // [STAGES][BK][LDB]
@@ -55,6 +61,7 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     bid /= tiles_n;
     const int tm = (int)(bid % tiles_m);
     const long long b = bid / tiles_m;
+    if (g.lower && tn * BN > tm * BM + BM - 1) return;       // tile strictly above the diagonal
     const cplx* __restrict__ A = g.A + b * g.sA;
     const cplx* __restrict__ B = g.B + b * g.sB;
     cplx* __restrict__ C = g.C + b * g.sC;
@@ -80,12 +87,22 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
             bool ok = gm < g.M && gk < g.K;
             cp_async16(as + r * LDA + c, ok ? A + (size_t)gm * g.lda + gk : A, ok);
         }
+        if (TB) {
 #pragma unroll
-        for (int i = tid; i < BK * BN; i += NT) {
-            int r = i / BN, c = i % BN;
-            int gk = k0 + r, gn = n_base + c;
-            bool ok = gk < g.K && gn < g.N;
-            cp_async16(bs + r * LDB + c, ok ? B + (size_t)gk * g.ldb + gn : B, ok);
+            for (int i = tid; i < BN * BK; i += NT) {
+                int r = i / BK, c = i % BK;
+                int gn = n_base + r, gk = k0 + c;
+                bool ok = gn < g.N && gk < g.K;
+                cp_async16(bs + r * LDB + c, ok ? B + (size_t)gn * g.ldb + gk : B, ok);
+            }
+        } else {
+#pragma unroll
+            for (int i = tid; i < BK * BN; i += NT) {
+                int r = i / BN, c = i % BN;
+                int gk = k0 + r, gn = n_base + c;
+                bool ok = gk < g.K && gn < g.N;
+                cp_async16(bs + r * LDB + c, ok ? B + (size_t)gk * g.ldb + gn : B, ok);
+            }
         }
     };
 
@@ -112,7 +129,8 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
                 nai[mt] = -a[mt].y;
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bq[nt] = bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+            for (int nt = 0; nt < 4; ++nt)
+                bq[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -150,16 +168,36 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     }
 }
 
-// Persistent variant for the large sweep updates: one CTA per SM walks its share of the 64x64
-// output tiles; the cp.async ring runs ACROSS tiles (no pipeline refill per tile) and the C tile of
-// a mode-1 update is prefetched into registers under the last k-tile's DMMAs, so neither the
-// operand nor the accumulator-read latency is exposed.
-template <int STAGES>
+// Persistent variant for the large updates: one CTA per SM walks its share of the 64x64 output
+// tiles; the cp.async ring runs ACROSS tiles (no pipeline refill per tile) and the C tile of a
+// mode-1 update is prefetched into registers under the last k-tile's DMMAs, so neither the
+// operand nor the accumulator-read latency is exposed.  With `lower` the tile list of a batch is
+// the triangle  t = tm (tm + 1) / 2 + tn,  tn <= tm  (row-major, so concurrently running CTAs
+// share the A panel of one or two tile rows).
+struct TileCoord { unsigned b, tm, tn; };
+__device__ __forceinline__ TileCoord decode_tile(unsigned tile, unsigned tiles_per_batch, unsigned tiles_n, int lower) {
+    TileCoord t;
+    t.b = tile / tiles_per_batch;
+    unsigned r = tile - t.b * tiles_per_batch;
+    if (lower) {
+        unsigned tm = (unsigned)((sqrtf(8.0f * (float)r + 1.0f) - 1.0f) * 0.5f);
+        while ((tm + 1) * (tm + 2) / 2 <= r) ++tm;
+        while (tm * (tm + 1) / 2 > r) --tm;
+        t.tm = tm;
+        t.tn = r - tm * (tm + 1) / 2;
+    } else {
+        t.tm = r / tiles_n;
+        t.tn = r - t.tm * tiles_n;
+    }
+    return t;
+}
+
+template <int STAGES, bool TB>
 __global__ void __launch_bounds__(256, 1)
-zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long total_tiles) {
+zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles) {
     constexpr int WN = 2, BM = 64, BN = 64, BK = 16, NT = 256;
-    constexpr int LDA = BK + 4, LDB = BN + 2;
-    constexpr int A_ELEMS = BM * LDA, B_ELEMS = BK * LDB;
+    constexpr int LDA = BK + 4, LDB = TB ? BK + 4 : BN + 2;
+    constexpr int A_ELEMS = BM * LDA, B_ELEMS = TB ? BN * LDB : BK * LDB;
     extern __shared__ __align__(16) unsigned char zg_smem[];
     cplx* As = reinterpret_cast<cplx*>(zg_smem);
     cplx* Bs = As + STAGES * A_ELEMS;
@@ -170,19 +208,17 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long to
     const int KT = (g.K + BK - 1) / BK;
     const unsigned ntiles = (unsigned)total_tiles;
     if (blockIdx.x >= ntiles) return;
-    const unsigned tiles_per_batch = (unsigned)tiles_m * (unsigned)tiles_n;
 
     // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor); no divisions in the hot loop
     unsigned ld_tile = blockIdx.x;
     int ld_kt = 0, ld_stage = 0, ld_m = 0, ld_n = 0;
     const cplx *ld_A = g.A, *ld_B = g.B;
     auto decode_load = [&]() {
-        unsigned b = ld_tile / tiles_per_batch, r = ld_tile - b * tiles_per_batch;
-        unsigned tm = r / (unsigned)tiles_n, tn = r - tm * (unsigned)tiles_n;
-        ld_m = (int)tm * BM;
-        ld_n = (int)tn * BN;
-        ld_A = g.A + (long long)b * g.sA;
-        ld_B = g.B + (long long)b * g.sB;
+        TileCoord t = decode_tile(ld_tile, tiles_per_batch, (unsigned)tiles_n, g.lower);
+        ld_m = (int)t.tm * BM;
+        ld_n = (int)t.tn * BN;
+        ld_A = g.A + (long long)t.b * g.sA;
+        ld_B = g.B + (long long)t.b * g.sB;
     };
     decode_load();
     auto issue_load = [&]() {
@@ -196,12 +232,22 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long to
             bool ok = gm < g.M && gk < g.K;
             cp_async16(as + r * LDA + c, ok ? ld_A + (size_t)gm * g.lda + gk : ld_A, ok);
         }
+        if (TB) {
 #pragma unroll
-        for (int i = tid; i < BK * BN; i += NT) {
-            int r = i / BN, c = i % BN;
-            int gk = k0 + r, gn = ld_n + c;
-            bool ok = gk < g.K && gn < g.N;
-            cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gk * g.ldb + gn : ld_B, ok);
+            for (int i = tid; i < BN * BK; i += NT) {
+                int r = i / BK, c = i % BK;
+                int gn = ld_n + r, gk = k0 + c;
+                bool ok = gn < g.N && gk < g.K;
+                cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gn * g.ldb + gk : ld_B, ok);
+            }
+        } else {
+#pragma unroll
+            for (int i = tid; i < BK * BN; i += NT) {
+                int r = i / BN, c = i % BN;
+                int gk = k0 + r, gn = ld_n + c;
+                bool ok = gk < g.K && gn < g.N;
+                cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gk * g.ldb + gn : ld_B, ok);
+            }
         }
         ld_stage = ld_stage + 1 == STAGES ? 0 : ld_stage + 1;
         if (++ld_kt == KT) {
@@ -220,10 +266,9 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long to
     cplx cpre[2][4][2];
     int stage = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        unsigned b = tile / tiles_per_batch, rr = tile - b * tiles_per_batch;
-        unsigned tm = rr / (unsigned)tiles_n, tn = rr - tm * (unsigned)tiles_n;
-        cplx* __restrict__ C = g.C + (long long)b * g.sC;
-        const int m_base = (int)tm * BM, n_base = (int)tn * BN;
+        const TileCoord tc = decode_tile(tile, tiles_per_batch, (unsigned)tiles_n, g.lower);
+        cplx* __restrict__ C = g.C + (long long)tc.b * g.sC;
+        const int m_base = (int)tc.tm * BM, n_base = (int)tc.tn * BN;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -261,7 +306,8 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long to
                 nai[mt] = -a[mt].y;
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bq[nt] = bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+            for (int nt = 0; nt < 4; ++nt)
+                bq[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -302,9 +348,9 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, long long to
     cp_async_wait<0>();
 }
 
-template <int WM, int WN, int STAGES>
+template <int WM, int WN, int STAGES, bool TB>
 constexpr size_t zgemm_smem_bytes() {
-    return sizeof(cplx) * STAGES * ((16 * WM) * (16 + 4) + 16 * (32 * WN + 2));
+    return sizeof(cplx) * STAGES * ((16 * WM) * (16 + 4) + (TB ? (32 * WN) * (16 + 4) : 16 * (32 * WN + 2)));
 }
 
 // optional live timing of every GEMM launch (CUDA events on the launching stream); see capi.cu
@@ -317,54 +363,67 @@ struct ZgemmTiming {
 extern ZgemmTiming g_zgemm_timing;
 extern int g_zgemm_variant;   // 0: persistent kernel for large problems, 1: always the tiled kernel
 
+template <bool TB>
+static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
+    if (g.M <= 32 && g.N <= 32) {
+        int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
+        long long blocks = (long long)tm * tn * g.batch;
+        constexpr size_t sm = zgemm_smem_bytes<2, 1, 2, TB>();
+        zgemm_dmma_kernel<2, 1, 2, TB><<<(unsigned)blocks, 64, sm, stream>>>(g, tm, tn);
+        ++g_fdfd_launches;
+        return 0;
+    }
+    int tm = (g.M + 63) / 64, tn = (g.N + 63) / 64;
+    long long per_batch = g.lower ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
+    long long blocks = per_batch * g.batch;
+    if (blocks > 2147483647LL || (long long)tm * tn * g.batch > 2147483647LL) {
+        snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
+        return -1;
+    }
+    if (g_zgemm_variant == 0 && blocks >= 148) {
+        constexpr int ST = 4;
+        constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB>();
+        static bool attr_p = false;
+        if (!attr_p) {
+            cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sm);
+            attr_p = true;
+        }
+        zgemm_dmma_persistent_kernel<ST, TB><<<148, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+    } else {
+        constexpr size_t sm = zgemm_smem_bytes<4, 2, 3, TB>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            attr_set = true;
+        }
+        zgemm_dmma_kernel<4, 2, 3, TB><<<(unsigned)((long long)tm * tn * g.batch), 256, sm, stream>>>(g, tm, tn);
+    }
+    ++g_fdfd_launches;
+    return 0;
+}
+
 static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return 0;
+    if (g.lower && g.M != g.N) {
+        snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm: lower needs a square C");
+        return -1;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_zgemm_timing.on) {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    if (g.M <= 32 && g.N <= 32) {
-        int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
-        long long blocks = (long long)tm * tn * g.batch;
-        constexpr size_t sm = zgemm_smem_bytes<2, 1, 2>();
-        zgemm_dmma_kernel<2, 1, 2><<<(unsigned)blocks, 64, sm, stream>>>(g, tm, tn);
-        ++g_fdfd_launches;
-    } else {
-        int tm = (g.M + 63) / 64, tn = (g.N + 63) / 64;
-        long long blocks = (long long)tm * tn * g.batch;
-        if (blocks > 2147483647LL) {
-            snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
-            return -1;
-        }
-        if (g_zgemm_variant == 0 && blocks >= 148) {
-            constexpr int ST = 4;
-            constexpr size_t sm = sizeof(cplx) * ST * (64 * 20 + 16 * 66);
-            static bool attr_p = false;
-            if (!attr_p) {
-                cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sm);
-                attr_p = true;
-            }
-            zgemm_dmma_persistent_kernel<ST><<<148, 256, sm, stream>>>(g, tm, tn, blocks);
-            ++g_fdfd_launches;
-        } else {
-            constexpr size_t sm = zgemm_smem_bytes<4, 2, 3>();
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                attr_set = true;
-            }
-            zgemm_dmma_kernel<4, 2, 3><<<(unsigned)blocks, 256, sm, stream>>>(g, tm, tn);
-            ++g_fdfd_launches;
-        }
-    }
+    int rc = g.transb ? zgemm_launch<true>(g, stream) : zgemm_launch<false>(g, stream);
+    if (rc) return rc;
     if (g_zgemm_timing.on) {
         cudaEventRecord(e1, stream);
         g_zgemm_timing.ev.push_back(e0);
         g_zgemm_timing.ev.push_back(e1);
-        g_zgemm_timing.flops.push_back(8.0 * g.M * (double)g.N * g.K * g.batch);
+        // flops actually computed: a lower-masked launch does (about) half of M*N*K
+        double mn = g.lower ? 0.5 * (double)g.M * ((double)g.N + 64.0) : (double)g.M * (double)g.N;
+        g_zgemm_timing.flops.push_back(8.0 * mn * g.K * g.batch);
         g_zgemm_timing.big.push_back((g.M <= 32 && g.N <= 32) ? 0 : 1);
     }
     cudaError_t e = cudaGetLastError();

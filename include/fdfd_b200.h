@@ -39,7 +39,7 @@ int fdfd_gemm_timing(int enable);
 int fdfd_gemm_timing_read(double* out6);
 int fdfd_dmma_peak(double* tflops);
 int fdfd_phase_timing(int enable);
-int fdfd_phase_timing_read(double* out10);   /* ms: assemble,pivot,panel,rowgemm,copy,update,extract,solve_fwd,solve_bwd,stencil */
+int fdfd_phase_timing_read(double* out12);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur */
 int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflops);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
@@ -128,14 +128,17 @@ int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl,
                          double neff, int order, int averaged, double* vals, double* vecs);
 
 /* ---- test hook for the batched complex GEMM that carries the factorisation (zgemm.cuh):
- * C[b] = A[b] B[b] (mode 0) or C[b] -= A[b] B[b] (mode 1); packed row-major batches on the host. */
+ * C[b] = A[b] op(B[b]) (mode 0) or C[b] -= A[b] op(B[b]) (mode 1); packed row-major batches on the
+ * host.  transb: 0 = B is K x N, 1 = B is N x K (C = A B^T).  lower != 0 (M == N): only the 64x64
+ * tiles on or below the diagonal are computed, the rest of C is left untouched.                  */
 int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, int N, int K, int batch,
-                            int mode);
+                            int mode, int transb, int lower);
 
 /* kernel selection for A/B measurements: 0 = persistent kernel for large problems (default), 1 = tiled only */
 int fdfd_zgemm_set_variant(int v);
 /* device-only timing of one batched GEMM shape (CUDA events, `iters` launches) */
-int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int iters, double* ms_per_launch);
+int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int transb, int lower, int iters,
+                     double* ms_per_launch);
 
 #ifdef __cplusplus
 }

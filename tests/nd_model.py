@@ -1,13 +1,24 @@
 """numpy model of the GPU direct solver: executes an ndplan exactly the way the CUDA kernels do
-(padded batched fronts, blocked Gauss-Jordan sweep, level-by-level forward/backward solve).
-Used to validate the plan on CPU and as a line-by-line reference for the kernels."""
+(padded batched fronts, symmetric front algebra on the row-scaled operator, blocked Gauss-Jordan
+inversion of the eliminated block, level-by-level forward/backward solve).
+Used to validate the plan on CPU and as a line-by-line reference for the kernels.
+
+Row scaling: D A with D = diag(sxf[ix] * syf[iy]) is complex SYMMETRIC (the forward stretch factors
+are the only asymmetry of the sc-PML operator), so only the lower triangle of a front is kept and
+    E^-1,   G = F_RE E^-1,   S = F_RR - G F_RE^T
+is all a level computes; the substitution uses  u_E = E^-1 f_E - G^T u_R."""
 import numpy as np
 
 
-def sweep(F, k, tile=32):
-    """In-place blocked Gauss-Jordan sweep of the leading k pivots of every front in the batch.
-    Afterwards F = [[Z, Z*F_ER], [-F_RE*Z, S]] with Z = F_EE^-1, S the Schur complement."""
-    nb, n, _ = F.shape
+def row_scale(isxf, isyf):
+    """d[node] = sxf[ix] * syf[iy] = 1 / (isxf[ix] * isyf[iy])"""
+    return (1.0 / (np.asarray(isxf)[:, None] * np.asarray(isyf)[None, :])).reshape(-1)
+
+
+def gj_inverse(E, tile=32):
+    """Blocked Gauss-Jordan inversion of every matrix in the batch (pivoting inside tiles only)."""
+    F = E.copy()
+    nb, k, _ = F.shape
     for j0 in range(0, k, tile):
         J = slice(j0, min(j0 + tile, k))
         P = np.linalg.inv(F[:, J, J])
@@ -22,12 +33,18 @@ def sweep(F, k, tile=32):
     return F
 
 
-def factor(levels, planes, nx, ny, tile=32):
+def _lower_to_full(L):
+    """Symmetric matrix from its lower triangle (the upper one of the input is ignored)."""
+    T = np.tril(L)
+    return T + np.transpose(np.tril(L, -1), (0, 2, 1))
+
+
+def factor(levels, planes, nx, ny, dscale, tile=32):
     c0, cxm, cxp, cym, cyp = [p.reshape(-1) for p in planes]
     store = []
     S_prev = None
     for lv in levels:
-        F = np.zeros((lv.nb, lv.nmax, lv.nmax), dtype=np.complex128)
+        F = np.zeros((lv.nb, lv.nmax, lv.nmax), dtype=np.complex128)       # lower triangle only
         for b in range(lv.nb):
             c = lv.cls[b]
             for s in range(lv.k_cls[c], lv.kmax):          # identity on padded pivots
@@ -42,34 +59,35 @@ def factor(levels, planes, nx, ny, tile=32):
                     x = (lv.x0[b] + lv.slot_lx[c, s]) % nx
                     y = (lv.y0[b] + lv.slot_ly[c, s]) % ny
                     node = x * ny + y
-                    nr = ((x + 1) % nx) * ny + y
-                    nu = x * ny + (y + 1) % ny
-                    F[b, s, s] += c0[node]
-                    F[b, s, r] += cxp[node]
-                    F[b, r, s] += cxm[nr]
-                    F[b, s, u] += cyp[node]
-                    F[b, u, s] += cym[nu]
+                    F[b, s, s] += c0[node] * dscale[node]
+                    F[b, max(s, r), min(s, r)] += cxp[node] * dscale[node]
+                    F[b, max(s, u), min(s, u)] += cyp[node] * dscale[node]
         else:
             mc = lv.child_mmax
             for b in range(lv.nb):
                 c = lv.cls[b]
                 for ch, cmap in ((lv.ch1[b], lv.c1map[c]), (lv.ch2[b], lv.c2map[c])):
                     idx = cmap[:mc]
-                    ok = idx >= 0
-                    ii = idx[ok]
-                    F[b][np.ix_(ii, ii)] += S_prev[ch][np.ix_(np.where(ok)[0], np.where(ok)[0])]
-        sweep(F, lv.kmax, tile)
+                    ok = np.where(idx >= 0)[0]
+                    for a in ok:
+                        for bb in ok:
+                            p, q = idx[a], idx[bb]
+                            if p >= q:
+                                F[b, p, q] += S_prev[ch][max(a, bb), min(a, bb)]
         k = lv.kmax
-        store.append((F[:, :k, :].copy(), F[:, k:, :k].copy()))      # [Z | X], -W
-        S_prev = F[:, k:, k:].copy()
+        Einv = gj_inverse(_lower_to_full(F[:, :k, :k]), tile)
+        FRE = F[:, k:, :k]
+        G = FRE @ Einv
+        S_prev = np.tril(F[:, k:, k:] - G @ np.transpose(FRE, (0, 2, 1)))   # lower triangle only
+        store.append((Einv, G))
     return store
 
 
-def solve(levels, store, b, nx, ny):
-    b = np.asarray(b, dtype=np.complex128).reshape(-1)
+def solve(levels, store, b, nx, ny, dscale):
+    b = np.asarray(b, dtype=np.complex128).reshape(-1) * dscale
     ring_prev = None
     ysave = []
-    for lv, (EZX, RW) in zip(levels, store):
+    for lv, (Einv, G) in zip(levels, store):
         f = np.zeros((lv.nb, lv.nmax), dtype=np.complex128)
         if lv.kind == "leaf":
             for i in range(lv.nb):
@@ -88,14 +106,14 @@ def solve(levels, store, b, nx, ny):
                     np.add.at(f[i], idx[ok], ring_prev[ch][ok])
         k = lv.kmax
         fe = f[:, :k]
-        ring_prev = f[:, k:] + np.einsum('bmk,bk->bm', RW, fe)
-        ysave.append(np.einsum('bkj,bj->bk', EZX[:, :, :k], fe))
+        ring_prev = f[:, k:] - np.einsum('bmk,bk->bm', G, fe)
+        ysave.append(np.einsum('bkj,bj->bk', Einv, fe))
     # backward
     u_parent = None
     out = np.zeros(nx * ny, dtype=np.complex128)
     for li in range(len(levels) - 1, -1, -1):
         lv = levels[li]
-        EZX, _ = store[li]
+        _, G = store[li]
         k = lv.kmax
         u = np.zeros((lv.nb, lv.nmax), dtype=np.complex128)
         if li < len(levels) - 1:
@@ -106,7 +124,7 @@ def solve(levels, store, b, nx, ny):
                     idx = cmap[:par.child_mmax]
                     ok = idx >= 0
                     u[ch, k + np.where(ok)[0]] = u_parent[pb, idx[ok]]
-        u[:, :k] = ysave[li] - np.einsum('bkm,bm->bk', EZX[:, :, k:], u[:, k:])
+        u[:, :k] = ysave[li] - np.einsum('bmk,bm->bk', G, u[:, k:])
         u_parent = u
         if lv.kind == "leaf":
             for i in range(lv.nb):

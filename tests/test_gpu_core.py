@@ -29,15 +29,43 @@ def test_zgemm_hook():
     lib = _lib.load()
     _lib.require_gpu()
     rng = np.random.default_rng(0)
-    for (M, N, K, batch) in [(25, 25, 9, 7), (64, 64, 32, 3), (70, 130, 17, 2), (200, 96, 64, 1), (13, 40, 5, 11), (520, 530, 70, 2), (1000, 700, 64, 1)]:
+
+    def crand(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    for (M, N, K, batch) in [(25, 25, 9, 7), (64, 64, 32, 3), (70, 130, 17, 2), (200, 96, 64, 1), (13, 40, 5, 11),
+                             (520, 530, 70, 2), (1000, 700, 64, 1), (300, 200, 500, 3)]:
+        A, C0 = crand(batch, M, K), crand(batch, M, N)
+        for transb in (0, 1):
+            B = crand(batch, N, K) if transb else crand(batch, K, N)
+            prod = A @ (np.transpose(B, (0, 2, 1)) if transb else B)
+            for mode in (0, 1):
+                C = C0.copy()
+                _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, batch, mode,
+                                                       transb, 0))
+                ref = prod if mode == 0 else C0 - prod
+                assert relerr(C, ref) < 1e-14, (M, N, K, batch, mode, transb)
+
+
+def test_zgemm_lower_schur_update():
+    """S -= G F^T on the lower tiles only: the lower triangle is exact, entries of tiles strictly
+    above the diagonal tiles are untouched (persistent kernel for the big case, tiled for the small)."""
+    from fdfdpy_b200 import _lib
+    lib = _lib.load()
+    _lib.require_gpu()
+    rng = np.random.default_rng(1)
+    for (M, K, batch) in [(24, 3, 50), (100, 40, 9), (200, 130, 5), (1300, 300, 1), (770, 64, 3)]:
         A = rng.standard_normal((batch, M, K)) + 1j * rng.standard_normal((batch, M, K))
-        B = rng.standard_normal((batch, K, N)) + 1j * rng.standard_normal((batch, K, N))
-        C0 = rng.standard_normal((batch, M, N)) + 1j * rng.standard_normal((batch, M, N))
-        for mode in (0, 1):
-            C = C0.copy()
-            _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, batch, mode))
-            ref = A @ B if mode == 0 else C0 - A @ B
-            assert relerr(C, ref) < 1e-14, (M, N, K, batch, mode)
+        B = rng.standard_normal((batch, M, K)) + 1j * rng.standard_normal((batch, M, K))
+        C0 = rng.standard_normal((batch, M, M)) + 1j * rng.standard_normal((batch, M, M))
+        C = C0.copy()
+        _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, M, K, batch, 1, 1, 1))
+        ref = C0 - A @ np.transpose(B, (0, 2, 1))
+        assert relerr(np.tril(C), np.tril(ref)) < 1e-14, (M, K, batch)
+        ts = 32 if M <= 32 else 64
+        ti = np.arange(M) // ts
+        above = ti[None, :] > ti[:, None]
+        assert np.array_equal(C[:, above], C0[:, above]), (M, K, batch)
 
 
 def test_operator_parity_golden(core, golden):

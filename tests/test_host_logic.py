@@ -60,18 +60,23 @@ def test_cabi_exports_every_declared_symbol():
 @pytest.mark.parametrize("shape,npml", [((16, 16), [3, 3]), ((23, 17), [4, 3]), ((37, 52), [0, 6]), ((8, 64), [2, 9])])
 @pytest.mark.parametrize("pol", ["Ez", "Hz"])
 def test_elimination_plan_numpy_model(shape, npml, pol):
-    """The plan executed the way the kernels do (padded fronts, blocked sweep, level-wise solve)."""
+    """The plan executed the way the kernels do (padded symmetric fronts, blocked inversion, level-wise solve)."""
     from fdfdpy_b200.ndplan import build_plan
-    from tests.nd_model import factor, solve
+    from tests.nd_model import factor, solve, row_scale
     nx, ny = shape
     rng = np.random.default_rng(0)
     eps = 1 + 5 * rng.random((nx, ny))
     omega = 2 * np.pi * 200e12
     planes = orc.stencil_planes(omega, eps, 0.04, npml, pol, 1e-6)
     levels = build_plan(nx, ny)
-    store = factor(levels, planes, nx, ny, tile=8)
+    isxf, _, isyf, _ = orc.pml_inverse_factors(omega, 1e-6, (nx, ny), npml, 0.04)
+    d = row_scale(isxf, isyf)
+    # the row-scaled operator is complex symmetric: that is what lets the fronts keep one triangle
+    As = (orc.planes_to_csr(planes).multiply(d[:, None])).tocsr()
+    assert abs(As - As.T).max() <= 1e-12 * abs(As).max()
+    store = factor(levels, planes, nx, ny, d, tile=8)
     b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
-    u = solve(levels, store, b, nx, ny)
+    u = solve(levels, store, b, nx, ny, d)
     ref = orc.sparse_solve(orc.planes_to_csr(planes), b).reshape(nx, ny)
     assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-11
 

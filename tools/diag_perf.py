@@ -10,7 +10,7 @@ from fdfdpy_b200 import core  # noqa: E402
 OMEGA = 2 * np.pi * 200e12
 sizes = [int(a) for a in sys.argv[1:]] or [512, 1024]
 import os
-tile = int(os.environ.get("FDFD_TILE", "32"))
+tile = int(os.environ.get("FDFD_TILE", "64"))
 for n in sizes:
     rng = np.random.default_rng(0)
     eps = 1 + 11 * (rng.random((n, n)) > 0.5)
@@ -26,10 +26,10 @@ for n in sizes:
     op.lib.fdfd_phase_timing(1)
     d.factor()
     t4 = time.time()
-    ph = np.zeros(10)
+    ph = np.zeros(12)
     op.lib.fdfd_phase_timing_read(_lib.ptr(ph))
     op.lib.fdfd_phase_timing(0)
-    names = "assemble pivot panel rowgemm copy update extract solve_fwd solve_bwd stencil".split()
+    names = "assemble pivot panel rowgemm copy update expand solve_fwd solve_bwd stencil ggemm schur".split()
     print("   phases ms:", " ".join(f"{k}={v:.1f}" for k, v in zip(names, ph)), "sum=%.1f" % ph.sum(), flush=True)
     b = np.zeros((n, n), dtype=complex)
     b[n // 2, n // 2] = 1j * OMEGA
