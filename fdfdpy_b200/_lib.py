@@ -46,6 +46,7 @@ SIGNATURES = {
     "fdfd_dmma_peak": (C.c_int, [_dp]),
     "fdfd_phase_timing": (C.c_int, [C.c_int]),
     "fdfd_phase_timing_read": (C.c_int, [_vp]),
+    "fdfd_phase_timing_read_levels": (C.c_int, [_vp, C.c_int]),
     "fdfd_dmma_probe": (C.c_int, [C.c_int, C.c_int, _dp]),
     "fdfd_host_register": (C.c_int, [_vp, C.c_double]),
     "fdfd_host_unregister": (C.c_int, [_vp]),

@@ -127,8 +127,9 @@ int fdfd_gemm_timing_read(double* out) {
 }
 int fdfd_phase_timing(int enable) {
     for (cudaEvent_t e : g_phase_timing.ev) cudaEventDestroy(e);
-    g_phase_timing.ev.clear(); g_phase_timing.cat.clear();
+    g_phase_timing.ev.clear(); g_phase_timing.cat.clear(); g_phase_timing.lvl.clear();
     g_phase_timing.on = enable != 0;
+    g_phase_timing.level = -1;
     return 0;
 }
 /* per-phase totals in ms since fdfd_phase_timing(1): assemble, pivot, panel, rowgemm, copy, update,
@@ -140,6 +141,19 @@ int fdfd_phase_timing_read(double* out12) {
         float ms = 0;
         FDFD_CHECK(cudaEventElapsedTime(&ms, g_phase_timing.ev[2 * i], g_phase_timing.ev[2 * i + 1]));
         out12[g_phase_timing.cat[i]] += ms;
+    }
+    return 0;
+}
+/* the same totals split by elimination-tree level: out[level * 12 + phase], levels 0..max_levels-1 */
+int fdfd_phase_timing_read_levels(double* out, int max_levels) {
+    FDFD_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < max_levels * PH_COUNT; ++i) out[i] = 0;
+    for (size_t i = 0; i < g_phase_timing.cat.size(); ++i) {
+        int l = g_phase_timing.lvl[i];
+        if (l < 0 || l >= max_levels) continue;
+        float ms = 0;
+        FDFD_CHECK(cudaEventElapsedTime(&ms, g_phase_timing.ev[2 * i], g_phase_timing.ev[2 * i + 1]));
+        out[l * PH_COUNT + g_phase_timing.cat[i]] += ms;
     }
     return 0;
 }

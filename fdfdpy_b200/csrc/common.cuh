@@ -64,8 +64,10 @@ enum FdfdPhase { PH_ASSEMBLE = 0, PH_PIVOT, PH_PANEL, PH_ROWGEMM, PH_COPY, PH_UP
                  PH_SOLVE_BWD, PH_STENCIL, PH_GGEMM, PH_SCHUR, PH_COUNT };
 struct PhaseTiming {
     bool on = false;
+    int level = -1;                 // elimination-tree level the next scopes belong to (-1: none)
     std::vector<cudaEvent_t> ev;
     std::vector<int> cat;
+    std::vector<int> lvl;
 };
 extern PhaseTiming g_phase_timing;
 struct PhaseScope {
@@ -80,6 +82,7 @@ struct PhaseScope {
         g_phase_timing.ev.push_back(e0);
         g_phase_timing.ev.push_back(e1);
         g_phase_timing.cat.push_back(cat);
+        g_phase_timing.lvl.push_back(g_phase_timing.level);
     }
     ~PhaseScope() {
         if (active) cudaEventRecord(g_phase_timing.ev.back(), st);

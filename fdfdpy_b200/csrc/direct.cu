@@ -158,36 +158,131 @@ __global__ void pivot_inverse_kernel(const cplx* __restrict__ F, int nmax, int j
     }
 }
 
-// Cbuf[b][r][:] = r in J ? 0 : F[b][r][J];   F[b][r][J] = r in J ? I : 0
+// Register-resident variant for tiles up to 64 x 64 (one CTA of 256 threads, each thread owns a 4 x 4
+// block of the zero/identity-padded tile): in-place Gauss-Jordan with IMPLICIT partial pivoting (rows
+// are never moved; the pivot row of column c is the largest entry among rows not used yet), two
+// barriers per column, only the pivot column and row travel through shared memory.  With pr(c) the
+// pivot row of column c, the stored result M satisfies  A^-1[pc(r)][pr(c)] = M[r][c]  (pc = pr^-1),
+// which the final store applies.  ~20x faster than the shared-memory kernel above on a 64-wide tile.
 __global__ void __launch_bounds__(256)
-panel_kernel(cplx* __restrict__ F, cplx* __restrict__ Cbuf, int nmax, int j0, int tw, int tcap, int chunks) {
-    const long long b = blockIdx.x / chunks;
-    const int chunk = blockIdx.x % chunks;
-    cplx* Fb = F + b * (long long)nmax * nmax;
-    cplx* Cb = Cbuf + b * (long long)nmax * tcap;
-    const int total = nmax * tw;
-    const int per = (total + chunks - 1) / chunks;
-    const int e0 = chunk * per, e1 = min(total, e0 + per);
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        int r = e / tw, c = e % tw;
-        bool inJ = r >= j0 && r < j0 + tw;
-        cplx* f = Fb + (size_t)r * nmax + j0 + c;
-        Cb[r * tcap + c] = inJ ? make_double2(0.0, 0.0) : *f;
-        *f = make_double2((inJ && r - j0 == c) ? 1.0 : 0.0, 0.0);
+tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx* dst, long long d_stride, int d_ld,
+                    int* __restrict__ info, int sym) {
+    __shared__ cplx colbuf[2][64];
+    __shared__ cplx rowbuf[64];
+    __shared__ int prow_of_col[64], pcol_of_row[64];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, lane = tid & 31;
+    const int R0 = ty * 4, C0 = tx * 4;
+    const cplx* S = src + (long long)blockIdx.x * s_stride;
+    cplx a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int r = R0 + i, c = C0 + j;
+            if (r < tw && c < tw) a[i][j] = (sym && c > r) ? S[(size_t)c * s_ld + r] : S[(size_t)r * s_ld + c];
+            else a[i][j] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) colbuf[0][R0 + i] = a[i][0];
+    }
+    unsigned long long used = 0ull;
+    for (int c = 0; c < 64; ++c) {
+        const cplx* cb = colbuf[c & 1];
+        __syncthreads();
+        // every warp finds the pivot row redundantly (lanes cover rows lane and lane + 32)
+        double v0 = ((used >> lane) & 1ull) ? -1.0 : cabs2(cb[lane]);
+        double v1 = ((used >> (lane + 32)) & 1ull) ? -1.0 : cabs2(cb[lane + 32]);
+        double best = v0;
+        int p = lane;
+        if (v1 > best) { best = v1; p = lane + 32; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, p, o);
+            if (ob > best || (ob == best && oi < p)) { best = ob; p = oi; }
+        }
+        if (!(best > 1e-300)) {                      // singular (or NaN): flag it, keep going on any free row
+            p = __ffsll((long long)~used) - 1;
+            if (tid == 0) atomicExch(info, 1);
+        }
+        if (ty == (p >> 2)) {
+            const int pi = p & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cplx t = a[0][j];
+                if (pi == 1) t = a[1][j];
+                if (pi == 2) t = a[2][j];
+                if (pi == 3) t = a[3][j];
+                rowbuf[C0 + j] = (C0 + j == c) ? make_double2(1.0, 0.0) : t;
+            }
+        }
+        __syncthreads();
+        const cplx ipiv = crecip(cb[p]);
+        cplx pr[4], f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[j] = cmul(rowbuf[C0 + j], ipiv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = cb[R0 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool piv = (R0 + i) == p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cplx t = (C0 + j == c) ? make_double2(0.0, 0.0) : a[i][j];
+                t.x -= f[i].x * pr[j].x - f[i].y * pr[j].y;
+                t.y -= f[i].x * pr[j].y + f[i].y * pr[j].x;
+                a[i][j] = piv ? pr[j] : t;
+            }
+        }
+        used |= 1ull << p;
+        if (tid == 0) { prow_of_col[c] = p; pcol_of_row[p] = c; }
+        const int cn = c + 1;
+        if (cn < 64 && tx == (cn >> 2)) {
+            const int cj = cn & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cplx t = a[i][0];
+                if (cj == 1) t = a[i][1];
+                if (cj == 2) t = a[i][2];
+                if (cj == 3) t = a[i][3];
+                colbuf[cn & 1][R0 + i] = t;
+            }
+        }
+    }
+    __syncthreads();
+    cplx* D = dst + (long long)blockIdx.x * d_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int orow = pcol_of_row[R0 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ocol = prow_of_col[C0 + j];
+            if (orow < tw && ocol < tw) D[(size_t)orow * d_ld + ocol] = a[i][j];
+        }
     }
 }
 
+// dst[b][c][r] = src[b][r][c] for an (rows x cols) block; 32 x 32 tiles through shared memory.
+// mirror != 0 (square, src == dst): copies the strict lower triangle onto the upper one instead.
 __global__ void __launch_bounds__(256)
-copy_rows_kernel(cplx* __restrict__ F, const cplx* __restrict__ Rbuf, int nmax, int j0, int tw, int tcap,
-                 int chunks) {
-    const long long b = blockIdx.x / chunks;
-    const int chunk = blockIdx.x % chunks;
-    cplx* Fb = F + b * (long long)nmax * nmax + (size_t)j0 * nmax;
-    const cplx* Rb = Rbuf + b * (long long)tcap * nmax;
-    const int total = nmax * tw;
-    const int per = (total + chunks - 1) / chunks;
-    const int e0 = chunk * per, e1 = min(total, e0 + per);
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) Fb[e] = Rb[e];
+transpose_kernel(const cplx* src, long long s_stride, int s_ld, cplx* dst, long long d_stride, int d_ld, int rows,
+                 int cols, int mirror) {
+    __shared__ cplx tile[32][33];
+    const int tr = blockIdx.y, tc = blockIdx.x;
+    if (mirror && tc > tr) return;
+    const cplx* S = src + (long long)blockIdx.z * s_stride;
+    cplx* D = dst + (long long)blockIdx.z * d_stride;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int i = ly; i < 32; i += 8) {
+        int r = tr * 32 + i, c = tc * 32 + lx;
+        if (r < rows && c < cols) tile[i][lx] = S[(size_t)r * s_ld + c];
+    }
+    __syncthreads();
+    for (int i = ly; i < 32; i += 8) {
+        int c = tc * 32 + i, r = tr * 32 + lx;       // element (r, c) of src goes to (c, r) of dst
+        if (r < rows && c < cols && (!mirror || r > c)) D[(size_t)c * d_ld + r] = tile[lx][i];
+    }
 }
 
 // Einv[b] (kmax x kmax, full) = symmetric expansion of the lower triangle of F[b][0:kmax, 0:kmax]
@@ -464,86 +559,117 @@ static int chunks_for(long long per_front_elems, long long nb) {
     return (int)(c < 1 ? 1 : c);
 }
 
-// one arena for all transient factorisation buffers: two ping-pong front batches plus the pivot /
-// column-panel / row-panel scratch of the blocked inversion, sized for the largest level; allocated
-// once and kept
-static int ensure_factor_workspace(NdSolver* s) {
-    size_t maxF = 0, maxP = 0, maxC = 0;
-    for (auto& L : s->levels) {
-        const size_t nb = L.nb, nmax = L.nmax, kmax = L.kmax;
-        maxF = std::max(maxF, nb * nmax * nmax);
-        if (L.kmax > s->tile) {
-            maxP = std::max(maxP, nb * (size_t)s->tile * s->tile);
-            maxC = std::max(maxC, nb * kmax * s->tile);
-        }
+// ---- recursive symmetric block inversion ---------------------------------------------------
+// E = [A B^T; B D] (full symmetric storage, in place):
+//   Ainv = A^-1 (recursion);  T = B Ainv;  S = D - T B^T;  Sinv = S^-1 (recursion);
+//   E21 = -Sinv T;  E11 = Ainv - T^T E21;  E12 = E21^T.
+// n^3 / 2 complex MACs, all of them in large-K GEMMs; the base case is the register-resident 64 x 64
+// tile inverse.  T and T^T live in a workspace stack (they must survive the recursion into S).
+static int inv_split(int n) { return ((n / 2 + 63) / 64) * 64; }
+static size_t inv_ws_need(int n) {
+    if (n <= 64) return 0;
+    int n1 = inv_split(n), n2 = n - n1;
+    return std::max(inv_ws_need(n1), 2 * (size_t)n1 * n2 + inv_ws_need(n2));
+}
+
+static int launch_transpose(const cplx* src, long long s_stride, int s_ld, cplx* dst, long long d_stride, int d_ld,
+                            int rows, int cols, int mirror, long long nb, cudaStream_t st) {
+    if (nb > 65535) FDFD_FAIL("transpose batch too large");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, (unsigned)nb);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, s_stride, s_ld, dst, d_stride, d_ld, rows, cols, mirror);
+    ++g_fdfd_launches;
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, long long nb, cplx* ws,
+                            cudaStream_t st) {
+    if (n <= 64) {
+        PhaseScope ph(PH_PIVOT, st);
+        tile_inverse_kernel<<<(unsigned)nb, 256, 0, st>>>(E, sE, ld, n, E, sE, ld, s->d_info, 0);
+        ++g_fdfd_launches;
+        FDFD_CHECK(cudaGetLastError());
+        return 0;
     }
-    size_t need = 2 * maxF + maxP + 2 * maxC;
+    const int n1 = inv_split(n), n2 = n - n1;
+    cplx *A = E, *B = E + (size_t)n1 * ld, *D = B + n1, *Bt = E + n1;
+    cplx *T = ws, *Tt = ws + (size_t)nb * n1 * n2, *ws_next = ws + 2 * (size_t)nb * n1 * n2;
+    const long long sT = (long long)n1 * n2;
+    if (sym_invert_batch(s, A, sE, ld, n1, nb, ws, st)) return -1;
+    GemmBatch g;
+    g.batch = (int)nb;
+    {   // T = B Ainv  (Ainv symmetric: NT form)
+        PhaseScope ph(PH_ROWGEMM, st);
+        g.transb = 1; g.lower = 0; g.mode = 0;
+        g.A = B; g.sA = sE; g.lda = ld;
+        g.B = A; g.sB = sE; g.ldb = ld;
+        g.C = T; g.sC = sT; g.ldc = n1;
+        g.M = n2; g.N = n1; g.K = n1;
+        if (zgemm_batched(g, st)) return -1;
+    }
+    {   // S = D - T B^T  (lower tiles, then mirrored: the recursion wants full storage)
+        PhaseScope ph(PH_UPDATE, st);
+        g.transb = 1; g.lower = 1; g.mode = 1;
+        g.A = T; g.sA = sT; g.lda = n1;
+        g.B = B; g.sB = sE; g.ldb = ld;
+        g.C = D; g.sC = sE; g.ldc = ld;
+        g.M = n2; g.N = n2; g.K = n1;
+        if (zgemm_batched(g, st)) return -1;
+    }
+    {
+        PhaseScope ph(PH_COPY, st);
+        if (launch_transpose(D, sE, ld, D, sE, ld, n2, n2, 1, nb, st)) return -1;
+        if (launch_transpose(T, sT, n1, Tt, sT, n2, n2, n1, 0, nb, st)) return -1;
+    }
+    if (sym_invert_batch(s, D, sE, ld, n2, nb, ws_next, st)) return -1;
+    {   // E21 = -Sinv T
+        PhaseScope ph(PH_ROWGEMM, st);
+        g.transb = 0; g.lower = 0; g.mode = 2;
+        g.A = D; g.sA = sE; g.lda = ld;
+        g.B = T; g.sB = sT; g.ldb = n1;
+        g.C = B; g.sC = sE; g.ldc = ld;
+        g.M = n2; g.N = n1; g.K = n2;
+        if (zgemm_batched(g, st)) return -1;
+    }
+    {   // E11 = Ainv - T^T E21  (lower tiles + mirror)
+        PhaseScope ph(PH_UPDATE, st);
+        g.transb = 0; g.lower = 1; g.mode = 1;
+        g.A = Tt; g.sA = sT; g.lda = n2;
+        g.B = B; g.sB = sE; g.ldb = ld;
+        g.C = A; g.sC = sE; g.ldc = ld;
+        g.M = n1; g.N = n1; g.K = n2;
+        if (zgemm_batched(g, st)) return -1;
+    }
+    {
+        PhaseScope ph(PH_COPY, st);
+        if (launch_transpose(A, sE, ld, A, sE, ld, n1, n1, 1, nb, st)) return -1;
+        if (launch_transpose(B, sE, ld, Bt, sE, ld, n2, n1, 0, nb, st)) return -1;      // E12 = E21^T
+    }
+    s->factor_flops += 8.0 * (double)nb * ((double)n2 * n1 * n1 + 0.5 * (double)n2 * n2 * n1 +
+                                           (double)n2 * n2 * n1 + 0.5 * (double)n1 * n1 * n2);
+    return 0;
+}
+
+// one arena for all transient factorisation buffers: two ping-pong front batches plus the workspace
+// stack of the block inversion, sized for the largest level; allocated once and kept
+static int ensure_factor_workspace(NdSolver* s) {
+    size_t maxF = 0, maxW = 0;
+    for (auto& L : s->levels) {
+        const size_t nb = L.nb, nmax = L.nmax;
+        maxF = std::max(maxF, nb * nmax * nmax);
+        maxW = std::max(maxW, nb * inv_ws_need(L.kmax));
+    }
+    size_t need = 2 * maxF + maxW;
     if (need > s->fws_cap) {
         if (s->fws) cudaFree(s->fws);
         s->fws = nullptr;
         s->fws_cap = 0;
-        FDFD_CHECK(cudaMalloc(&s->fws, sizeof(cplx) * need));
+        FDFD_CHECK(cudaMalloc(&s->fws, sizeof(cplx) * std::max(need, (size_t)1)));
         s->fws_cap = need;
     }
     s->fws_F[0] = s->fws;
     s->fws_F[1] = s->fws + maxF;
-    s->fws_P = s->fws + 2 * maxF;
-    s->fws_C = s->fws_P + maxP;
-    s->fws_R = s->fws_C + maxC;
-    return 0;
-}
-
-// In-place blocked Gauss-Jordan inversion of a batch of full n x n matrices (n > tile):
-// per 64-wide pivot tile J:  P = E_JJ^-1 (shared memory, partial pivoting inside the tile),
-// column panel saved / zeroed, R = P E_J,: , rank-T update E -= C R.
-static int gj_invert_batch(NdSolver* s, cplx* E, int n, long long nb, cudaStream_t st) {
-    const int tcap = s->tile;
-    cplx *Pbuf = s->fws_P, *Cbuf = s->fws_C, *Rbuf = s->fws_R;
-    for (int j0 = 0; j0 < n; j0 += tcap) {
-        const int tw = (n - j0) < tcap ? (n - j0) : tcap;
-        size_t smem = sizeof(cplx) * ((size_t)tw * 2 * tw + tw);
-        int threads = tw * tw >= 512 ? 256 : (tw * tw >= 128 ? 128 : 64);
-        if (smem > 48 * 1024)
-            FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        {
-            PhaseScope ph(PH_PIVOT, st);
-            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(E, n, j0, tw, Pbuf, tcap, s->d_info, 0);
-            ++g_fdfd_launches;
-        }
-        int chunks = chunks_for((long long)n * tw, nb);
-        {
-            PhaseScope ph(PH_PANEL, st);
-            panel_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(E, Cbuf, n, j0, tw, tcap, chunks);
-            ++g_fdfd_launches;
-        }
-        FDFD_CHECK(cudaGetLastError());
-        GemmBatch g;
-        g.transb = 0; g.lower = 0;
-        g.A = Pbuf; g.sA = (long long)tcap * tcap; g.lda = tcap;
-        g.B = E + (size_t)j0 * n; g.sB = (long long)n * n; g.ldb = n;
-        g.C = Rbuf; g.sC = (long long)tcap * n; g.ldc = n;
-        g.M = tw; g.N = n; g.K = tw; g.batch = (int)nb; g.mode = 0;
-        {
-            PhaseScope ph(PH_ROWGEMM, st);
-            if (zgemm_batched(g, st)) return -1;
-        }
-        {
-            PhaseScope ph(PH_COPY, st);
-            copy_rows_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(E, Rbuf, n, j0, tw, tcap, chunks);
-            ++g_fdfd_launches;
-        }
-        FDFD_CHECK(cudaGetLastError());
-        g.A = Cbuf; g.sA = (long long)n * tcap; g.lda = tcap;
-        g.B = Rbuf; g.sB = (long long)tcap * n; g.ldb = n;
-        g.C = E; g.sC = (long long)n * n; g.ldc = n;
-        g.M = n; g.N = n; g.K = tw; g.mode = 1;
-        {
-            PhaseScope ph(PH_UPDATE, st);
-            if (zgemm_batched(g, st)) return -1;
-        }
-        s->factor_flops += 8.0 * (double)nb * ((double)n * n * tw + (double)tw * tw * n);
-    }
+    s->fws_W = s->fws + 2 * maxF;
     return 0;
 }
 
@@ -560,6 +686,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     s->factor_flops = 0;
     for (size_t li = 0; li < s->levels.size(); ++li) {
         NdLevel& L = s->levels[li];
+        g_phase_timing.level = (int)li;
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
         cplx* F = s->fws_F[li & 1];
@@ -582,14 +709,18 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         }
         FDFD_CHECK(cudaGetLastError());
         // ---- Einv = F_EE^-1
-        if (kmax <= s->tile) {
+        if (kmax <= 64) {
             size_t smem = sizeof(cplx) * ((size_t)kmax * 2 * kmax + kmax);
             int threads = kmax * kmax >= 512 ? 256 : (kmax * kmax >= 128 ? 128 : 64);
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
             PhaseScope ph(PH_PIVOT, st);
-            pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, 0, kmax, L.Einv, kmax, s->d_info, 1);
+            if (kmax > 16)
+                tile_inverse_kernel<<<(unsigned)nb, 256, 0, st>>>(F, (long long)nmax * nmax, nmax, kmax, L.Einv,
+                                                                  (long long)kmax * kmax, kmax, s->d_info, 1);
+            else
+                pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, 0, kmax, L.Einv, kmax, s->d_info, 1);
             ++g_fdfd_launches;
         } else {
             {
@@ -598,7 +729,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                 sym_expand_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.Einv, kmax, nmax, chunks);
                 ++g_fdfd_launches;
             }
-            if (gj_invert_batch(s, L.Einv, kmax, nb, st)) return -1;
+            if (sym_invert_batch(s, L.Einv, (long long)kmax * kmax, kmax, kmax, nb, s->fws_W, st)) return -1;
         }
         FDFD_CHECK(cudaGetLastError());
         if (mmax > 0) {
@@ -630,6 +761,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         prev_k = kmax;
         prev_n = nmax;
     }
+    g_phase_timing.level = -1;
     int info = 0;
     FDFD_CHECK(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     FDFD_CHECK(cudaStreamSynchronize(st));
@@ -670,9 +802,10 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
     cplx *f = s->ws_a, *ring_prev = s->ws_ring_a, *ring_cur = s->ws_ring_b;
     // ---- forward (leaves -> root)
     {
-    PhaseScope phf(PH_SOLVE_FWD, st);
     for (size_t li = 0; li < nlev; ++li) {
         NdLevel& L = s->levels[li];
+        g_phase_timing.level = (int)li;
+        PhaseScope phf(PH_SOLVE_FWD, st);
         const long long nb = L.nb;
         long long tot = nb * L.nmax;
         if (L.kind == 0)
@@ -688,10 +821,11 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
     }
     }
     // ---- backward (root -> leaves)
-    PhaseScope phb(PH_SOLVE_BWD, st);
     cplx *u = s->ws_a, *u_par = s->ws_b;
     for (size_t li = nlev; li-- > 0;) {
         NdLevel& L = s->levels[li];
+        g_phase_timing.level = (int)li;
+        PhaseScope phb(PH_SOLVE_BWD, st);
         const long long nb = L.nb;
         FDFD_CHECK(cudaMemsetAsync(u, 0, sizeof(cplx) * (size_t)nb * L.nmax * NR, st));
         if (li + 1 < nlev) {
@@ -710,6 +844,7 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         FDFD_CHECK(cudaGetLastError());
         std::swap(u, u_par);
     }
+    g_phase_timing.level = -1;
     return 0;
 }
 

@@ -33,14 +33,14 @@ struct NdLevel {
 
 struct NdSolver {
     int nx, ny;
-    int tile;                         // pivot block width of the blocked sweep
+    int tile;                         // (kept for ABI compatibility; the block inversion uses 64-wide base tiles)
     std::vector<NdLevel> levels;
     bool factored;
     size_t factor_bytes;
     double factor_flops;              // real flops of the last factorisation (8 per complex MAC)
     int* d_info;                      // device flag: non-zero if a pivot tile was singular
-    // factorisation arena (allocated once): ping-pong front batches + pivot / panel scratch
-    cplx *fws, *fws_F[2], *fws_P, *fws_C, *fws_R;
+    // factorisation arena (allocated once): ping-pong front batches + block-inversion workspace stack
+    cplx *fws, *fws_F[2], *fws_W;
     size_t fws_cap;
     // solve workspace (grown on demand)
     cplx *ws_a, *ws_b, *ws_ring_a, *ws_ring_b, *ws_ye;

@@ -22,7 +22,7 @@ struct GemmBatch {
     const cplx* B; long long sB; int ldb;
     cplx* C; long long sC; int ldc;
     int M, N, K, batch;
-    int mode;   // 0: C = AB, 1: C -= AB
+    int mode;   // 0: C = AB, 1: C -= AB, 2: C = -AB
     int transb; // 0: B is K x N, 1: B is N x K (C = A B^T)
     int lower;  // 1: only tiles with tile_row >= tile_col
 };
@@ -160,6 +160,8 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
                     if (g.mode == 1) {
                         cplx o = p[e];
                         v = make_double2(o.x - v.x, o.y - v.y);
+                    } else if (g.mode == 2) {
+                        v = make_double2(-v.x, -v.y);
                     }
                     p[e] = v;
                 }
@@ -337,6 +339,7 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
                         if (col + e < g.N) {
                             cplx v = make_double2(cr[mt][nt][e], ci[mt][nt][e]);
                             if (g.mode == 1) v = make_double2(cpre[mt][nt][e].x - v.x, cpre[mt][nt][e].y - v.y);
+                            else if (g.mode == 2) v = make_double2(-v.x, -v.y);
                             p[e] = v;
                         }
                     }

@@ -40,6 +40,7 @@ int fdfd_gemm_timing_read(double* out6);
 int fdfd_dmma_peak(double* tflops);
 int fdfd_phase_timing(int enable);
 int fdfd_phase_timing_read(double* out12);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur */
+int fdfd_phase_timing_read_levels(double* out, int max_levels);   /* out[level * 12 + phase] */
 int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflops);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);

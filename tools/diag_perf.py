@@ -35,6 +35,19 @@ for n in sizes:
     b[n // 2, n // 2] = 1j * OMEGA
     x = d.solve(b, max_refine=0)
     t5 = time.time()
+    op.lib.fdfd_phase_timing(1)
+    d.factor()
+    x = d.solve(b, max_refine=-1)
+    nl = len(d.levels)
+    pl = np.zeros((nl, 12))
+    op.lib.fdfd_phase_timing_read_levels(_lib.ptr(pl), nl)
+    op.lib.fdfd_phase_timing(0)
+    print("   per level ms (" + " ".join(names) + "):")
+    for li, lv in enumerate(d.levels):
+        print(f"   L{li:02d} nb={lv.nb:8d} k={lv.kmax:5d} m={lv.mmax:5d} | " + " ".join(f"{v:7.2f}" for v in pl[li]) +
+              f" | sum {pl[li].sum():8.2f}", flush=True)
+    print("   totals: " + " ".join(f"{k}={v:.1f}" for k, v in zip(names, pl.sum(0))), flush=True)
+    t5 = time.time()
     x = d.solve(b, max_refine=3, tol=1e-12)
     t6 = time.time()
     st = d.stats()
