@@ -211,57 +211,64 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
     const unsigned ntiles = (unsigned)total_tiles;
     if (blockIdx.x >= ntiles) return;
 
-    // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor); no divisions in the hot loop
+    // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor).  Each thread copies four 16-byte
+    // chunks of the A tile and four of the B tile per k-tile; their global pointers only advance by a
+    // constant per k-tile, so the hot loop carries two pointers and two row masks and no index math.
+    const int a_r = tid >> 4, a_c = tid & 15;                       // A (and B^T): rows a_r + 16 i, k column a_c
+    const int b_r = TB ? a_r : tid >> 6, b_c = TB ? a_c : tid & 63; // B (K x N): k rows b_r + 4 i, n column b_c
+    const long long a_step = 16LL * g.lda, b_step = TB ? 16LL * g.ldb : 4LL * g.ldb;
+    const long long b_adv = TB ? 16LL : 16LL * g.ldb;
     unsigned ld_tile = blockIdx.x;
-    int ld_kt = 0, ld_stage = 0, ld_m = 0, ld_n = 0;
-    const cplx *ld_A = g.A, *ld_B = g.B;
+    int ld_kt = 0, ld_stage = 0;
+    unsigned amask = 0, bmask = 0;
+    const cplx *pa = g.A, *pb = g.B;
     auto decode_load = [&]() {
         TileCoord t = decode_tile(ld_tile, tiles_per_batch, (unsigned)tiles_n, g.lower);
-        ld_m = (int)t.tm * BM;
-        ld_n = (int)t.tn * BN;
-        ld_A = g.A + (long long)t.b * g.sA;
-        ld_B = g.B + (long long)t.b * g.sB;
+        const int ld_m = (int)t.tm * BM, ld_n = (int)t.tn * BN;
+        pa = g.A + (long long)t.b * g.sA + (long long)(ld_m + a_r) * g.lda + a_c;
+        amask = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) amask |= (ld_m + a_r + 16 * i < g.M ? 1u : 0u) << i;
+        if (TB) {
+            pb = g.B + (long long)t.b * g.sB + (long long)(ld_n + b_r) * g.ldb + b_c;
+            bmask = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bmask |= (ld_n + b_r + 16 * i < g.N ? 1u : 0u) << i;
+        } else {
+            pb = g.B + (long long)t.b * g.sB + (long long)b_r * g.ldb + ld_n + b_c;
+            bmask = ld_n + b_c < g.N ? 0xFu : 0u;
+        }
     };
     decode_load();
     auto issue_load = [&]() {
         const int k0 = ld_kt * BK;
-        cplx* as = As + ld_stage * A_ELEMS;
-        cplx* bs = Bs + ld_stage * B_ELEMS;
+        cplx* as = As + ld_stage * A_ELEMS + a_r * LDA + a_c;
+        cplx* bs = Bs + ld_stage * B_ELEMS + b_r * LDB + b_c;
+        const bool kok = k0 + a_c < g.K;
 #pragma unroll
-        for (int i = tid; i < BM * BK; i += NT) {
-            int r = i / BK, c = i % BK;
-            int gm = ld_m + r, gk = k0 + c;
-            bool ok = gm < g.M && gk < g.K;
-            cp_async16(as + r * LDA + c, ok ? ld_A + (size_t)gm * g.lda + gk : ld_A, ok);
+        for (int i = 0; i < 4; ++i) {
+            bool ok = kok && ((amask >> i) & 1u);
+            cp_async16(as + i * 16 * LDA, ok ? pa + i * a_step : g.A, ok);
         }
-        if (TB) {
 #pragma unroll
-            for (int i = tid; i < BN * BK; i += NT) {
-                int r = i / BK, c = i % BK;
-                int gn = ld_n + r, gk = k0 + c;
-                bool ok = gn < g.N && gk < g.K;
-                cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gn * g.ldb + gk : ld_B, ok);
-            }
-        } else {
-#pragma unroll
-            for (int i = tid; i < BK * BN; i += NT) {
-                int r = i / BN, c = i % BN;
-                int gk = k0 + r, gn = ld_n + c;
-                bool ok = gk < g.K && gn < g.N;
-                cp_async16(bs + r * LDB + c, ok ? ld_B + (size_t)gk * g.ldb + gn : ld_B, ok);
-            }
+        for (int i = 0; i < 4; ++i) {
+            bool ok = TB ? (kok && ((bmask >> i) & 1u)) : (bmask && k0 + b_r + 4 * i < g.K);
+            cp_async16(bs + i * (TB ? 16 : 4) * LDB, ok ? pb + i * b_step : g.B, ok);
         }
+        pa += BK;
+        pb += b_adv;
         ld_stage = ld_stage + 1 == STAGES ? 0 : ld_stage + 1;
         if (++ld_kt == KT) {
             ld_kt = 0;
             ld_tile += gridDim.x;
             if (ld_tile < ntiles) decode_load();
+            else amask = bmask = 0;         // past the end: the copies degenerate to zero fills of a dead stage
         }
     };
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (ld_tile < ntiles) issue_load();
+        issue_load();
         cp_async_commit();
     }
     double cr[2][4][2], ci[2][4][2];
@@ -278,8 +285,6 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
       for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (ld_tile < ntiles) issue_load();
-        cp_async_commit();
         const bool last = kt == KT - 1;
         if (last && g.mode == 1) {
 #pragma unroll
@@ -324,6 +329,12 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
                     dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
                     dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
                 }
+            if (kk == 0) {
+                // refill the stage consumed in the previous iteration; issued here, under the first
+                // k-step's DMMAs, so the tensor pipe is not idle while the copies are set up
+                issue_load();
+                cp_async_commit();
+            }
         }
         if (last) {
 #pragma unroll
