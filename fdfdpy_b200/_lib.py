@@ -75,6 +75,7 @@ SIGNATURES = {
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int]),
     "fdfd_zgemm_set_variant": (C.c_int, [C.c_int]),
+    "fdfd_direct_set_small_fronts": (C.c_int, [C.c_int]),
     "fdfd_zgemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "fdfd_mode_solve_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                        C.c_int, C.c_int, _vp, _vp]),

@@ -133,18 +133,18 @@ int fdfd_phase_timing(int enable) {
     return 0;
 }
 /* per-phase totals in ms since fdfd_phase_timing(1): assemble, pivot, panel, rowgemm, copy, update,
- * expand, solve_fwd, solve_bwd, stencil, ggemm, schur (12 doubles). Synchronises the device. */
-int fdfd_phase_timing_read(double* out12) {
+ * expand, solve_fwd, solve_bwd, stencil, ggemm, schur, small (13 doubles). Synchronises the device. */
+int fdfd_phase_timing_read(double* out13) {
     FDFD_CHECK(cudaDeviceSynchronize());
-    for (int i = 0; i < PH_COUNT; ++i) out12[i] = 0;
+    for (int i = 0; i < PH_COUNT; ++i) out13[i] = 0;
     for (size_t i = 0; i < g_phase_timing.cat.size(); ++i) {
         float ms = 0;
         FDFD_CHECK(cudaEventElapsedTime(&ms, g_phase_timing.ev[2 * i], g_phase_timing.ev[2 * i + 1]));
-        out12[g_phase_timing.cat[i]] += ms;
+        out13[g_phase_timing.cat[i]] += ms;
     }
     return 0;
 }
-/* the same totals split by elimination-tree level: out[level * 12 + phase], levels 0..max_levels-1 */
+/* the same totals split by elimination-tree level: out[level * 13 + phase], levels 0..max_levels-1 */
 int fdfd_phase_timing_read_levels(double* out, int max_levels) {
     FDFD_CHECK(cudaDeviceSynchronize());
     for (int i = 0; i < max_levels * PH_COUNT; ++i) out[i] = 0;
@@ -364,6 +364,8 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
 }
 
 int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }
+extern int g_small_front_enabled;
+int fdfd_direct_set_small_fronts(int enable) { g_small_front_enabled = enable != 0; return 0; }
 
 int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int transb, int lower, int iters,
                      double* ms_per_launch) {

@@ -61,7 +61,7 @@ __device__ __forceinline__ cplx ldg_c(const cplx* p) { return __ldg(p); }
 
 // ---- optional live phase timing (CUDA events on the launching stream), read by bench.py ----
 enum FdfdPhase { PH_ASSEMBLE = 0, PH_PIVOT, PH_PANEL, PH_ROWGEMM, PH_COPY, PH_UPDATE, PH_EXTRACT, PH_SOLVE_FWD,
-                 PH_SOLVE_BWD, PH_STENCIL, PH_GGEMM, PH_SCHUR, PH_COUNT };
+                 PH_SOLVE_BWD, PH_STENCIL, PH_GGEMM, PH_SCHUR, PH_SMALL, PH_COUNT };
 struct PhaseTiming {
     bool on = false;
     int level = -1;                 // elimination-tree level the next scopes belong to (-1: none)

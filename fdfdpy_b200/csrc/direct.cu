@@ -89,90 +89,42 @@ merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// blocked Gauss-Jordan sweep pieces
+// tile inversion
 // ------------------------------------------------------------------------------------------
-// P[b] = inverse of the tw x tw pivot tile F[b][j0:j0+tw, j0:j0+tw]; Gauss-Jordan on [A | I] in
-// shared memory with partial (row) pivoting inside the tile.
-// sym != 0: F holds only the lower triangle of a symmetric matrix.
-__global__ void pivot_inverse_kernel(const cplx* __restrict__ F, int nmax, int j0, int tw,
-                                     cplx* __restrict__ P, int tcap, int* __restrict__ info, int sym) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* sm = reinterpret_cast<cplx*>(smem_raw);          // [tw][2*tw]
-    cplx* scol = sm + (size_t)tw * 2 * tw;                  // [tw]
-    __shared__ int s_piv;
-    const long long b = blockIdx.x;
-    const cplx* Fb = F + b * (long long)nmax * nmax;
-    const int w2 = 2 * tw;
-    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
-        int r = i / tw, c = i % tw;
-        sm[r * w2 + c] = (sym && c > r) ? Fb[(size_t)(j0 + c) * nmax + j0 + r] : Fb[(size_t)(j0 + r) * nmax + j0 + c];
-        sm[r * w2 + tw + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
-    }
-    __syncthreads();
-    for (int col = 0; col < tw; ++col) {
-        if (threadIdx.x < 32) {
-            double best = -1.0;
-            int bi = col;
-            for (int r = col + threadIdx.x; r < tw; r += 32) {
-                double v = cabs2(sm[r * w2 + col]);
-                if (v > best) { best = v; bi = r; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                double ob = __shfl_down_sync(0xffffffffu, best, o);
-                int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (threadIdx.x == 0) {
-                s_piv = bi;
-                if (!(best > 1e-300)) atomicExch(info, 1);
-            }
-        }
-        __syncthreads();
-        const int p = s_piv;
-        const cplx ipiv = crecip(sm[p * w2 + col]);
-        __syncthreads();
-        for (int c = threadIdx.x; c < w2; c += blockDim.x) {
-            cplx a = sm[col * w2 + c], bb = sm[p * w2 + c];
-            if (p != col) sm[p * w2 + c] = a;
-            sm[col * w2 + c] = cmul(bb, ipiv);
-        }
-        __syncthreads();
-        for (int r = threadIdx.x; r < tw; r += blockDim.x) scol[r] = sm[r * w2 + col];
-        __syncthreads();
-        for (int i = threadIdx.x; i < tw * w2; i += blockDim.x) {
-            int r = i / w2, c = i % w2;
-            if (r == col) continue;
-            cplx f = scol[r];
-            cplx pr = sm[col * w2 + c];
-            cplx v = sm[i];
-            v.x -= f.x * pr.x - f.y * pr.y;
-            v.y -= f.x * pr.y + f.y * pr.x;
-            sm[i] = v;
-        }
-        __syncthreads();
-    }
-    cplx* Pb = P + b * (long long)tcap * tcap;
-    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
-        int r = i / tw, c = i % tw;
-        Pb[r * tcap + c] = sm[r * w2 + tw + c];
-    }
+// Register-resident in-place Gauss-Jordan inversion of a tile of up to TS x TS (TS = 32: 64 threads,
+// TS = 64: 256 threads; each thread owns a 4 x 4 block) with IMPLICIT partial pivoting: rows are never
+// moved, the pivot row of column c is the largest entry among the rows not used yet, found with one
+// integer warp reduction on an order-preserving key.  Two barriers per column; only the pivot column
+// and row travel through shared memory.  With pr(c) the pivot row of column c, the stored result M
+// satisfies  A^-1[pc(r)][pr(c)] = M[r][c]  (pc = pr^-1), which the final store applies.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return r;
+}
+__device__ __forceinline__ cplx fast_crecip(cplx z) {
+    // |z|^2 stays far inside the double range for operator entries (|z| ~ 1e-20 .. 1e20)
+    double inv = fast_rcp(z.x * z.x + z.y * z.y);
+    return make_double2(z.x * inv, -z.y * inv);
 }
 
-// Register-resident variant for tiles up to 64 x 64 (one CTA of 256 threads, each thread owns a 4 x 4
-// block of the zero/identity-padded tile): in-place Gauss-Jordan with IMPLICIT partial pivoting (rows
-// are never moved; the pivot row of column c is the largest entry among rows not used yet), two
-// barriers per column, only the pivot column and row travel through shared memory.  With pr(c) the
-// pivot row of column c, the stored result M satisfies  A^-1[pc(r)][pr(c)] = M[r][c]  (pc = pr^-1),
-// which the final store applies.  ~20x faster than the shared-memory kernel above on a 64-wide tile.
-__global__ void __launch_bounds__(256)
-tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx* dst, long long d_stride, int d_ld,
-                    int* __restrict__ info, int sym) {
-    __shared__ cplx colbuf[2][64];
-    __shared__ cplx rowbuf[64];
-    __shared__ int prow_of_col[64], pcol_of_row[64];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, lane = tid & 31;
+template <int TS>
+struct TileInvSmem {
+    cplx colbuf[2][TS];
+    cplx rowbuf[TS];
+    int prow_of_col[TS], pcol_of_row[TS];
+};
+
+template <int TS>
+__device__ __forceinline__ void reg_tile_inverse(const cplx* S, int s_ld, int sym, int tw, cplx* D, int d_ld,
+                                                 TileInvSmem<TS>& sm, int* info, int tid, int bar_id) {
+    constexpr int GD = TS / 4, NTH = GD * GD;
+    const int ty = tid / GD, tx = tid % GD, lane = tid & 31;
     const int R0 = ty * 4, C0 = tx * 4;
-    const cplx* S = src + (long long)blockIdx.x * s_stride;
+    auto bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(NTH) : "memory"); };
     cplx a[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -184,26 +136,28 @@ tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx*
         }
     if (tx == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) colbuf[0][R0 + i] = a[i][0];
+        for (int i = 0; i < 4; ++i) sm.colbuf[0][R0 + i] = a[i][0];
     }
     unsigned long long used = 0ull;
-    for (int c = 0; c < 64; ++c) {
-        const cplx* cb = colbuf[c & 1];
-        __syncthreads();
-        // every warp finds the pivot row redundantly (lanes cover rows lane and lane + 32)
-        double v0 = ((used >> lane) & 1ull) ? -1.0 : cabs2(cb[lane]);
-        double v1 = ((used >> (lane + 32)) & 1ull) ? -1.0 : cabs2(cb[lane + 32]);
-        double best = v0;
-        int p = lane;
-        if (v1 > best) { best = v1; p = lane + 32; }
+    for (int c = 0; c < tw; ++c) {
+        const cplx* cb = sm.colbuf[c & 1];
+        bar();
+        // every warp finds the pivot row redundantly: key = high bits of |entry|^2, low bits = 63 - row
+        unsigned key = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, p, o);
-            if (ob > best || (ob == best && oi < p)) { best = ob; p = oi; }
+        for (int h = 0; h < TS / 32; ++h) {
+            int row = lane + 32 * h;
+            if (row < tw && !((used >> row) & 1ull)) {
+                unsigned hi = (unsigned)__double2hiint(cabs2(cb[row]));
+                unsigned kk = (hi & 0xFFFFFFC0u) | (unsigned)(63 - row);
+                key = kk > key ? kk : key;
+            }
         }
-        if (!(best > 1e-300)) {                      // singular (or NaN): flag it, keep going on any free row
-            p = __ffsll((long long)~used) - 1;
+        key = __reduce_max_sync(0xffffffffu, key);
+        int p = 63 - (int)(key & 63u);
+        const unsigned ex = (key >> 20) & 0x7FFu;
+        if (ex == 0u || ex == 0x7FFu) {              // zero / denormal / inf / nan pivot: flag it, keep going
+            if (ex == 0u) p = __ffsll((long long)(~used)) - 1;
             if (tid == 0) atomicExch(info, 1);
         }
         if (ty == (p >> 2)) {
@@ -214,14 +168,14 @@ tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx*
                 if (pi == 1) t = a[1][j];
                 if (pi == 2) t = a[2][j];
                 if (pi == 3) t = a[3][j];
-                rowbuf[C0 + j] = (C0 + j == c) ? make_double2(1.0, 0.0) : t;
+                sm.rowbuf[C0 + j] = (C0 + j == c) ? make_double2(1.0, 0.0) : t;
             }
         }
-        __syncthreads();
-        const cplx ipiv = crecip(cb[p]);
+        bar();
+        const cplx ipiv = fast_crecip(cb[p]);
         cplx pr[4], f[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pr[j] = cmul(rowbuf[C0 + j], ipiv);
+        for (int j = 0; j < 4; ++j) pr[j] = cmul(sm.rowbuf[C0 + j], ipiv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) f[i] = cb[R0 + i];
 #pragma unroll
@@ -236,9 +190,9 @@ tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx*
             }
         }
         used |= 1ull << p;
-        if (tid == 0) { prow_of_col[c] = p; pcol_of_row[p] = c; }
+        if (tid == 0) { sm.prow_of_col[c] = p; sm.pcol_of_row[p] = c; }
         const int cn = c + 1;
-        if (cn < 64 && tx == (cn >> 2)) {
+        if (cn < tw && tx == (cn >> 2)) {
             const int cj = cn & 3;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -246,22 +200,157 @@ tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx*
                 if (cj == 1) t = a[i][1];
                 if (cj == 2) t = a[i][2];
                 if (cj == 3) t = a[i][3];
-                colbuf[cn & 1][R0 + i] = t;
+                sm.colbuf[cn & 1][R0 + i] = t;
             }
         }
     }
-    __syncthreads();
-    cplx* D = dst + (long long)blockIdx.x * d_stride;
+    bar();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int orow = pcol_of_row[R0 + i];
+        if (R0 + i >= tw) continue;
+        const int orow = sm.pcol_of_row[R0 + i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int ocol = prow_of_col[C0 + j];
-            if (orow < tw && ocol < tw) D[(size_t)orow * d_ld + ocol] = a[i][j];
+            if (C0 + j >= tw) continue;
+            D[(size_t)orow * d_ld + sm.prow_of_col[C0 + j]] = a[i][j];
         }
     }
 }
+
+template <int TS>
+__global__ void __launch_bounds__(TS * TS / 16)
+tile_inverse_kernel(const cplx* src, long long s_stride, int s_ld, int tw, cplx* dst, long long d_stride, int d_ld,
+                    int* __restrict__ info, int sym) {
+    __shared__ TileInvSmem<TS> sm;
+    reg_tile_inverse<TS>(src + (long long)blockIdx.x * s_stride, s_ld, sym, tw, dst + (long long)blockIdx.x * d_stride,
+                         d_ld, sm, info, threadIdx.x, 1);
+}
+
+static void launch_tile_inverse(const cplx* src, long long s_stride, int s_ld, int tw, cplx* dst, long long d_stride,
+                                int d_ld, int* info, int sym, long long nb, cudaStream_t st) {
+    if (tw <= 32)
+        tile_inverse_kernel<32><<<(unsigned)nb, 64, 0, st>>>(src, s_stride, s_ld, tw, dst, d_stride, d_ld, info, sym);
+    else
+        tile_inverse_kernel<64><<<(unsigned)nb, 256, 0, st>>>(src, s_stride, s_ld, tw, dst, d_stride, d_ld, info, sym);
+    ++g_fdfd_launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused small-front level: one CTA per front does assemble -> Einv -> G -> S in shared memory.
+// Used for the bottom of the tree (k <= 32), where a level is millions of tiny fronts and the
+// generic path (four kernels, the full padded front written to and re-read from HBM) is pure memory
+// traffic.  Global traffic here: child Schur blocks (or planes) in, Einv / G / compact S out.
+// ------------------------------------------------------------------------------------------
+struct SmallFrontArgs {
+    int kind, kmax, mmax, nx, ny;
+    const int *cls, *k_cls;
+    const int *x0, *y0, *slot_lx, *slot_ly, *slot_right, *slot_up;     // leaf tables
+    const int *ch1, *ch2, *inv1, *inv2;                                // merge tables
+    const cplx *planes, *isxf, *isyf;
+    const cplx* Sc;      // child Schur blocks: entry (a, b), a >= b, of child c at Sc[c * sc + (kc + a) * nc + kc + b]
+    long long sc;
+    int kc, nc;
+    cplx *Einv, *G, *S;  // outputs; S compact [nb][mmax][mmax], lower triangle
+    int* info;
+};
+
+__device__ __forceinline__ void small_front_put(cplx* W, cplx* R, cplx* Sm, int k, int m, int p, int q, cplx v) {
+    // p >= q in front slot numbering (E slots first)
+    if (p < k) {
+        W[p * 2 * k + q] = v;
+        W[q * 2 * k + p] = v;
+    } else if (q < k) {
+        R[(p - k) * k + q] = v;
+    } else {
+        Sm[(p - k) * m + (q - k)] = v;
+    }
+}
+
+__global__ void small_front_kernel(SmallFrontArgs a) {
+    extern __shared__ __align__(16) unsigned char sf_smem[];
+    const int k = a.kmax, m = a.mmax, n = k + m, w2 = 2 * k;
+    cplx* W = reinterpret_cast<cplx*>(sf_smem);      // [k][2k]: row r = [ E[r][:] | Einv[r][:] ]
+    cplx* R = W + (size_t)k * w2;                     // [m][k]   F_RE
+    cplx* Gs = R + (size_t)m * k;                     // [m][k]   G
+    cplx* Sm = Gs + (size_t)m * k;                    // [m][m]   F_RR -> S (lower)
+    __shared__ TileInvSmem<32> tis;
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int c = a.cls[b];
+    const int kcls = a.k_cls[c];
+    const cplx zero = make_double2(0.0, 0.0);
+    for (int e = tid; e < k * w2 + 2 * m * k + m * m; e += nt) W[e] = zero;
+    __syncthreads();
+    for (int r = kcls + tid; r < k; r += nt) W[r * w2 + r] = make_double2(1.0, 0.0);       // padded pivots
+    // ---- assemble
+    if (a.kind == 0) {
+        const size_t ncell = (size_t)a.nx * a.ny;
+        for (int s = tid; s < n; s += nt) {
+            int r = a.slot_right[c * n + s];
+            if (r < 0) continue;
+            int u = a.slot_up[c * n + s];
+            int x = a.x0[b] + a.slot_lx[c * n + s], y = a.y0[b] + a.slot_ly[c * n + s];
+            if (x >= a.nx) x -= a.nx;
+            if (y >= a.ny) y -= a.ny;
+            size_t node = (size_t)x * a.ny + y;
+            const cplx d = row_scale(a.isxf, a.isyf, x, y);
+            small_front_put(W, R, Sm, k, m, s, s, cmul(a.planes[node], d));
+            small_front_put(W, R, Sm, k, m, max(s, r), min(s, r), cmul(a.planes[2 * ncell + node], d));
+            small_front_put(W, R, Sm, k, m, max(s, u), min(s, u), cmul(a.planes[4 * ncell + node], d));
+        }
+    } else {
+        const int* i1 = a.inv1 + (size_t)c * n;
+        const int* i2 = a.inv2 + (size_t)c * n;
+        const cplx* S1 = a.Sc + (long long)a.ch1[b] * a.sc;
+        const cplx* S2 = a.Sc + (long long)a.ch2[b] * a.sc;
+        for (int e = tid; e < n * n; e += nt) {
+            int p = e / n, q = e - p * n;
+            if (q > p) continue;
+            int a1 = i1[p], b1 = i1[q], a2 = i2[p], b2 = i2[q];
+            bool h1 = a1 >= 0 && b1 >= 0, h2 = a2 >= 0 && b2 >= 0;
+            if (!h1 && !h2) continue;
+            cplx v = zero;
+            if (h1) v = S1[(size_t)(a.kc + max(a1, b1)) * a.nc + a.kc + min(a1, b1)];
+            if (h2) v = cadd(v, S2[(size_t)(a.kc + max(a2, b2)) * a.nc + a.kc + min(a2, b2)]);
+            if (p == q && p < k && p >= kcls) continue;                  // padded pivot keeps its 1
+            small_front_put(W, R, Sm, k, m, p, q, v);
+        }
+    }
+    __syncthreads();
+    // ---- Einv (right half of W) by the first 64 threads, register-resident
+    if (tid < 64) reg_tile_inverse<32>(W, w2, 0, k, W + k, w2, tis, a.info, tid, 1);
+    __syncthreads();
+    // ---- G = F_RE Einv
+    cplx* Eo = a.Einv + b * (long long)k * k;
+    for (int e = tid; e < k * k; e += nt) Eo[e] = W[(e / k) * w2 + k + e % k];
+    cplx* Go = a.G + b * (long long)m * k;
+    for (int e = tid; e < m * k; e += nt) {
+        int i = e / k, cc = e - i * k;
+        cplx acc = zero;
+        for (int l = 0; l < k; ++l) cfma(acc, R[i * k + l], W[l * w2 + k + cc]);
+        Gs[e] = acc;
+        Go[e] = acc;
+    }
+    __syncthreads();
+    // ---- S = F_RR - G F_RE^T (lower)
+    cplx* So = a.S + b * (long long)m * m;
+    for (int e = tid; e < m * m; e += nt) {
+        int i = e / m, j = e - i * m;
+        if (j > i) continue;
+        cplx acc = Sm[e];
+        for (int l = 0; l < k; ++l) {
+            cplx g = Gs[i * k + l], r = R[j * k + l];
+            acc.x -= g.x * r.x - g.y * r.y;
+            acc.y -= g.x * r.y + g.y * r.x;
+        }
+        So[e] = acc;
+    }
+}
+
+static size_t small_front_smem(int k, int m) {
+    return sizeof(cplx) * ((size_t)k * 2 * k + 2 * (size_t)m * k + (size_t)m * m);
+}
+static bool small_front_ok(int k, int m) { return k <= 32 && small_front_smem(k, m) <= 220 * 1024; }
 
 // dst[b][c][r] = src[b][r][c] for an (rows x cols) block; 32 x 32 tiles through shared memory.
 // mirror != 0 (square, src == dst): copies the strict lower triangle onto the upper one instead.
@@ -551,6 +640,8 @@ void nd_destroy(NdSolver* s) {
     delete s;
 }
 
+int g_small_front_enabled = 1;     // A/B switch (fdfd_direct_set_small_fronts): 0 = generic path on every level
+
 static int chunks_for(long long per_front_elems, long long nb) {
     // enough CTAs to fill the machine when there are few big fronts, one CTA per front otherwise
     long long want = (148LL * 8 + nb - 1) / nb;
@@ -586,8 +677,7 @@ static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, l
                             cudaStream_t st) {
     if (n <= 64) {
         PhaseScope ph(PH_PIVOT, st);
-        tile_inverse_kernel<<<(unsigned)nb, 256, 0, st>>>(E, sE, ld, n, E, sE, ld, s->d_info, 0);
-        ++g_fdfd_launches;
+        launch_tile_inverse(E, sE, ld, n, E, sE, ld, s->d_info, 0, nb, st);
         FDFD_CHECK(cudaGetLastError());
         return 0;
     }
@@ -693,6 +783,36 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         // factor storage is allocated on the first factorisation and reused afterwards
         if (!L.Einv) FDFD_CHECK(cudaMalloc(&L.Einv, sizeof(cplx) * (size_t)nb * kmax * kmax));
         if (mmax > 0 && !L.G) FDFD_CHECK(cudaMalloc(&L.G, sizeof(cplx) * (size_t)nb * mmax * kmax));
+        if (small_front_ok(kmax, mmax) && mmax > 0 && g_small_front_enabled) {
+            // bottom of the tree: one fused kernel per level, compact Schur blocks handed to the parent
+            SmallFrontArgs a;
+            a.kind = L.kind; a.kmax = kmax; a.mmax = mmax; a.nx = s->nx; a.ny = s->ny;
+            a.cls = L.cls; a.k_cls = L.k_cls;
+            a.x0 = L.x0; a.y0 = L.y0; a.slot_lx = L.slot_lx; a.slot_ly = L.slot_ly;
+            a.slot_right = L.slot_right; a.slot_up = L.slot_up;
+            a.ch1 = L.ch1; a.ch2 = L.ch2; a.inv1 = L.inv1; a.inv2 = L.inv2;
+            a.planes = op->planes; a.isxf = op->isxf; a.isyf = op->isyf;
+            a.Sc = Fprev; a.sc = (long long)prev_n * prev_n; a.kc = prev_k; a.nc = prev_n;
+            a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
+            size_t smem = small_front_smem(kmax, mmax);
+            int threads = nmax <= 40 ? 64 : (nmax <= 64 ? 128 : 256);
+            if (smem > 48 * 1024)
+                FDFD_CHECK(cudaFuncSetAttribute(small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            {
+                PhaseScope ph(PH_SMALL, st);
+                small_front_kernel<<<(unsigned)nb, threads, smem, st>>>(a);
+                ++g_fdfd_launches;
+            }
+            FDFD_CHECK(cudaGetLastError());
+            s->factor_flops += 8.0 * (double)nb * ((double)kmax * kmax * kmax + (double)mmax * kmax * kmax +
+                                                   0.5 * (double)mmax * mmax * kmax);
+            s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * kmax + (size_t)nb * mmax * kmax);
+            Fprev = F;
+            prev_k = 0;
+            prev_n = mmax;
+            continue;
+        }
         {
             PhaseScope ph(PH_ASSEMBLE, st);
             if (L.kind == 0) {
@@ -710,18 +830,9 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         FDFD_CHECK(cudaGetLastError());
         // ---- Einv = F_EE^-1
         if (kmax <= 64) {
-            size_t smem = sizeof(cplx) * ((size_t)kmax * 2 * kmax + kmax);
-            int threads = kmax * kmax >= 512 ? 256 : (kmax * kmax >= 128 ? 128 : 64);
-            if (smem > 48 * 1024)
-                FDFD_CHECK(cudaFuncSetAttribute(pivot_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
             PhaseScope ph(PH_PIVOT, st);
-            if (kmax > 16)
-                tile_inverse_kernel<<<(unsigned)nb, 256, 0, st>>>(F, (long long)nmax * nmax, nmax, kmax, L.Einv,
-                                                                  (long long)kmax * kmax, kmax, s->d_info, 1);
-            else
-                pivot_inverse_kernel<<<(unsigned)nb, threads, smem, st>>>(F, nmax, 0, kmax, L.Einv, kmax, s->d_info, 1);
-            ++g_fdfd_launches;
+            launch_tile_inverse(F, (long long)nmax * nmax, nmax, kmax, L.Einv, (long long)kmax * kmax, kmax, s->d_info,
+                                1, nb, st);
         } else {
             {
                 PhaseScope ph(PH_EXTRACT, st);

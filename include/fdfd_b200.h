@@ -39,8 +39,8 @@ int fdfd_gemm_timing(int enable);
 int fdfd_gemm_timing_read(double* out6);
 int fdfd_dmma_peak(double* tflops);
 int fdfd_phase_timing(int enable);
-int fdfd_phase_timing_read(double* out12);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur */
-int fdfd_phase_timing_read_levels(double* out, int max_levels);   /* out[level * 12 + phase] */
+int fdfd_phase_timing_read(double* out13);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur,small */
+int fdfd_phase_timing_read_levels(double* out, int max_levels);   /* out[level * 13 + phase] */
 int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflops);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
@@ -137,6 +137,8 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, 
 
 /* kernel selection for A/B measurements: 0 = persistent kernel for large problems (default), 1 = tiled only */
 int fdfd_zgemm_set_variant(int v);
+/* 1 (default): levels of tiny fronts (k <= 32) run as one fused kernel each; 0: generic path everywhere */
+int fdfd_direct_set_small_fronts(int enable);
 /* device-only timing of one batched GEMM shape (CUDA events, `iters` launches) */
 int fdfd_zgemm_bench(int M, int N, int K, int batch, int mode, int transb, int lower, int iters,
                      double* ms_per_launch);

@@ -26,10 +26,10 @@ for n in sizes:
     op.lib.fdfd_phase_timing(1)
     d.factor()
     t4 = time.time()
-    ph = np.zeros(12)
+    ph = np.zeros(13)
     op.lib.fdfd_phase_timing_read(_lib.ptr(ph))
     op.lib.fdfd_phase_timing(0)
-    names = "assemble pivot panel rowgemm copy update expand solve_fwd solve_bwd stencil ggemm schur".split()
+    names = "assemble pivot panel rowgemm copy update expand solve_fwd solve_bwd stencil ggemm schur small".split()
     print("   phases ms:", " ".join(f"{k}={v:.1f}" for k, v in zip(names, ph)), "sum=%.1f" % ph.sum(), flush=True)
     b = np.zeros((n, n), dtype=complex)
     b[n // 2, n // 2] = 1j * OMEGA
@@ -39,7 +39,7 @@ for n in sizes:
     d.factor()
     x = d.solve(b, max_refine=-1)
     nl = len(d.levels)
-    pl = np.zeros((nl, 12))
+    pl = np.zeros((nl, 13))
     op.lib.fdfd_phase_timing_read_levels(_lib.ptr(pl), nl)
     op.lib.fdfd_phase_timing(0)
     print("   per level ms (" + " ".join(names) + "):")
