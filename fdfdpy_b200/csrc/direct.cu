@@ -235,9 +235,67 @@ static void launch_tile_inverse(const cplx* src, long long s_stride, int s_ld, i
     ++g_fdfd_launches;
 }
 
+// One warp inverts a k x k matrix (k <= KMAX <= 32) held one ROW per lane in registers: in-place
+// Gauss-Jordan with implicit partial pivoting (see reg_tile_inverse), pivot search by one integer warp
+// reduction, pivot row broadcast by shuffles; no shared memory, no barriers.  E / Einv are row-major
+// with leading dimension ld; Einv may alias E.
+template <int KMAX>
+__device__ __forceinline__ void warp_invert(const cplx* E, cplx* Einv, int ld, int k, int* info) {
+    const int lane = threadIdx.x & 31;
+    cplx a[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        a[j] = (lane < k && j < k) ? E[lane * ld + j] : make_double2(lane == j ? 1.0 : 0.0, 0.0);
+    unsigned used = 0u;
+    int my_col = lane;                                  // column this row was the pivot of
+    int prow_of_col = lane;                             // lane c keeps the pivot row of column c
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+        if (c < k) {                                    // warp-uniform
+            unsigned key = 0u;
+            if (lane < k && !((used >> lane) & 1u))
+                key = ((unsigned)__double2hiint(cabs2(a[c])) & 0xFFFFFFE0u) | (unsigned)(31 - lane);
+            key = __reduce_max_sync(0xffffffffu, key);
+            int p = 31 - (int)(key & 31u);
+            const unsigned ex = (key >> 20) & 0x7FFu;
+            if (ex == 0u || ex == 0x7FFu) {
+                if (ex == 0u) p = __ffs((int)(~used)) - 1;
+                if (lane == 0) atomicExch(info, 1);
+            }
+            cplx piv;
+            piv.x = __shfl_sync(0xffffffffu, a[c].x, p);
+            piv.y = __shfl_sync(0xffffffffu, a[c].y, p);
+            const cplx ipiv = fast_crecip(piv);
+            const cplx f = a[c];
+            const bool is_p = lane == p;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+                cplx t = (j == c) ? make_double2(1.0, 0.0) : a[j];
+                cplx pr;
+                pr.x = __shfl_sync(0xffffffffu, t.x, p);
+                pr.y = __shfl_sync(0xffffffffu, t.y, p);
+                pr = cmul(pr, ipiv);
+                cplx v = (j == c) ? make_double2(0.0, 0.0) : a[j];
+                v.x -= f.x * pr.x - f.y * pr.y;
+                v.y -= f.x * pr.y + f.y * pr.x;
+                a[j] = is_p ? pr : v;
+            }
+            used |= 1u << p;
+            if (is_p) my_col = c;
+            if (lane == c) prow_of_col = p;
+        }
+    }
+    // A^-1[pc(r)][pr(c)] = M[r][c]:  this lane's row goes to output row my_col, its entry j to column pr(j)
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+        int oc = __shfl_sync(0xffffffffu, prow_of_col, j);
+        if (lane < k && j < k) Einv[my_col * ld + oc] = a[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // fused small-front level: one CTA per front does assemble -> Einv -> G -> S in shared memory.
-// Used for the bottom of the tree (k <= 32), where a level is millions of tiny fronts and the
+// Used for the bottom of the tree (k <= 16), where a level is millions of tiny fronts and the
 // generic path (four kernels, the full padded front written to and re-read from HBM) is pure memory
 // traffic.  Global traffic here: child Schur blocks (or planes) in, Einv / G / compact S out.
 // ------------------------------------------------------------------------------------------
@@ -266,24 +324,48 @@ __device__ __forceinline__ void small_front_put(cplx* W, cplx* R, cplx* Sm, int 
     }
 }
 
+// sum of the two children's Schur entries that land on front entry (p, q), p >= q
+__device__ __forceinline__ cplx small_front_gather(const SmallFrontArgs& a, const cplx* S1, const cplx* S2,
+                                                   const int* i1, const int* i2, int p, int q) {
+    cplx v = make_double2(0.0, 0.0);
+    int a1 = i1[p], b1 = i1[q], a2 = i2[p], b2 = i2[q];
+    if (a1 >= 0 && b1 >= 0) v = S1[(size_t)(a.kc + max(a1, b1)) * a.nc + a.kc + min(a1, b1)];
+    if (a2 >= 0 && b2 >= 0) v = cadd(v, S2[(size_t)(a.kc + max(a2, b2)) * a.nc + a.kc + min(a2, b2)]);
+    return v;
+}
+
+template <int KMAX>
 __global__ void small_front_kernel(SmallFrontArgs a) {
     extern __shared__ __align__(16) unsigned char sf_smem[];
     const int k = a.kmax, m = a.mmax, n = k + m, w2 = 2 * k;
     cplx* W = reinterpret_cast<cplx*>(sf_smem);      // [k][2k]: row r = [ E[r][:] | Einv[r][:] ]
     cplx* R = W + (size_t)k * w2;                     // [m][k]   F_RE
     cplx* Gs = R + (size_t)m * k;                     // [m][k]   G
-    cplx* Sm = Gs + (size_t)m * k;                    // [m][m]   F_RR -> S (lower)
-    __shared__ TileInvSmem<32> tis;
+    cplx* Sm = Gs + (size_t)m * k;                    // [m][m]   F_RR, leaf levels only
+    __shared__ int s_i1[128], s_i2[128];
     const long long b = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int c = a.cls[b];
     const int kcls = a.k_cls[c];
     const cplx zero = make_double2(0.0, 0.0);
-    for (int e = tid; e < k * w2 + 2 * m * k + m * m; e += nt) W[e] = zero;
+    const bool leaf = a.kind == 0;
+    const cplx *S1 = nullptr, *S2 = nullptr;
+    {
+        const int nz = k * w2 + m * k + (leaf ? m * k + m * m : 0);      // W, R (and Gs, Sm for a leaf)
+        for (int e = tid; e < nz; e += nt) W[e] = zero;
+    }
+    if (!leaf) {
+        for (int i = tid; i < n; i += nt) {
+            s_i1[i] = a.inv1[(size_t)c * n + i];
+            s_i2[i] = a.inv2[(size_t)c * n + i];
+        }
+        S1 = a.Sc + (long long)a.ch1[b] * a.sc;
+        S2 = a.Sc + (long long)a.ch2[b] * a.sc;
+    }
     __syncthreads();
     for (int r = kcls + tid; r < k; r += nt) W[r * w2 + r] = make_double2(1.0, 0.0);       // padded pivots
-    // ---- assemble
-    if (a.kind == 0) {
+    // ---- assemble F_EE, F_RE (and F_RR for a leaf)
+    if (leaf) {
         const size_t ncell = (size_t)a.nx * a.ny;
         for (int s = tid; s < n; s += nt) {
             int r = a.slot_right[c * n + s];
@@ -299,26 +381,16 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
             small_front_put(W, R, Sm, k, m, max(s, u), min(s, u), cmul(a.planes[4 * ncell + node], d));
         }
     } else {
-        const int* i1 = a.inv1 + (size_t)c * n;
-        const int* i2 = a.inv2 + (size_t)c * n;
-        const cplx* S1 = a.Sc + (long long)a.ch1[b] * a.sc;
-        const cplx* S2 = a.Sc + (long long)a.ch2[b] * a.sc;
-        for (int e = tid; e < n * n; e += nt) {
-            int p = e / n, q = e - p * n;
-            if (q > p) continue;
-            int a1 = i1[p], b1 = i1[q], a2 = i2[p], b2 = i2[q];
-            bool h1 = a1 >= 0 && b1 >= 0, h2 = a2 >= 0 && b2 >= 0;
-            if (!h1 && !h2) continue;
-            cplx v = zero;
-            if (h1) v = S1[(size_t)(a.kc + max(a1, b1)) * a.nc + a.kc + min(a1, b1)];
-            if (h2) v = cadd(v, S2[(size_t)(a.kc + max(a2, b2)) * a.nc + a.kc + min(a2, b2)]);
-            if (p == q && p < k && p >= kcls) continue;                  // padded pivot keeps its 1
+        for (int e = tid; e < n * k; e += nt) {          // columns q < k of the lower triangle
+            int p = e / k, q = e - p * k;
+            if (q > p || (p == q && p >= kcls)) continue;                // padded pivot keeps its 1
+            cplx v = small_front_gather(a, S1, S2, s_i1, s_i2, p, q);
             small_front_put(W, R, Sm, k, m, p, q, v);
         }
     }
     __syncthreads();
-    // ---- Einv (right half of W) by the first 64 threads, register-resident
-    if (tid < 64) reg_tile_inverse<32>(W, w2, 0, k, W + k, w2, tis, a.info, tid, 1);
+    // ---- Einv (right half of W) by the first warp, one row per lane
+    if (tid < 32) warp_invert<KMAX>(W, W + k, w2, k, a.info);
     __syncthreads();
     // ---- G = F_RE Einv
     cplx* Eo = a.Einv + b * (long long)k * k;
@@ -332,12 +404,13 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
         Go[e] = acc;
     }
     __syncthreads();
-    // ---- S = F_RR - G F_RE^T (lower)
+    // ---- S = F_RR - G F_RE^T (lower), F_RR gathered from the children on the fly
     cplx* So = a.S + b * (long long)m * m;
     for (int e = tid; e < m * m; e += nt) {
         int i = e / m, j = e - i * m;
         if (j > i) continue;
-        cplx acc = Sm[e];
+        cplx acc = leaf ? Sm[e] : small_front_gather(a, S1, S2, s_i1, s_i2, k + i, k + j);
+#pragma unroll 5
         for (int l = 0; l < k; ++l) {
             cplx g = Gs[i * k + l], r = R[j * k + l];
             acc.x -= g.x * r.x - g.y * r.y;
@@ -347,10 +420,12 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
     }
 }
 
-static size_t small_front_smem(int k, int m) {
-    return sizeof(cplx) * ((size_t)k * 2 * k + 2 * (size_t)m * k + (size_t)m * m);
+static size_t small_front_smem(int k, int m, bool leaf) {
+    return sizeof(cplx) * ((size_t)k * 2 * k + 2 * (size_t)m * k + (leaf ? (size_t)m * m : 0));
 }
-static bool small_front_ok(int k, int m) { return k <= 32 && small_front_smem(k, m) <= 220 * 1024; }
+static bool small_front_ok(int k, int m, bool leaf) {
+    return k <= 16 && k + m <= 128 && small_front_smem(k, m, leaf) <= 200 * 1024;
+}
 
 // dst[b][c][r] = src[b][r][c] for an (rows x cols) block; 32 x 32 tiles through shared memory.
 // mirror != 0 (square, src == dst): copies the strict lower triangle onto the upper one instead.
@@ -515,6 +590,33 @@ forward_mv_kernel(const cplx* __restrict__ Einv, const cplx* __restrict__ G, con
             if (r < kmax) yE[(b * kmax + r) * NR + j] = acc[j];
             else ring[(b * mmax + (r - kmax)) * NR + j] = csub(v[r * NR + j], acc[j]);
         }
+    }
+}
+
+// the same with one THREAD per output row, for the levels of tiny fronts (k <= 16) where a warp per
+// row would leave most lanes idle
+template <int NR>
+__global__ void __launch_bounds__(256)
+forward_mv_thread_kernel(const cplx* __restrict__ Einv, const cplx* __restrict__ G, const cplx* __restrict__ f,
+                         cplx* __restrict__ yE, cplx* __restrict__ ring, int kmax, int mmax, int nmax, long long nb) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * nmax) return;
+    long long b = gid / nmax;
+    int r = (int)(gid % nmax);
+    const cplx* row = r < kmax ? Einv + (b * kmax + r) * kmax : G + (b * mmax + (r - kmax)) * kmax;
+    const cplx* v = f + b * nmax * NR;
+    cplx acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int c = 0; c < kmax; ++c) {
+        cplx m = ldg_c(row + c);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        if (r < kmax) yE[(b * kmax + r) * NR + j] = acc[j];
+        else ring[(b * mmax + (r - kmax)) * NR + j] = csub(v[r * NR + j], acc[j]);
     }
 }
 
@@ -783,7 +885,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         // factor storage is allocated on the first factorisation and reused afterwards
         if (!L.Einv) FDFD_CHECK(cudaMalloc(&L.Einv, sizeof(cplx) * (size_t)nb * kmax * kmax));
         if (mmax > 0 && !L.G) FDFD_CHECK(cudaMalloc(&L.G, sizeof(cplx) * (size_t)nb * mmax * kmax));
-        if (small_front_ok(kmax, mmax) && mmax > 0 && g_small_front_enabled) {
+        if (small_front_ok(kmax, mmax, L.kind == 0) && mmax > 0 && g_small_front_enabled) {
             // bottom of the tree: one fused kernel per level, compact Schur blocks handed to the parent
             SmallFrontArgs a;
             a.kind = L.kind; a.kmax = kmax; a.mmax = mmax; a.nx = s->nx; a.ny = s->ny;
@@ -794,14 +896,17 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             a.planes = op->planes; a.isxf = op->isxf; a.isyf = op->isyf;
             a.Sc = Fprev; a.sc = (long long)prev_n * prev_n; a.kc = prev_k; a.nc = prev_n;
             a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
-            size_t smem = small_front_smem(kmax, mmax);
+            size_t smem = small_front_smem(kmax, mmax, L.kind == 0);
             int threads = nmax <= 40 ? 64 : (nmax <= 64 ? 128 : 256);
+            auto kern = kmax <= 3 ? small_front_kernel<3>
+                        : kmax <= 7 ? small_front_kernel<7>
+                        : kmax <= 9 ? small_front_kernel<9>
+                        : kmax <= 12 ? small_front_kernel<12> : small_front_kernel<16>;
             if (smem > 48 * 1024)
-                FDFD_CHECK(cudaFuncSetAttribute(small_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
+                FDFD_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 PhaseScope ph(PH_SMALL, st);
-                small_front_kernel<<<(unsigned)nb, threads, smem, st>>>(a);
+                kern<<<(unsigned)nb, threads, smem, st>>>(a);
                 ++g_fdfd_launches;
             }
             FDFD_CHECK(cudaGetLastError());
@@ -925,8 +1030,12 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         else
             { merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
                                                                         L.inv2, L.nmax, L.child_mmax, nb); ++g_fdfd_launches; }
-        { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
-                                                                       L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        if (L.kmax <= 16)
+            { forward_mv_thread_kernel<NR><<<ceil_div(tot, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
+                                                                             L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        else
+            { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
+                                                                           L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         std::swap(ring_prev, ring_cur);
     }
