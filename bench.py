@@ -244,6 +244,22 @@ def run_ours(args):
     dev_ms = ms.value
     relres_dev = relres.value
 
+    # ---------------- where the step goes: the four library calls timed one by one (outside the timed region)
+    breakdown = {}
+    calls = [
+        ("assemble", lambda: lib.fdfd_op_assemble_dev(op.h, d_eps, None, 1)),
+        ("factor", lambda: lib.fdfd_direct_factor(direct.h, op.h)),
+        ("solve_refine", lambda: lib.fdfd_direct_solve_dev(direct.h, op.h, d_b, d_x, 1, 3, 1e-12, C.byref(relres),
+                                                          C.byref(steps_ref))),
+        ("derive_fields", lambda: lib.fdfd_op_derive_fields_dev(op.h, d_x, d_f, d_f2, -1)),
+    ]
+    for name, fn in calls:
+        tms = C.c_double(0)
+        _lib.check(lib.fdfd_timer_start(op.h))
+        _lib.check(fn())
+        _lib.check(lib.fdfd_timer_stop(op.h, C.byref(tms)))
+        breakdown[name + "_ms"] = tms.value
+
     # ---------------- stencil kernel on its own (HBM roofline of the matrix-free path) ----------------
     reps = 20
     for _ in range(3):
@@ -304,7 +320,11 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     big_ms, big_fl, big_n = gt[0], gt[1], gt[2]
     achieved = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
-    fp64_peak = dmma.value
+    # FP64 tensor-pipe ceiling: 64 DFMA/clk/SM (one m8n8k4 DMMA per SM sub-partition every 4 clocks) x 148 SMs at
+    # the SM clock sampled under load; the register-resident DMMA probe is reported next to it (it is
+    # power-limited when run alone: every SM issuing DMMA back to back pulls the clock below what the solver sees)
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    fp64_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
     line = {
         "metric": "fdfd_solve_throughput", "value": value, "unit": "Mcell/s",
         "solves_per_s": world / (ms_per_step * 1e-3),
@@ -313,18 +333,22 @@ def run_ours(args):
         "config": workload_config(n),
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "Mcell/s", "ms_per_step": e2e_max * 1e3,
-                "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": int(3 * nbytes),
-                "host_memory": "pageable numpy arrays through Simulation (eps_r setter + solve_fields)",
+                "h2d_bytes_per_step": int(eps.nbytes + src.nbytes), "d2h_bytes_per_step": int(3 * nbytes),
+                "host_memory": "inputs: the caller's pageable float64 numpy arrays (eps_r setter, src), widened to "
+                               "complex on the device; outputs: three complex128 fields in page-locked arrays "
+                               "from the library's pool, through Simulation.solve_fields",
                 "relres": e2e_relres},
         "gpu_launches": int(launches),
         "relres": relres_dev, "refine_steps": steps_ref.value,
         "wall_ms_per_step": wall / args.steps * 1e3,
+        "breakdown": breakdown,
         "roofline": {
             "kernel": "zgemm_dmma_kernel<4,2,3> (rank-T sweep update, complex128 on DMMA m8n8k4)",
             "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-            "peak_source": "FP64 DMMA ceiling measured in this run by a register-resident mma.sync loop "
+            "peak_source": "FP64 tensor pipe: 148 SMs x 128 flop/clk x the SM clock sampled under load "
                            "(MEASURED_PEAKS.json has no FP64 entry; vendor-nominal is 40 TFLOP/s)",
+            "dmma_probe_tflops": dmma.value,
             "launches_timed": int(big_n), "kernel_ms_per_step": big_ms / args.steps,
             "share_of_step": big_ms / dev_ms if dev_ms else None,
             "algorithmic_flops_per_step": big_fl / args.steps,

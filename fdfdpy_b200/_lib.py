@@ -6,6 +6,8 @@ symbol table can be checked on a CPU box).
 """
 import ctypes as C
 import os
+import threading
+import weakref
 
 import numpy as np
 
@@ -50,6 +52,11 @@ SIGNATURES = {
     "fdfd_dmma_probe": (C.c_int, [C.c_int, C.c_int, _dp]),
     "fdfd_host_register": (C.c_int, [_vp, C.c_double]),
     "fdfd_host_unregister": (C.c_int, [_vp]),
+    "fdfd_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_double]),
+    "fdfd_host_free": (C.c_int, [_vp]),
+    "fdfd_op_assemble_host_f64": (C.c_int, [_vp, _vp, C.c_int]),
+    "fdfd_solve_fields_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, C.c_int,
+                                         C.c_int, C.c_double, _dp, _ip]),
     "fdfd_op_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.c_int, C.c_double]),
     "fdfd_op_destroy": (None, [_vp]),
@@ -133,3 +140,53 @@ def as_c128(a):
 
 def as_i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ---- page-locked result arrays -------------------------------------------------------------------
+# Fields handed back to the caller are numpy arrays over cudaHostAlloc'ed buffers: the device->host
+# copy runs at full PCIe rate and skips the first-touch page faults of a fresh np.empty.  A buffer
+# returns to the free list when the last array viewing it is garbage collected, so an optimisation
+# loop that overwrites its fields every iteration keeps re-using the same few buffers.
+PINNED_MIN_BYTES = 1 << 20          # smaller arrays are ordinary numpy memory
+PINNED_KEEP_BYTES = 8 << 30         # free-list cap; beyond it released buffers go back to the driver
+_pool_lock = threading.Lock()
+_pool_free = {}                     # nbytes -> [address, ...]
+_pool_free_bytes = 0
+
+
+def _pinned_release(addr, nbytes):
+    global _pool_free_bytes
+    with _pool_lock:
+        if _pool_free_bytes + nbytes <= PINNED_KEEP_BYTES:
+            _pool_free.setdefault(nbytes, []).append(addr)
+            _pool_free_bytes += nbytes
+            return
+    try:
+        _lib.fdfd_host_free(_vp(addr))
+    except Exception:
+        pass
+
+
+def pinned_empty(shape, dtype=c128):
+    """np.empty over page-locked memory from the pool (plain np.empty for small arrays or when the
+    driver refuses to pin more memory)."""
+    global _pool_free_bytes
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes < PINNED_MIN_BYTES:
+        return np.empty(shape, dtype=dtype)
+    lib = load()
+    addr = None
+    with _pool_lock:
+        lst = _pool_free.get(nbytes)
+        if lst:
+            addr = lst.pop()
+            _pool_free_bytes -= nbytes
+    if addr is None:
+        p = _vp()
+        if lib.fdfd_host_alloc(C.byref(p), float(nbytes)) != 0 or not p.value:
+            return np.empty(shape, dtype=dtype)
+        addr = p.value
+    buf = (C.c_char * nbytes).from_address(addr)
+    weakref.finalize(buf, _pinned_release, addr, nbytes)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)

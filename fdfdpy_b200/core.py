@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import as_c128, as_i32, check, ptr
+from ._lib import as_c128, as_i32, check, pinned_empty, ptr
 from .ndplan import build_plan
 
 POL = {"Ez": 0, "Hz": 1}
@@ -50,11 +50,18 @@ class MaxwellOperator:
         self.assemble(eps_r, eps_nl, averaging)
 
     def assemble(self, eps_r, eps_nl=None, averaging=True):
-        er = as_c128(eps_r)
-        if er.shape != (self.nx, self.ny):
+        eps_r = np.asarray(eps_r)
+        if eps_r.shape != (self.nx, self.ny):
             raise ValueError("eps_r shape changed; build a new operator")
-        en = None if eps_nl is None else as_c128(np.broadcast_to(eps_nl, er.shape))
-        check(self.lib.fdfd_op_assemble_host(self.h, ptr(er), ptr(en), int(bool(averaging))))
+        if eps_nl is None and np.isrealobj(eps_r):
+            # real permittivity goes over PCIe as float64 and is widened on the device
+            er = np.ascontiguousarray(eps_r, dtype=np.float64)
+            check(self.lib.fdfd_op_assemble_host_f64(self.h, ptr(er), int(bool(averaging))))
+            en = None
+        else:
+            er = as_c128(eps_r)
+            en = None if eps_nl is None else as_c128(np.broadcast_to(eps_nl, er.shape))
+            check(self.lib.fdfd_op_assemble_host(self.h, ptr(er), ptr(en), int(bool(averaging))))
         self.has_nl = en is not None
         if self._direct is not None:
             self._direct.factored = False
@@ -71,7 +78,7 @@ class MaxwellOperator:
     def dot(self, x, fused=False):
         x = as_c128(x)
         nvec = x.size // (self.nx * self.ny)
-        y = np.empty_like(x)
+        y = pinned_empty(x.shape)
         check(self.lib.fdfd_op_apply_host(self.h, ptr(x), ptr(y), nvec, int(fused)))
         return y
 
@@ -101,7 +108,7 @@ class MaxwellOperator:
     def derive_fields(self, X, averaging=None):
         """In-plane fields; ``averaging`` overrides the operator's Hz edge-averaging flag."""
         X = as_c128(X)
-        f1, f2 = np.empty_like(X), np.empty_like(X)
+        f1, f2 = pinned_empty(X.shape), pinned_empty(X.shape)
         av = -1 if averaging is None else int(bool(averaging))
         check(self.lib.fdfd_op_derive_fields_host(self.h, ptr(X), ptr(f1), ptr(f2), av))
         return f1.reshape(self.nx, self.ny), f2.reshape(self.nx, self.ny)
@@ -190,12 +197,34 @@ class DirectSolver:
         b = as_c128(b)
         n = self.op.nx * self.op.ny
         nrhs = b.size // n
-        x = np.empty_like(b)
+        x = pinned_empty(b.shape)
         rr, steps = C.c_double(0), C.c_int(0)
         check(self.lib.fdfd_direct_solve_host(self.h, self.op.h, ptr(b), ptr(x), nrhs, int(max_refine), float(tol),
                                               C.byref(rr), C.byref(steps)))
         self.last_relres, self.last_refine_steps = rr.value, steps.value
         return x
+
+    def solve_fields(self, src, scale, averaging=None, max_refine=3, tol=1e-12):
+        """x = A^-1 (scale * src) and the two in-plane fields in ONE library call
+        (simulation.py:113-178): src crosses PCIe once (as float64 when it is real), x never comes
+        back up for the derived fields, and the three results land in page-locked arrays."""
+        if not self.factored:
+            self.factor()
+        src = np.asarray(src)
+        shape = (self.op.nx, self.op.ny)
+        if src.size != shape[0] * shape[1]:
+            raise ValueError("src must have the grid's shape")
+        real = np.isrealobj(src)
+        s = np.ascontiguousarray(src, dtype=np.float64 if real else np.complex128)
+        x, f1, f2 = pinned_empty(shape), pinned_empty(shape), pinned_empty(shape)
+        rr, steps = C.c_double(0), C.c_int(0)
+        av = -1 if averaging is None else int(bool(averaging))
+        scale = complex(scale)
+        check(self.lib.fdfd_solve_fields_host(self.h, self.op.h, ptr(s), int(real), scale.real, scale.imag, ptr(x),
+                                              ptr(f1), ptr(f2), av, int(max_refine), float(tol), C.byref(rr),
+                                              C.byref(steps)))
+        self.last_relres, self.last_refine_steps = rr.value, steps.value
+        return x, f1, f2
 
 
 def mode_solve(eps_line, omega, dl, pol, L0, neff, order=1, averaged=False):

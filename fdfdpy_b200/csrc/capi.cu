@@ -201,6 +201,11 @@ int fdfd_host_register(void* host, double bytes) {
     FDFD_CHECK(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault));
     return 0;
 }
+int fdfd_host_alloc(void** host_ptr, double bytes) {
+    FDFD_CHECK(cudaHostAlloc(host_ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+int fdfd_host_free(void* host_ptr) { FDFD_CHECK(cudaFreeHost(host_ptr)); return 0; }
 int fdfd_host_unregister(void* host) { FDFD_CHECK(cudaHostUnregister(host)); return 0; }
 int fdfd_op_sync(fdfd_op* op) { FDFD_CHECK(cudaStreamSynchronize(op->stream)); return 0; }
 
@@ -222,6 +227,17 @@ int fdfd_op_assemble_host(fdfd_op* op, const double* eps_r, const double* eps_nl
     FDFD_CHECK(cudaMemcpyAsync(op->eps_r, eps_r, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
     if (eps_nl) FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, eps_nl, sizeof(cplx) * n, cudaMemcpyHostToDevice, op->stream));
     if (op_assemble_dev(op, op->eps_r, eps_nl ? op->eps_nl : nullptr, averaging)) return -1;
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+int fdfd_op_assemble_host_f64(fdfd_op* op, const double* eps_r_f64, int averaging) {
+    // real permittivity: half the PCIe bytes, widened to complex on the device
+    size_t n = op->n();
+    cplx* io = nullptr;
+    if (op_io_buffer(op, &io)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(io, eps_r_f64, sizeof(double) * n, cudaMemcpyHostToDevice, op->stream));
+    if (op_scale_expand(op, io, 1, make_double2(1.0, 0.0), op->eps_r, n)) return -1;
+    if (op_assemble_dev(op, op->eps_r, nullptr, averaging)) return -1;
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     return 0;
 }
@@ -303,6 +319,25 @@ int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b, double*
     FDFD_CHECK(cudaMemcpyAsync(db.p, b, sizeof(cplx) * cnt, cudaMemcpyHostToDevice, op->stream));
     if (fdfd_direct_solve_dev(s, op, db.p, dx.p, nrhs, max_refine, tol, relres, refine_steps)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(x, dx.p, sizeof(cplx) * cnt, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+
+int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
+                           double scale_im, double* x, double* f1, double* f2, int averaging, int max_refine,
+                           double tol, double* relres, int* refine_steps) {
+    const size_t n = op->n();
+    cplx* io = nullptr;
+    if (op_io_buffer(op, &io)) return -1;
+    cplx *b = io, *xx = io + n, *g1 = io + 2 * n, *g2 = io + 3 * n;
+    FDFD_CHECK(cudaMemcpyAsync(g1, src, (src_is_real ? sizeof(double) : sizeof(cplx)) * n, cudaMemcpyHostToDevice,
+                               op->stream));
+    if (op_scale_expand(op, g1, src_is_real, make_double2(scale_re, scale_im), b, n)) return -1;
+    if (fdfd_direct_solve_dev(s, op, b, xx, 1, max_refine, tol, relres, refine_steps)) return -1;
+    if (op_derive_fields(op, xx, g1, g2, averaging)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(x, xx, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(f1, g1, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(f2, g2, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     return 0;
 }

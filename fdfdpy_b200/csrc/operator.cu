@@ -257,9 +257,36 @@ void op_destroy(FdfdOp* op) {
     if (!op) return;
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
+    if (op->io_buf) cudaFree(op->io_buf);
     if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
     cudaStreamDestroy(op->stream);
     delete op;
+}
+
+int op_io_buffer(FdfdOp* op, cplx** out) {
+    if (!op->io_buf) FDFD_CHECK(cudaMalloc(&op->io_buf, sizeof(cplx) * 4 * op->n()));
+    *out = op->io_buf;
+    return 0;
+}
+
+template <bool REAL>
+__global__ void scale_expand_kernel(const void* __restrict__ in, cplx scale, cplx* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (REAL) {
+        double v = static_cast<const double*>(in)[i];
+        out[i] = make_double2(v * scale.x, v * scale.y);
+    } else {
+        out[i] = cmul(static_cast<const cplx*>(in)[i], scale);
+    }
+}
+
+int op_scale_expand(const FdfdOp* op, const void* d_in, int in_is_real, cplx scale, cplx* d_out, size_t n) {
+    if (in_is_real) scale_expand_kernel<true><<<ceil_div(n, 256), 256, 0, op->stream>>>(d_in, scale, d_out, n);
+    else scale_expand_kernel<false><<<ceil_div(n, 256), 256, 0, op->stream>>>(d_in, scale, d_out, n);
+    ++g_fdfd_launches;
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
 }
 
 int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging) {

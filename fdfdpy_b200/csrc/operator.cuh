@@ -21,6 +21,8 @@ struct FdfdOp {
     cplx *eps_r, *eps_nl;
     // five stencil planes c0,cxm,cxp,cym,cyp (device, 5*nx*ny)
     cplx *planes;
+    // lazily allocated staging for the *_host entry points (4*nx*ny complex: b, x, f1, f2)
+    cplx *io_buf;
     size_t n() const { return (size_t)nx * ny; }
 };
 
@@ -35,5 +37,9 @@ int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
 int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
 // r = b - A x (planes), returns nothing; used by iterative refinement
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec);
+// staging buffer of the host entry points (allocated on first use, kept until op_destroy)
+int op_io_buffer(FdfdOp* op, cplx** out);
+// out[i] = scale * in[i] for n real (in_is_real) or complex inputs; in and out must not overlap
+int op_scale_expand(const FdfdOp* op, const void* d_in, int in_is_real, cplx scale, cplx* d_out, size_t n);
 // in-plane fields from the solved transverse field (simulation.py:138-176)
 int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2, int averaging);

@@ -192,23 +192,26 @@ class Simulation:
         s = solver.lower()
         if s not in DIRECT_SOLVERS + KRYLOV_SOLVERS:
             raise ValueError('Invalid solver choice: {}, options are pardiso or scipy'.format(str(solver)))
-        b = np.asarray(self.src) * 1j * self.omega
+        src = np.asarray(self.src)
         op = self._op if not include_nl else self._nl_operator(self.eps_nl)
-        if not b.any():
-            X = np.zeros(b.shape, dtype=np.complex128)      # linalg.py:129-130
-        elif s in KRYLOV_SOLVERS:
-            X, info = op.krylov(b, method=s, tol=1e-12, maxiter=500000)
-            self.last_solve = info
-            if not info['converged']:
-                raise RuntimeError("{} did not converge: {}".format(s, info))
-        elif not include_nl:
+        if not include_nl and s in DIRECT_SOLVERS and src.any():
+            # the hot path: one library call, b = i w src formed on the device
             d = self._linear_factors()
-            X = d.solve(b)
+            X, f1, f2 = d.solve_fields(src, 1j * self.omega, averaging=averaging)
             self.last_solve = dict(relres=d.last_relres, refine_steps=d.last_refine_steps)
         else:
-            X = self._solve_perturbed(op, b)
-        X = X.reshape(self.Nx, self.Ny)
-        f1, f2 = op.derive_fields(X, averaging=averaging)
+            b = src * 1j * self.omega
+            if not b.any():
+                X = np.zeros(b.shape, dtype=np.complex128)      # linalg.py:129-130
+            elif s in KRYLOV_SOLVERS:
+                X, info = op.krylov(b, method=s, tol=1e-12, maxiter=500000)
+                self.last_solve = info
+                if not info['converged']:
+                    raise RuntimeError("{} did not converge: {}".format(s, info))
+            else:
+                X = self._solve_perturbed(op, b)
+            X = X.reshape(self.Nx, self.Ny)
+            f1, f2 = op.derive_fields(X, averaging=averaging)
         names = ('Hx', 'Hy', 'Ez') if self.pol == 'Ez' else ('Ex', 'Ey', 'Hz')
         if not include_nl:
             for k, v in zip(names, (f1, f2, X)):

@@ -45,6 +45,9 @@ int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflo
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
 int fdfd_host_unregister(void* host);
+/* page-locked host buffers for the result arrays the Python host hands back (recycled by a pool) */
+int fdfd_host_alloc(void** host_ptr, double bytes);
+int fdfd_host_free(void* host_ptr);
 
 /* ---- operator: replaces linalg.py:39 construct_A, pml.py:44 S_create, derivatives.py:7 createDws.
  * pol: 0 = 'Ez', 1 = 'Hz'.  The sc-PML inverse stretch factors are computed on the device at
@@ -57,6 +60,8 @@ int fdfd_op_create(fdfd_op** out, int nx, int ny, double omega, double dl, int n
 void fdfd_op_destroy(fdfd_op* op);
 int fdfd_op_assemble_host(fdfd_op* op, const double* eps_r_c128, const double* eps_nl_c128, int averaging);
 int fdfd_op_assemble_dev(fdfd_op* op, const void* d_eps_r, const void* d_eps_nl, int averaging);
+/* the same for a real (float64) eps_r without nonlinearity: half the host->device bytes */
+int fdfd_op_assemble_host_f64(fdfd_op* op, const double* eps_r_f64, int averaging);
 /* inverse stretch factors 1/s as four 1-D complex arrays (lengths nx, nx, ny, ny): pml.py:63-76 */
 int fdfd_op_get_sfactors_host(fdfd_op* op, double* isxf, double* isxb, double* isyf, double* isyb);
 /* the five planes c0,cxm,cxp,cym,cyp (5*nx*ny complex) for export of A as a sparse matrix */
@@ -103,6 +108,13 @@ int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b_c128, do
                            int max_refine, double tol, double* relres, int* refine_steps);
 int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_x, int nrhs,
                           int max_refine, double tol, double* relres, int* refine_steps);
+
+/* Simulation.solve_fields in one call (simulation.py:113-178): b = scale * src (src real float64 or
+ * complex128 on the host), x = A^-1 b with refinement as above, in-plane fields derived from the
+ * device-resident x; the three fields come back in one pass (no re-upload of x).                 */
+int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
+                           double scale_im, double* x_c128, double* f1_c128, double* f2_c128, int averaging,
+                           int max_refine, double tol, double* relres, int* refine_steps);
 
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).

@@ -181,3 +181,42 @@ def test_born_equals_newton(Simulation):
         assert relerr(e_newton, e_born) < 1e-3
     with pytest.raises(AssertionError):
         sim.solve_fields_nl(solver_nl='LM2')
+
+
+def test_fused_solve_fields_call_and_pinned_pool(Simulation):
+    """The one-call hot path (fdfd_solve_fields_host: real or complex src, b formed on the device,
+    fields returned in page-locked arrays) equals the step-by-step path and the oracle."""
+    import gc
+    from fdfdpy_b200 import _lib
+    rng = np.random.default_rng(3)
+    omega, dl, npml = 2 * np.pi * 200e12, 0.05, [8, 10]
+    shape = (300, 260)                       # > 1 MB per field, so the pinned pool is exercised
+    eps = 1 + 5 * (rng.random(shape) > 0.6)
+    sim = Simulation(omega, eps, dl, npml, "Ez")
+    src_c = np.zeros(shape, dtype=complex)
+    src_c[150, 130] = 1 + 2j
+    src_c[40, 200] = -0.5j
+    sim.src = src_c                           # complex source
+    hx, hy, ez = sim.solve_fields()
+    rhx, rhy, rez = orc.solve_fields(omega, eps, dl, npml, "Ez", 1e-6, src_c)
+    assert relerr(ez, rez) < 1e-8 and relerr(hx, rhx) < 1e-8 and relerr(hy, rhy) < 1e-8
+    # step-by-step path of the same handles
+    d = sim._op.direct()
+    x2 = d.solve(src_c * 1j * omega).reshape(shape)
+    f1, f2 = sim._op.derive_fields(x2)
+    assert relerr(x2, ez) < 1e-12 and relerr(f1, hx) < 1e-12 and relerr(f2, hy) < 1e-12
+    # real source takes the float64 upload
+    sim.src = np.real(src_c)
+    ez_r = sim.solve_fields()[2]
+    assert relerr(ez_r, orc.solve_fields(omega, eps, dl, npml, "Ez", 1e-6, np.real(src_c))[2]) < 1e-8
+    # results stay valid after later solves (no aliasing of live buffers) ...
+    keep = ez.copy()
+    for _ in range(3):
+        sim.solve_fields()
+    assert np.array_equal(keep, ez)
+    # ... and released buffers are recycled
+    addr = ez_r.ctypes.data
+    del ez_r, hx, hy, f1, f2, x2
+    sim.fields = {k: None for k in sim.fields}
+    gc.collect()
+    assert any(addr in lst for lst in _lib._pool_free.values())
