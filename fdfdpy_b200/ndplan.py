@@ -206,3 +206,65 @@ def plan_stats(levels):
     transient = max(lv.nb * lv.nmax * lv.nmax for lv in levels)
     macs = sum(lv.nb * lv.kmax * lv.nmax * lv.nmax for lv in levels)
     return stored, transient, macs
+
+
+def shard_plan(levels, world, rank):
+    """This rank's part of the elimination tree when one grid is split over ``world`` GPUs.
+
+    The top log2(world) merges of the tree cut the torus into ``world`` slabs/blocks; each rank
+    owns the whole subtree below one of them (no communication there).  Above, a front belongs to
+    the lowest rank of the group of ranks below it; its second child lives on the rank half a
+    group further on, which hands its Schur block (factorisation), its ring right-hand side
+    (forward solve) and receives its ring solution (backward solve) -- one point-to-point
+    exchange per shared level, a binary reduction tree over the ranks.
+
+    Returns levels aligned one to one with ``levels``.  Local fronts are renumbered 0..nb-1;
+    ``nb`` may be 0 on shared levels.  ``recv_from`` >= 0: before this level, slot ``nb_child``
+    of the child batch is filled by that rank (``ch2`` already points at it).  ``send_to`` >= 0:
+    before this level, this rank's single child front goes to that rank.
+    """
+    if world < 1 or world & (world - 1):
+        raise ValueError("world size must be a power of two, got {}".format(world))
+    nlev = len(levels)
+    if world > 1 and (nlev < 2 or levels[0].nb < world or world > (1 << (nlev - 1))):
+        raise ValueError("grid too small to split over {} ranks".format(world))
+    owner = [None] * nlev
+    group = [1] * nlev
+    owner[-1] = np.zeros(1, dtype=np.int64)
+    group[-1] = world
+    for l in range(nlev - 1, 0, -1):
+        lv, g = levels[l], group[l]
+        child = np.empty(levels[l - 1].nb, dtype=np.int64)
+        child[lv.ch1] = owner[l]
+        child[lv.ch2] = owner[l] + (g // 2 if g > 1 else 0)
+        owner[l - 1], group[l - 1] = child, max(g // 2, 1)
+    out = []
+    loc_prev = None
+    for l, lv in enumerate(levels):
+        mine = np.flatnonzero(owner[l] == rank)
+        loc = np.full(lv.nb, -1, dtype=np.int64)
+        loc[mine] = np.arange(len(mine))
+        nl = Level()
+        nl.__dict__.update(lv.__dict__)
+        nl.nb = int(len(mine))
+        nl.gids = mine
+        nl.cls = lv.cls[mine]
+        nl.send_to = nl.recv_from = -1
+        g = group[l]
+        if lv.kind == "leaf":
+            nl.x0, nl.y0 = lv.x0[mine], lv.y0[mine]
+        else:
+            nl.ch1 = loc_prev[lv.ch1[mine]].astype(np.int32)
+            if g > 1:
+                assert nl.nb <= 1
+                nl.ch2 = np.ones(nl.nb, dtype=np.int32)        # the slot after the single local child
+                if nl.nb == 1:
+                    nl.recv_from = rank + g // 2
+                elif rank % g == g // 2:
+                    nl.send_to = rank - g // 2
+            else:
+                nl.ch2 = loc_prev[lv.ch2[mine]].astype(np.int32)
+            assert nl.nb == 0 or (nl.ch1.min() >= 0 and nl.ch2.min() >= 0)
+        out.append(nl)
+        loc_prev = loc
+    return out

@@ -39,11 +39,21 @@ def _lower_to_full(L):
     return T + np.transpose(np.tril(L, -1), (0, 2, 1))
 
 
-def factor(levels, planes, nx, ny, dscale, tile=32):
+def factor(levels, planes, nx, ny, dscale, tile=32, comm=None):
+    """``comm`` (send(array, dst) / recv(shape, src) / allreduce(array)) runs a plan produced by
+    ndplan.shard_plan: the exchanges sit exactly where nd_factor / nd_solve_chunk put them."""
     c0, cxm, cxp, cym, cyp = [p.reshape(-1) for p in planes]
     store = []
     S_prev = None
     for lv in levels:
+        if getattr(lv, "send_to", -1) >= 0:
+            comm.send(S_prev[0], lv.send_to)
+        if getattr(lv, "recv_from", -1) >= 0:
+            S_prev = np.concatenate([S_prev[:1], comm.recv(S_prev[0].shape, lv.recv_from)[None]])
+        if lv.nb == 0:
+            store.append(None)
+            S_prev = np.zeros((0, lv.mmax, lv.mmax), dtype=np.complex128)
+            continue
         F = np.zeros((lv.nb, lv.nmax, lv.nmax), dtype=np.complex128)       # lower triangle only
         for b in range(lv.nb):
             c = lv.cls[b]
@@ -83,11 +93,20 @@ def factor(levels, planes, nx, ny, dscale, tile=32):
     return store
 
 
-def solve(levels, store, b, nx, ny, dscale):
+def solve(levels, store, b, nx, ny, dscale, comm=None):
     b = np.asarray(b, dtype=np.complex128).reshape(-1) * dscale
     ring_prev = None
     ysave = []
-    for lv, (Einv, G) in zip(levels, store):
+    for lv, fac in zip(levels, store):
+        if getattr(lv, "send_to", -1) >= 0:
+            comm.send(ring_prev[0], lv.send_to)
+        if getattr(lv, "recv_from", -1) >= 0:
+            ring_prev = np.concatenate([ring_prev[:1], comm.recv(ring_prev[0].shape, lv.recv_from)[None]])
+        if lv.nb == 0:
+            ysave.append(None)
+            ring_prev = np.zeros((0, lv.mmax), dtype=np.complex128)
+            continue
+        Einv, G = fac
         f = np.zeros((lv.nb, lv.nmax), dtype=np.complex128)
         if lv.kind == "leaf":
             for i in range(lv.nb):
@@ -113,17 +132,26 @@ def solve(levels, store, b, nx, ny, dscale):
     out = np.zeros(nx * ny, dtype=np.complex128)
     for li in range(len(levels) - 1, -1, -1):
         lv = levels[li]
-        _, G = store[li]
         k = lv.kmax
-        u = np.zeros((lv.nb, lv.nmax), dtype=np.complex128)
-        if li < len(levels) - 1:
-            par = levels[li + 1]
+        par = levels[li + 1] if li < len(levels) - 1 else None
+        remote_child = par is not None and getattr(par, "recv_from", -1) >= 0
+        u = np.zeros((lv.nb + (1 if remote_child else 0), lv.nmax), dtype=np.complex128)
+        if par is not None:
             for pb in range(par.nb):
                 c = par.cls[pb]
                 for ch, cmap in ((par.ch1[pb], par.c1map[c]), (par.ch2[pb], par.c2map[c])):
                     idx = cmap[:par.child_mmax]
                     ok = idx >= 0
                     u[ch, k + np.where(ok)[0]] = u_parent[pb, idx[ok]]
+            if remote_child:                       # the second child's ring solution goes back to its rank
+                comm.send(u[1], par.recv_from)
+                u = u[:1]
+            if getattr(par, "send_to", -1) >= 0:
+                u[0] = comm.recv(u[0].shape, par.send_to)
+        if lv.nb == 0:
+            u_parent = u
+            continue
+        G = store[li][1]
         u[:, :k] = ysave[li] - np.einsum('bmk,bm->bk', G, u[:, k:])
         u_parent = u
         if lv.kind == "leaf":
@@ -134,4 +162,6 @@ def solve(levels, store, b, nx, ny, dscale):
                         x = (lv.x0[i] + lv.slot_lx[c, s]) % nx
                         y = (lv.y0[i] + lv.slot_ly[c, s]) % ny
                         out[x * ny + y] = u[i, s]
+    if comm is not None:
+        out = comm.allreduce(out)                  # every cell is written by exactly one rank
     return out.reshape(nx, ny)

@@ -1,0 +1,102 @@
+"""world_size-2/-4 gloo tests (CPU) of the multi-GPU host logic: the sharded elimination plan
+(ndplan.shard_plan) executed by the numpy model with the same point-to-point exchanges the CUDA
+library issues over NCCL, and the slab decomposition of the stencil with its halo exchange."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class GlooComm:
+    def __init__(self, dist, torch):
+        self.dist, self.torch = dist, torch
+
+    def send(self, arr, dst):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.float64).copy())
+        self.dist.send(t, dst)
+
+    def recv(self, shape, src):
+        out = np.empty(shape, dtype=np.complex128)
+        t = self.torch.from_numpy(out.view(np.float64))
+        self.dist.recv(t, src)
+        return out
+
+    def allreduce(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.float64).copy())
+        self.dist.all_reduce(t)
+        return t.numpy().view(np.complex128)
+
+
+def _worker_direct(rank, world, port, shape, npml, pol, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        from fdfdpy_b200.ndplan import build_plan, shard_plan
+        from oracle import fdfd_oracle as orc
+        from tests.nd_model import factor, solve, row_scale
+        nx, ny = shape
+        rng = np.random.default_rng(0)
+        eps = 1 + 5 * rng.random((nx, ny))
+        omega = 2 * np.pi * 200e12
+        planes = orc.stencil_planes(omega, eps, 0.04, npml, pol, 1e-6)
+        isxf, _, isyf, _ = orc.pml_inverse_factors(omega, 1e-6, (nx, ny), npml, 0.04)
+        d = row_scale(isxf, isyf)
+        levels = shard_plan(build_plan(nx, ny), world, rank)
+        comm = GlooComm(dist, torch)
+        store = factor(levels, planes, nx, ny, d, tile=8, comm=comm)
+        b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+        u = solve(levels, store, b, nx, ny, d, comm=comm)
+        ref = orc.sparse_solve(orc.planes_to_csr(planes), b).reshape(nx, ny)
+        q.put((rank, float(np.linalg.norm(u - ref) / np.linalg.norm(ref)),
+               int(sum(lv.nb * int(lv.kmax) for lv in levels))))
+    except Exception as e:                      # surface the failure instead of hanging the peer
+        q.put((rank, repr(e), 0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,npml,pol", [(2, (24, 20), [3, 3], "Ez"), (2, (19, 33), [0, 4], "Hz"),
+                                                  (4, (32, 28), [3, 3], "Ez")])
+def test_sharded_elimination_tree_gloo(world, shape, npml, pol):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_direct, args=(r, world, port, shape, npml, pol, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, _ in res:
+        assert isinstance(err, float), (rank, err)
+        assert err < 1e-11, (rank, err)
+
+
+def test_shard_plan_partitions_the_tree():
+    from fdfdpy_b200.ndplan import build_plan, shard_plan
+    levels = build_plan(96, 80)
+    for world in (1, 2, 4, 8):
+        shards = [shard_plan(levels, world, r) for r in range(world)]
+        for l, lv in enumerate(levels):
+            gids = np.concatenate([s[l].gids for s in shards])
+            assert sorted(gids.tolist()) == list(range(lv.nb))          # every front owned exactly once
+            sends = sorted((r, s[l].send_to) for r, s in enumerate(shards) if s[l].send_to >= 0)
+            recvs = sorted((s[l].recv_from, r) for r, s in enumerate(shards) if s[l].recv_from >= 0)
+            assert sends == recvs                                        # every send has its receive
+        if world > 1:
+            assert sum(1 for lv in shards[0] if lv.recv_from >= 0) == int(np.log2(world))
+    with pytest.raises(ValueError):
+        shard_plan(levels, 3, 0)
