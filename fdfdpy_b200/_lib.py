@@ -25,7 +25,7 @@ class LevelDesc(C.Structure):
                 ("child_mmax", C.c_int),
                 ("cls", _ip), ("k_cls", _ip), ("ch1", _ip), ("ch2", _ip), ("c1map", _ip), ("c2map", _ip),
                 ("x0", _ip), ("y0", _ip), ("slot_lx", _ip), ("slot_ly", _ip), ("slot_right", _ip),
-                ("slot_up", _ip)]
+                ("slot_up", _ip), ("send_to", C.c_int), ("recv_from", C.c_int)]
 
 
 # name -> (restype, argtypes); mirrors include/fdfd_b200.h one to one
@@ -75,6 +75,12 @@ SIGNATURES = {
     "fdfd_direct_stats": (C.c_int, [_vp, _dp, _dp]),
     "fdfd_direct_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
     "fdfd_direct_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _dp, _ip]),
+    "fdfd_comm_load": (C.c_int, [C.c_char_p]),
+    "fdfd_comm_unique_id": (C.c_int, [_vp]),
+    "fdfd_comm_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int]),
+    "fdfd_comm_destroy": (None, [_vp]),
+    "fdfd_comm_allreduce_sum_dev": (C.c_int, [_vp, _vp, _vp, C.c_double]),
+    "fdfd_direct_set_comm": (C.c_int, [_vp, _vp]),
     "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                          _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,

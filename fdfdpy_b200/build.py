@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdfd_b200.so")
-SOURCES = ["operator.cu", "direct.cu", "krylov.cu", "mode.cu", "capi.cu"]
+SOURCES = ["operator.cu", "direct.cu", "krylov.cu", "mode.cu", "comm.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas", "-v"]
 
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

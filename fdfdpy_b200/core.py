@@ -148,18 +148,26 @@ class MaxwellOperator:
 class DirectSolver:
     """Structured direct solver handle (reference: linalg.py:123 solver_direct / pardisoSolver)."""
 
-    def __init__(self, op, tile=64):
+    def __init__(self, op, tile=64, comm=None):
+        """``comm`` (fdfdpy_b200.distributed.Communicator): this rank's shard of ONE grid's elimination
+        tree; operator and right-hand sides are replicated, the factors are split over the ranks."""
         self.op = op
         self.lib = op.lib
         self.h = C.c_void_p()
         check(self.lib.fdfd_direct_create(C.byref(self.h), op.nx, op.ny, int(tile)))
         self.levels = get_plan(op.nx, op.ny)
+        self.comm = comm
+        if comm is not None and comm.world > 1:
+            from .ndplan import shard_plan
+            self.levels = shard_plan(self.levels, comm.world, comm.rank)
+            check(self.lib.fdfd_direct_set_comm(self.h, comm.h))
         keep = []
         for lv in self.levels:
             d = _lib.LevelDesc()
             d.kind = 0 if lv.kind == "leaf" else 1
             d.nb, d.kmax, d.mmax, d.ncls = lv.nb, lv.kmax, lv.mmax, lv.ncls
             d.child_mmax = getattr(lv, "child_mmax", 0)
+            d.send_to, d.recv_from = getattr(lv, "send_to", -1), getattr(lv, "recv_from", -1)
             names = ["cls", "k_cls"] + (["x0", "y0", "slot_lx", "slot_ly", "slot_right", "slot_up"]
                                         if lv.kind == "leaf" else ["ch1", "ch2", "c1map", "c2map"])
             for nme in names:

@@ -289,6 +289,7 @@ int fdfd_direct_add_level(fdfd_direct* s, const fdfd_level_desc* d) {
     x.child_mmax = d->child_mmax; x.cls = d->cls; x.k_cls = d->k_cls; x.ch1 = d->ch1; x.ch2 = d->ch2;
     x.c1map = d->c1map; x.c2map = d->c2map; x.x0 = d->x0; x.y0 = d->y0; x.slot_lx = d->slot_lx;
     x.slot_ly = d->slot_ly; x.slot_right = d->slot_right; x.slot_up = d->slot_up;
+    x.send_to = d->send_to; x.recv_from = d->recv_from;
     return nd_add_level(s, &x);
 }
 void fdfd_direct_destroy(fdfd_direct* s) { nd_destroy(s); }
@@ -339,6 +340,21 @@ int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int s
     FDFD_CHECK(cudaMemcpyAsync(f1, g1, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
     FDFD_CHECK(cudaMemcpyAsync(f2, g2, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+
+int fdfd_comm_load(const char* libnccl_path) { return comm_load(libnccl_path); }
+int fdfd_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+int fdfd_comm_create(fdfd_comm** out, const void* id128, int rank, int world) {
+    return comm_create(out, id128, rank, world);
+}
+void fdfd_comm_destroy(fdfd_comm* c) { comm_destroy(c); }
+int fdfd_comm_allreduce_sum_dev(fdfd_comm* c, fdfd_op* op, void* d_buf, double count) {
+    return comm_allreduce_sum(c, d_buf, (size_t)count, op->stream);
+}
+int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c) {
+    s->comm = c;
+    s->factored = false;
     return 0;
 }
 

@@ -680,6 +680,9 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->d_info = nullptr;
     s->fws = nullptr;
     s->fws_cap = 0;
+    s->comm = nullptr;
+    s->xchg = nullptr;
+    s->xchg_cap = 0;
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
     *out = s;
     return 0;
@@ -690,6 +693,9 @@ int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
     memset(&L, 0, sizeof(L));
     L.kind = d->kind; L.nb = d->nb; L.kmax = d->kmax; L.mmax = d->mmax; L.nmax = d->kmax + d->mmax;
     L.ncls = d->ncls; L.child_mmax = d->child_mmax;
+    L.send_to = d->send_to; L.recv_from = d->recv_from;
+    if (L.nb > 1 && L.recv_from >= 0) FDFD_FAIL("a level that receives a child front must hold exactly one front");
+    if (L.nb > 0 && L.send_to >= 0) FDFD_FAIL("a level that sends its child front away cannot own fronts");
     if (upload_i32(&L.cls, d->cls, d->nb)) return -1;
     if (upload_i32(&L.k_cls, d->k_cls, d->ncls)) return -1;
     if (d->kind == 0) {
@@ -739,6 +745,7 @@ void nd_destroy(NdSolver* s) {
     cudaFree(s->ws_a); cudaFree(s->ws_b); cudaFree(s->ws_ring_a); cudaFree(s->ws_ring_b); cudaFree(s->ws_ye);
     cudaFree(s->d_info);
     if (s->fws) cudaFree(s->fws);
+    if (s->xchg) cudaFree(s->xchg);
     delete s;
 }
 
@@ -845,11 +852,22 @@ static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, l
 // one arena for all transient factorisation buffers: two ping-pong front batches plus the workspace
 // stack of the block inversion, sized for the largest level; allocated once and kept
 static int ensure_factor_workspace(NdSolver* s) {
-    size_t maxF = 0, maxW = 0;
-    for (auto& L : s->levels) {
-        const size_t nb = L.nb, nmax = L.nmax;
+    size_t maxF = 0, maxW = 0, maxX = 0;
+    for (size_t li = 0; li < s->levels.size(); ++li) {
+        NdLevel& L = s->levels[li];
+        // one extra slot where the parent level receives its second child from another rank
+        const bool extra = li + 1 < s->levels.size() && s->levels[li + 1].recv_from >= 0;
+        const size_t nb = L.nb + (extra ? 1 : 0), nmax = L.nmax;
         maxF = std::max(maxF, nb * nmax * nmax);
-        maxW = std::max(maxW, nb * inv_ws_need(L.kmax));
+        maxW = std::max(maxW, (size_t)L.nb * inv_ws_need(L.kmax));
+        if (L.send_to >= 0 || L.recv_from >= 0) maxX = std::max(maxX, (size_t)L.child_mmax * L.child_mmax);
+    }
+    if (maxX > s->xchg_cap) {
+        if (s->xchg) cudaFree(s->xchg);
+        s->xchg = nullptr;
+        s->xchg_cap = 0;
+        FDFD_CHECK(cudaMalloc(&s->xchg, sizeof(cplx) * maxX));
+        s->xchg_cap = maxX;
     }
     size_t need = 2 * maxF + maxW;
     if (need > s->fws_cap) {
@@ -882,6 +900,24 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
         cplx* F = s->fws_F[li & 1];
+        if (L.send_to >= 0 || L.recv_from >= 0) {
+            // sharded tree: the second child's Schur block crosses NVLink as a packed m x m square and lands
+            // in slot 1 of the child batch, in the layout the local child has (ch2 of this level points there)
+            if (!s->comm) FDFD_FAIL("sharded elimination plan without a communicator (fdfd_direct_set_comm)");
+            const size_t m = (size_t)(prev_n - prev_k), pitch_f = sizeof(cplx) * prev_n, pitch_x = sizeof(cplx) * m;
+            if ((int)m != L.child_mmax || !Fprev) FDFD_FAIL("sharded plan: child block size mismatch");
+            PhaseScope ph(PH_COPY, st);
+            if (L.send_to >= 0) {
+                FDFD_CHECK(cudaMemcpy2DAsync(s->xchg, pitch_x, Fprev + (size_t)prev_k * prev_n + prev_k, pitch_f, pitch_x, m,
+                                             cudaMemcpyDeviceToDevice, st));
+                if (comm_send(s->comm, s->xchg, 2 * m * m, L.send_to, st)) return -1;
+            } else {
+                if (comm_recv(s->comm, s->xchg, 2 * m * m, L.recv_from, st)) return -1;
+                FDFD_CHECK(cudaMemcpy2DAsync(Fprev + (size_t)prev_n * prev_n + (size_t)prev_k * prev_n + prev_k, pitch_f,
+                                             s->xchg, pitch_x, pitch_x, m, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        if (nb == 0) continue;          // this rank's part of the tree ended below this level
         // factor storage is allocated on the first factorisation and reused afterwards
         if (!L.Einv) FDFD_CHECK(cudaMalloc(&L.Einv, sizeof(cplx) * (size_t)nb * kmax * kmax));
         if (mmax > 0 && !L.G) FDFD_CHECK(cudaMalloc(&L.G, sizeof(cplx) * (size_t)nb * mmax * kmax));
@@ -979,6 +1015,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     }
     g_phase_timing.level = -1;
     int info = 0;
+    if (s->comm && s->comm->world > 1 && comm_allreduce_max_i32(s->comm, s->d_info, 1, st)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     FDFD_CHECK(cudaStreamSynchronize(st));
     if (info) FDFD_FAIL("direct solver: a pivot block is numerically singular (no inter-block pivoting)");
@@ -992,12 +1029,15 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
     const size_t nlev = s->levels.size();
     // workspace sizing
     size_t vec_need = 0, ring_need = 1, ye_need = 0;
-    for (auto& L : s->levels) {
-        vec_need = std::max(vec_need, (size_t)L.nb * L.nmax * NR);
-        ring_need = std::max(ring_need, (size_t)L.nb * std::max(L.mmax, 1) * NR);
+    for (size_t li = 0; li < nlev; ++li) {
+        NdLevel& L = s->levels[li];
+        const size_t slots = (size_t)L.nb + ((li + 1 < nlev && s->levels[li + 1].recv_from >= 0) ? 1 : 0);
+        vec_need = std::max(vec_need, slots * L.nmax * NR);
+        ring_need = std::max(ring_need, slots * std::max(L.mmax, 1) * NR);
         L.ye_off = ye_need;
         ye_need += (size_t)L.nb * L.kmax * NR;
     }
+    ye_need = std::max(ye_need, (size_t)1);
     if (vec_need > s->ws_vec_cap) {
         cudaFree(s->ws_a); cudaFree(s->ws_b);
         FDFD_CHECK(cudaMalloc(&s->ws_a, sizeof(cplx) * vec_need));
@@ -1023,6 +1063,12 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         g_phase_timing.level = (int)li;
         PhaseScope phf(PH_SOLVE_FWD, st);
         const long long nb = L.nb;
+        // sharded tree: the second child's ring right-hand side arrives in slot 1 of the child batch
+        const size_t ring_cnt = 2 * (size_t)L.child_mmax * NR;
+        if (L.send_to >= 0 && comm_send(s->comm, ring_prev, ring_cnt, L.send_to, st)) return -1;
+        if (L.recv_from >= 0 && comm_recv(s->comm, ring_prev + (size_t)L.child_mmax * NR, ring_cnt, L.recv_from, st))
+            return -1;
+        if (nb == 0) continue;
         long long tot = nb * L.nmax;
         if (L.kind == 0)
             { leaf_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, d_b, op->isxf, op->isyf, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,
@@ -1047,13 +1093,21 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         g_phase_timing.level = (int)li;
         PhaseScope phb(PH_SOLVE_BWD, st);
         const long long nb = L.nb;
-        FDFD_CHECK(cudaMemsetAsync(u, 0, sizeof(cplx) * (size_t)nb * L.nmax * NR, st));
-        if (li + 1 < nlev) {
-            NdLevel& P = s->levels[li + 1];
+        const NdLevel* Pp = li + 1 < nlev ? &s->levels[li + 1] : nullptr;
+        const bool remote_child = Pp && Pp->recv_from >= 0, from_parent = Pp && Pp->send_to >= 0;
+        const size_t vec_cnt = (size_t)L.nmax * NR;
+        if (nb + (remote_child ? 1 : 0) == 0) continue;
+        FDFD_CHECK(cudaMemsetAsync(u, 0, sizeof(cplx) * (size_t)(nb + (remote_child ? 1 : 0)) * vec_cnt, st));
+        if (Pp && Pp->nb > 0) {
+            const NdLevel& P = *Pp;
             long long tot = (long long)P.nb * 2 * P.child_mmax;
             { child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
                                                                          P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb); ++g_fdfd_launches; }
         }
+        // sharded tree: the remote child's ring solution (slot 1) goes back to the rank that owns it
+        if (remote_child && comm_send(s->comm, u + vec_cnt, 2 * vec_cnt, Pp->recv_from, st)) return -1;
+        if (from_parent && comm_recv(s->comm, u, 2 * vec_cnt, Pp->send_to, st)) return -1;
+        if (nb == 0) { std::swap(u, u_par); continue; }
         { backward_mvt_kernel<NR><<<ceil_div(nb * L.kmax, 32), 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
                                                                            L.mmax, L.nmax, nb); ++g_fdfd_launches; }
         if (L.kind == 0) {
@@ -1071,6 +1125,9 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
 int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs) {
     if (!s->factored) FDFD_FAIL("nd_solve called before nd_factor");
     const size_t n = (size_t)s->nx * s->ny;
+    const bool sharded = s->comm && s->comm->world > 1;
+    // sharded tree: every cell is written by exactly one rank; the sum over ranks is the whole field
+    if (sharded) FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(cplx) * n * nrhs, op->stream));
     for (int j0 = 0; j0 < nrhs;) {
         int rem = nrhs - j0, rc;
         if (rem >= 8) { rc = 8; if (nd_solve_chunk<8>(s, op, d_b + j0 * n, d_x + j0 * n, 8)) return -1; }
@@ -1079,5 +1136,6 @@ int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs
         else { rc = 1; if (nd_solve_chunk<1>(s, op, d_b + j0 * n, d_x + j0 * n, 1)) return -1; }
         j0 += rc;
     }
+    if (sharded && comm_allreduce_sum(s->comm, d_x, 2 * n * nrhs, op->stream)) return -1;
     return 0;
 }

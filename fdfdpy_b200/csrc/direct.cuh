@@ -2,6 +2,7 @@
 // Plan semantics are documented in fdfdpy_b200/ndplan.py; this side owns the numerics.
 #pragma once
 #include <vector>
+#include "comm.cuh"
 #include "operator.cuh"
 
 struct NdLevelDesc {          // host view handed over the C ABI, all arrays int32 host pointers
@@ -19,6 +20,7 @@ struct NdLevelDesc {          // host view handed over the C ABI, all arrays int
     const int* slot_ly;
     const int* slot_right;
     const int* slot_up;
+    int send_to, recv_from;   // sharded tree (ndplan.shard_plan): peer ranks of this level's exchange, -1 = none
 };
 
 struct NdLevel {
@@ -29,6 +31,7 @@ struct NdLevel {
     cplx* G;      // [nb][mmax][kmax]   F_RE F_EE^-1
     cplx* yE;     // solve workspace [nb][kmax][nrhs]
     size_t ye_off;
+    int send_to, recv_from;
 };
 
 struct NdSolver {
@@ -45,6 +48,10 @@ struct NdSolver {
     // solve workspace (grown on demand)
     cplx *ws_a, *ws_b, *ws_ring_a, *ws_ring_b, *ws_ye;
     size_t ws_vec_cap, ws_ring_cap, ws_ye_cap;
+    // sharded tree: communicator (not owned) and the packed Schur block in flight between two ranks
+    FdfdComm* comm;
+    cplx* xchg;
+    size_t xchg_cap;
 };
 
 int nd_create(NdSolver** out, int nx, int ny, int tile);

@@ -16,6 +16,7 @@ extern "C" {
 
 typedef struct FdfdOp fdfd_op;         /* the Maxwell operator A on the device               */
 typedef struct NdSolver fdfd_direct;   /* structured direct solver: plan + cached factorisation */
+typedef struct FdfdComm fdfd_comm;     /* one-process-per-GPU communicator (NCCL over NVLink/NVSwitch) */
 
 int fdfd_version(void);
 const char* fdfd_last_error(void);
@@ -93,6 +94,7 @@ typedef struct {
     const int* slot_ly;
     const int* slot_right; /* leaf: slot of the +x neighbour if this slot owns its entries, else -1 */
     const int* slot_up;
+    int send_to, recv_from; /* sharded tree (ndplan.shard_plan): peer ranks of this level's exchange, -1 = none */
 } fdfd_level_desc;
 
 int fdfd_direct_create(fdfd_direct** out, int nx, int ny, int tile);
@@ -115,6 +117,22 @@ int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_
 int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
                            double scale_im, double* x_c128, double* f1_c128, double* f2_c128, int averaging,
                            int max_refine, double tol, double* relres, int* refine_steps);
+
+/* ---- one grid split over several GPUs (no reference counterpart: the reference is single-process).
+ * One process per GPU.  Rank 0 makes a 128-byte id, the host program hands it to the other ranks
+ * (torch.distributed, MPI, a file ...), every rank then creates its communicator on its current
+ * device.  NCCL is loaded at run time (fdfd_comm_load; path may be NULL), never linked.          */
+int fdfd_comm_load(const char* libnccl_path);
+int fdfd_comm_unique_id(void* id128);
+int fdfd_comm_create(fdfd_comm** out, const void* id128, int rank, int world);
+void fdfd_comm_destroy(fdfd_comm* c);
+/* in-place sum over ranks of `count` doubles on the device (stream of `op`) */
+int fdfd_comm_allreduce_sum_dev(fdfd_comm* c, fdfd_op* op, void* d_buf, double count);
+/* direct solver on a sharded elimination tree: the levels added must come from ndplan.shard_plan
+ * for this rank; subtrees are factorised without communication, the log2(world) levels above them
+ * exchange one Schur block / ring vector per level point to point, the solution is summed over
+ * ranks (every cell is written by exactly one).  Operator, b and x are replicated on every rank. */
+int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c);
 
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).

@@ -1,0 +1,98 @@
+"""Multi-GPU check of the sharded paths, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_check.py [--parity 200x160] [--size 4096] [--reps 2]
+
+* parity: sharded direct solve vs the CPU oracle on a small grid (rank 0 checks, all ranks must agree);
+* size  : factor + solve timing of ONE size x size grid split over the ranks (device time, max over ranks).
+torch.distributed (gloo) is only the rendezvous that carries the 128-byte NCCL id and the timing reduction.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--parity", default="200x160")
+    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--pol", default="Ez")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    from fdfdpy_b200 import _lib, core
+    from fdfdpy_b200.distributed import Communicator
+    lib = _lib.load()
+    _lib.check(lib.fdfd_set_device(local))
+    comm = Communicator.from_torch()
+    omega = 2 * np.pi * 200e12
+    out = {"world": world}
+
+    if args.parity:
+        nx, ny = (int(v) for v in args.parity.split("x"))
+        rng = np.random.default_rng(1)
+        eps = 1 + 5 * (rng.random((nx, ny)) > 0.5)
+        b = rng.standard_normal((2, nx, ny)) + 1j * rng.standard_normal((2, nx, ny))
+        op = core.MaxwellOperator(omega, eps, 0.04, [10, 8], args.pol, 1e-6)
+        d = core.DirectSolver(op, comm=comm)
+        x = d.solve(b).reshape(2, nx, ny)
+        res = [float(np.linalg.norm(b[j].ravel() - op.dot(x[j]).ravel()) / np.linalg.norm(b[j])) for j in range(2)]
+        out["parity_relres"] = max(res)
+        xs = [None] * world
+        dist.all_gather_object(xs, x)
+        out["ranks_agree"] = bool(all(np.array_equal(xs[0], xi) for xi in xs))
+        if rank == 0:
+            from oracle import fdfd_oracle as orc
+            A = orc.construct_A(omega, eps, 0.04, [10, 8], args.pol, 1e-6)
+            ref = np.stack([orc.sparse_solve(A, b[j]).reshape(nx, ny) for j in range(2)])
+            out["parity_rel_l2_vs_oracle"] = float(np.linalg.norm(x - ref) / np.linalg.norm(ref))
+        del d, op
+
+    if args.size:
+        import bench
+        n = args.size
+        eps = bench.synthetic_eps(n)
+        src = bench.synthetic_src(n)
+        op = core.MaxwellOperator(bench.OMEGA0, eps, bench.DL, bench.NPML, "Ez", bench.L0)
+        d = core.DirectSolver(op, comm=comm)
+        import ctypes as C
+        times = []
+        for rep in range(args.reps + 1):
+            dist.barrier()
+            ms_f, ms_s = C.c_double(0), C.c_double(0)
+            _lib.check(lib.fdfd_timer_start(op.h))
+            d.factor()
+            _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms_f)))
+            t0 = time.perf_counter()
+            x, f1, f2 = d.solve_fields(src, 1j * bench.OMEGA0)
+            ms_s.value = (time.perf_counter() - t0) * 1e3
+            times.append((ms_f.value, ms_s.value, d.last_relres))
+        tt = torch.tensor([times[-1][0], times[-1][1]], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        st = d.stats()
+        out.update({"size": n, "factor_ms_max": float(tt[0]), "solve_fields_host_ms_max": float(tt[1]),
+                    "relres": times[-1][2], "factor_bytes_this_rank": st["factor_bytes"],
+                    "factor_ms_all_reps": [t[0] for t in times]})
+        fb, tb = C.c_double(0), C.c_double(0)
+        lib.fdfd_mem_info(C.byref(fb), C.byref(tb))
+        out["hbm_used_gb_this_rank"] = (tb.value - fb.value) / 1e9
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, out)
+    if rank == 0:
+        print(json.dumps({"rank0": out, "others": per_rank[1:]}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
