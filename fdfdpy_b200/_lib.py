@@ -81,6 +81,8 @@ SIGNATURES = {
     "fdfd_comm_destroy": (None, [_vp]),
     "fdfd_comm_allreduce_sum_dev": (C.c_int, [_vp, _vp, _vp, C.c_double]),
     "fdfd_direct_set_comm": (C.c_int, [_vp, _vp]),
+    "fdfd_slab_op_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, C.c_int, C.c_double]),
     "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                          _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,

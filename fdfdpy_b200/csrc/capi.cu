@@ -293,7 +293,10 @@ int fdfd_direct_add_level(fdfd_direct* s, const fdfd_level_desc* d) {
     return nd_add_level(s, &x);
 }
 void fdfd_direct_destroy(fdfd_direct* s) { nd_destroy(s); }
-int fdfd_direct_factor(fdfd_direct* s, fdfd_op* op) { return nd_factor(s, op); }
+int fdfd_direct_factor(fdfd_direct* s, fdfd_op* op) {
+    if (op->halo) FDFD_FAIL("the direct solver takes the whole-grid operator (sharded: fdfd_direct_set_comm), not a slab");
+    return nd_factor(s, op);
+}
 int fdfd_direct_stats(fdfd_direct* s, double* factor_bytes, double* factor_flops) {
     *factor_bytes = (double)s->factor_bytes;
     *factor_flops = s->factor_flops;
@@ -351,6 +354,12 @@ int fdfd_comm_create(fdfd_comm** out, const void* id128, int rank, int world) {
 void fdfd_comm_destroy(fdfd_comm* c) { comm_destroy(c); }
 int fdfd_comm_allreduce_sum_dev(fdfd_comm* c, fdfd_op* op, void* d_buf, double count) {
     return comm_allreduce_sum(c, d_buf, (size_t)count, op->stream);
+}
+int fdfd_slab_op_create(fdfd_op** out, fdfd_comm* comm, int gnx, int ny, int x0, int nxl, double omega, double dl,
+                        int npml_x, int npml_y, int pol, double L0) {
+    if (!(omega > 0) || !(dl > 0) || !(L0 > 0)) FDFD_FAIL("omega, dl and L0 must be positive");
+    if (npml_x < 0 || npml_y < 0) FDFD_FAIL("NPML entries must be >= 0");
+    return op_create_slab(out, comm, gnx, ny, x0, nxl, omega, dl, npml_x, npml_y, pol, L0);
 }
 int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c) {
     s->comm = c;

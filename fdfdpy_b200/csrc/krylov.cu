@@ -48,11 +48,13 @@ dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__
 }
 
 int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
-            int real_only) {
+            int real_only, FdfdComm* comm) {
     if (conj_a) { dot_partial_kernel<true><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
     else { dot_partial_kernel<false><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
     { dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out, real_only); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
+    // slabs: the scalar is summed over the ranks on the same stream, it never visits the host
+    if (comm && comm->world > 1 && comm_allreduce_sum(comm, out, 2, st)) return -1;
     return 0;
 }
 
@@ -151,8 +153,15 @@ __global__ void conj_couple_kernel(cplx* __restrict__ y, const cplx* __restrict_
     y[i] = subtract ? csub(y[i], t) : cadd(y[i], t);
 }
 
+// Slab operators (operator.cuh): vectors carry one halo row before and after the rows this rank owns.
+// The solvers below work on the owned rows (pointer = extended base + pad, n = owned cells) and hand the
+// extended base to the stencil, which fills the halos from the neighbouring ranks.
+static inline size_t kpad(const FdfdOp* op) { return op->halo ? (size_t)op->ny : 0; }
+static inline size_t kn(const FdfdOp* op) { return (size_t)(op->nx - 2 * op->halo) * op->ny; }
+
 static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cplx* c12) {
-    if (fused ? op_apply_fused(op, x, y, 1) : op_apply_planes(op, x, y, 1)) return -1;
+    const size_t pad = kpad(op);
+    if (fused ? op_apply_fused(op, x - pad, y - pad, 1) : op_apply_planes(op, x - pad, y - pad, 1)) return -1;
     if (c12) {
         { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), 0); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
@@ -161,7 +170,8 @@ static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cp
 }
 
 static int residual_A(const FdfdOp* op, const cplx* b, const cplx* x, cplx* r, const cplx* c12) {
-    if (op_residual(op, b, x, r, 1)) return -1;
+    const size_t pad = kpad(op);
+    if (op_residual(op, b - pad, x - pad, r - pad, 1)) return -1;
     if (c12) {
         { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(r, c12, x, op->n(), 1); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
@@ -172,14 +182,18 @@ static int residual_A(const FdfdOp* op, const cplx* b, const cplx* x, cplx* r, c
 int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
                     int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
     const int RI = (real_inner || c12) ? 1 : 0;   // an R-linear operator needs the real inner product
-    const size_t n = op->n();
+    const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
+    if (op->halo && (precond || c12)) FDFD_FAIL("slab operators take neither a preconditioner nor an anti-linear term");
+    FdfdComm* comm = op->comm;
+    d_b += pad; d_x += pad;
     cudaStream_t st = op->stream;
     const int nvec = precond ? 8 : 6;
     Scratch ws;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (n * nvec + RED_BLOCKS + S_COUNT)));
-    cplx *r = ws.base, *r0 = r + n, *p = r0 + n, *v = p + n, *s = v + n, *t = s + n;
-    cplx *ph = precond ? t + n : p, *sh = precond ? ph + n : s;
-    cplx* partial = ws.base + n * nvec;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (vs * nvec + RED_BLOCKS + S_COUNT)));
+    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(cplx) * vs * nvec, st));
+    cplx *r = ws.base + pad, *r0 = r + vs, *p = r0 + vs, *v = p + vs, *s = v + vs, *t = s + vs;
+    cplx *ph = precond ? t + vs : p, *sh = precond ? ph + vs : s;
+    cplx* partial = ws.base + vs * nvec;
     cplx* sc = partial + RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
     cplx h;
@@ -192,7 +206,7 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
     cplx init[S_COUNT];
     for (int i = 0; i < S_COUNT; ++i) init[i] = make_double2(1.0, 0.0);
     FDFD_CHECK(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, RI)) return -1;
+    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
@@ -201,29 +215,29 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     if (res->relres <= tol) { res->converged = 1; return 0; }
     for (int it = 1; it <= maxiter; ++it) {
-        if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO, RI)) return -1;
+        if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO, RI, comm)) return -1;
         { bicg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
         { bicg_p_kernel<<<nblk, 256, 0, st>>>(p, r, v, sc, n); ++g_fdfd_launches; }
         if (precond) { if (nd_solve(precond, op, p, ph, 1)) return -1; }
         if (apply_A(op, ph, v, fused, c12)) return -1;
-        if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V, RI)) return -1;
+        if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V, RI, comm)) return -1;
         { bicg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
         { bicg_s_kernel<<<nblk, 256, 0, st>>>(s, r, v, sc, n); ++g_fdfd_launches; }
         if (precond) { if (nd_solve(precond, op, s, sh, 1)) return -1; }
         if (apply_A(op, sh, t, fused, c12)) return -1;
-        if (dev_dot(st, t, s, n, true, partial, sc + S_TS, RI)) return -1;
-        if (dev_dot(st, t, t, n, true, partial, sc + S_TT, RI)) return -1;
+        if (dev_dot(st, t, s, n, true, partial, sc + S_TS, RI, comm)) return -1;
+        if (dev_dot(st, t, t, n, true, partial, sc + S_TT, RI, comm)) return -1;
         { bicg_omega_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
         { bicg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, ph, sh, s, t, sc, n); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
+            if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
             if (host_scalar(st, sc + S_RR, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;           // NaN: breakdown
@@ -232,7 +246,7 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
     }
     // report the TRUE residual of the returned iterate
     if (residual_A(op, d_b, d_x, r, c12)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     res->converged = res->relres <= tol * 10 ? res->converged : 0;
@@ -241,23 +255,28 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
 
 int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,
                 KrylovResult* res) {
-    const size_t n = op->n();
+    const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
+    FdfdComm* comm = op->comm;
+    d_b += pad; d_x += pad;
+    const cplx *sxf = op->isxf + op->halo, *syf = op->isyf;
+    const int nxo = op->nx - 2 * op->halo;
     cudaStream_t st = op->stream;
     Scratch ws;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (n * 4 + RED_BLOCKS + S_COUNT)));
-    cplx *r = ws.base, *p = r + n, *q = p + n, *bs = q + n;
-    cplx* partial = ws.base + n * 4;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (vs * 4 + RED_BLOCKS + S_COUNT)));
+    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(cplx) * vs * 4, st));
+    cplx *r = ws.base + pad, *p = r + vs, *q = p + vs, *bs = q + vs;
+    cplx* partial = ws.base + vs * 4;
     cplx* sc = partial + RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
     cplx h;
     if (check_every < 1) check_every = 1;
     // symmetrised system  D A x = D b,  D = diag(sxf[ix] syf[iy])
     FDFD_CHECK(cudaMemcpyAsync(bs, d_b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    { sym_scale_kernel<<<nblk, 256, 0, st>>>(bs, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
-    if (op_residual(op, d_b, d_x, r, 1)) return -1;
-    { sym_scale_kernel<<<nblk, 256, 0, st>>>(r, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
+    { sym_scale_kernel<<<nblk, 256, 0, st>>>(bs, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+    if (residual_A(op, d_b, d_x, r, nullptr)) return -1;
+    { sym_scale_kernel<<<nblk, 256, 0, st>>>(r, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR, 0)) return -1;
+    if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
@@ -266,20 +285,20 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, false, partial, sc + S_RHO, 0)) return -1;
+    if (dev_dot(st, r, r, n, false, partial, sc + S_RHO, 0, comm)) return -1;
     for (int it = 1; it <= maxiter; ++it) {
         if (apply_A(op, p, q, fused, nullptr)) return -1;
-        { sym_scale_kernel<<<nblk, 256, 0, st>>>(q, op->isxf, op->isyf, op->nx, op->ny); ++g_fdfd_launches; }
-        if (dev_dot(st, p, q, n, false, partial, sc + S_PQ, 0)) return -1;
+        { sym_scale_kernel<<<nblk, 256, 0, st>>>(q, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+        if (dev_dot(st, p, q, n, false, partial, sc + S_PQ, 0, comm)) return -1;
         { cocg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
         { cocg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, p, q, sc, n); ++g_fdfd_launches; }
-        if (dev_dot(st, r, r, n, false, partial, sc + S_RR, 0)) return -1;
+        if (dev_dot(st, r, r, n, false, partial, sc + S_RR, 0, comm)) return -1;
         { cocg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
         { cocg_p_kernel<<<nblk, 256, 0, st>>>(p, r, sc, n); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_TT, 0)) return -1;
+            if (dev_dot(st, r, r, n, true, partial, sc + S_TT, 0, comm)) return -1;
             if (host_scalar(st, sc + S_TT, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;
@@ -287,11 +306,11 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
         }
     }
     // true residual in the ORIGINAL (unscaled) system
-    if (op_residual(op, d_b, d_x, r, 1)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, 0)) return -1;
+    if (residual_A(op, d_b, d_x, r, nullptr)) return -1;
+    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     double rn = sqrt(h.x);
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, 0)) return -1;
+    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = rn / sqrt(h.x);
     return 0;
@@ -307,7 +326,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
     std::vector<double> bn(nrhs);
     cplx h;
     for (int j = 0; j < nrhs; ++j) {
-        if (dev_dot(st, d_b + j * n, d_b + j * n, n, true, partial, sc, 0)) return -1;
+        if (dev_dot(st, d_b + j * n, d_b + j * n, n, true, partial, sc, 0, nullptr)) return -1;
         if (host_scalar(st, sc, &h)) return -1;
         bn[j] = sqrt(h.x);
     }
@@ -318,7 +337,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
         if (op_residual(op, d_b, d_x, r, nrhs)) return -1;
         worst = 0.0;
         for (int j = 0; j < nrhs; ++j) {
-            if (dev_dot(st, r + j * n, r + j * n, n, true, partial, sc, 0)) return -1;
+            if (dev_dot(st, r + j * n, r + j * n, n, true, partial, sc, 0, nullptr)) return -1;
             if (host_scalar(st, sc, &h)) return -1;
             double rel = bn[j] > 0 ? sqrt(h.x) / bn[j] : 0.0;
             if (!(rel == rel)) rel = 1e300;

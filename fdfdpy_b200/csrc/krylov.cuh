@@ -10,7 +10,7 @@ struct KrylovResult {
 };
 
 int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
-            int real_only);
+            int real_only, FdfdComm* comm = nullptr);
 int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
                     int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res);
 int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,

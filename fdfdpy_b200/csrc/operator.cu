@@ -98,10 +98,11 @@ __global__ void assemble_planes_kernel(cplx* __restrict__ planes, const cplx* __
 template <bool RESID>
 __global__ void __launch_bounds__(256)
 stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ x, const cplx* __restrict__ b,
-                      cplx* __restrict__ y, int nx, int ny) {
+                      cplx* __restrict__ y, int nx, int ny, int halo) {
     size_t n = (size_t)nx * ny;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    if (idx >= n - 2 * (size_t)halo * ny) return;
+    idx += (size_t)halo * ny;                    // slab: rows 1..nx-2 only, the halo rows are inputs
     size_t voff = (size_t)blockIdx.y * n;
     const cplx* xv = x + voff;
     int ix = (int)(idx / ny), iy = (int)(idx % ny);
@@ -129,9 +130,9 @@ stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__
                         const cplx* __restrict__ isxf, const cplx* __restrict__ isxb,
                         const cplx* __restrict__ isyf, const cplx* __restrict__ isyb,
                         const cplx* __restrict__ x, cplx* __restrict__ y, int nx, int ny,
-                        double inv_mu_dx2, double inv_mu_dy2, double w2e0) {
+                        double inv_mu_dx2, double inv_mu_dy2, double w2e0, int halo) {
     int iy = blockIdx.x * blockDim.x + threadIdx.x;
-    int ix0 = blockIdx.y * FUSED_ROWS;
+    int ix0 = halo + blockIdx.y * FUSED_ROWS;
     if (iy >= ny) return;
     size_t n = (size_t)nx * ny;
     size_t voff = (size_t)blockIdx.z * n;
@@ -145,7 +146,7 @@ stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__
 #pragma unroll
     for (int r = 0; r < FUSED_ROWS; ++r) {
         int ix = ix0 + r;
-        if (ix >= nx) break;
+        if (ix >= nx - halo) break;
         int ixp = ix + 1 == nx ? 0 : ix + 1;
         size_t row = (size_t)ix * ny;
         cplx xr = ldg_c(xv + (size_t)ixp * ny + iy);
@@ -227,14 +228,22 @@ static AsmParams make_params(const FdfdOp* op) {
     return p;
 }
 
-int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol,
-              double L0) {
+// ext[j] = glob[(x0 - 1 + j) mod gnx]: the slab's slice of a per-row array, halo rows included
+__global__ void slab_slice_kernel(cplx* __restrict__ ext, const cplx* __restrict__ glob, int next, int gnx, int x0) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= next) return;
+    ext[j] = glob[((x0 - 1 + j) % gnx + gnx) % gnx];
+}
+
+static int op_create_impl(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol,
+                          double L0, int halo, int gnx, int x0, FdfdComm* comm) {
     if (nx < 2 || ny < 2) FDFD_FAIL("grid must be at least 2x2, got %dx%d", nx, ny);
     if (pol != 0 && pol != 1) FDFD_FAIL("pol must be 0 (Ez) or 1 (Hz)");
     FdfdOp* op = new FdfdOp();
     memset(op, 0, sizeof(*op));
     op->nx = nx; op->ny = ny; op->omega = omega; op->dl = dl; op->L0 = L0;
     op->npml_x = npml_x; op->npml_y = npml_y; op->pol = pol; op->averaging = 1;
+    op->halo = halo; op->gnx = gnx; op->x0 = x0; op->comm = comm;
     FDFD_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
     size_t n = op->n();
     FDFD_CHECK(cudaMalloc(&op->isxf, sizeof(cplx) * nx));
@@ -245,11 +254,49 @@ int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x,
     FDFD_CHECK(cudaMalloc(&op->eps_nl, sizeof(cplx) * n));
     FDFD_CHECK(cudaMalloc(&op->planes, sizeof(cplx) * n * 5));
     AsmParams p = make_params(op);
-    { pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0); ++g_fdfd_launches; }
+    if (!halo) {
+        { pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0); ++g_fdfd_launches; }
+    } else {
+        // the stretch factors of the WHOLE axis, then this slab's rows (and its neighbours' boundary rows)
+        cplx *gf = nullptr, *gb = nullptr;
+        FDFD_CHECK(cudaMalloc(&gf, sizeof(cplx) * gnx));
+        FDFD_CHECK(cudaMalloc(&gb, sizeof(cplx) * gnx));
+        { pml_axis_kernel<<<ceil_div(gnx, 128), 128, 0, op->stream>>>(gf, gb, gnx, npml_x, p.dx, omega, L0); ++g_fdfd_launches; }
+        { slab_slice_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, gf, nx, gnx, x0); ++g_fdfd_launches; }
+        { slab_slice_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxb, gb, nx, gnx, x0); ++g_fdfd_launches; }
+        FDFD_CHECK(cudaStreamSynchronize(op->stream));
+        cudaFree(gf); cudaFree(gb);
+    }
     { pml_axis_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->isyf, op->isyb, ny, npml_y, p.dy, omega, L0); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     *out = op;
+    return 0;
+}
+
+int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y, int pol, double L0) {
+    return op_create_impl(out, nx, ny, omega, dl, npml_x, npml_y, pol, L0, 0, nx, 0, nullptr);
+}
+
+int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nxl, double omega, double dl,
+                   int npml_x, int npml_y, int pol, double L0) {
+    if (nxl < 1 || x0 < 0 || x0 + nxl > gnx) FDFD_FAIL("slab rows [%d, %d) outside the %d-row grid", x0, x0 + nxl, gnx);
+    return op_create_impl(out, nxl + 2, ny, omega, dl, npml_x, npml_y, pol, L0, 1, gnx, x0, comm);
+}
+
+int op_halo_exchange(const FdfdOp* op, cplx* x) {
+    if (!op->halo) return 0;
+    const size_t ny = op->ny, row = sizeof(cplx) * ny;
+    cplx *first = x + ny, *last = x + (size_t)(op->nx - 2) * ny, *halo_lo = x, *halo_hi = x + (size_t)(op->nx - 1) * ny;
+    if (!op->comm || op->comm->world == 1) {         // one slab: the grid wraps onto itself
+        FDFD_CHECK(cudaMemcpyAsync(halo_lo, last, row, cudaMemcpyDeviceToDevice, op->stream));
+        FDFD_CHECK(cudaMemcpyAsync(halo_hi, first, row, cudaMemcpyDeviceToDevice, op->stream));
+        return 0;
+    }
+    const int w = op->comm->world, r = op->comm->rank, lower = (r + w - 1) % w, upper = (r + 1) % w;
+    // my first row is the upper halo of the rank below, my last row the lower halo of the rank above
+    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, 2 * ny, op->stream)) return -1;
+    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, 2 * ny, op->stream)) return -1;
     return 0;
 }
 
@@ -304,27 +351,36 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     return 0;
 }
 
+static int slab_prepare(const FdfdOp* op, const cplx* d_x, int nvec) {
+    if (!op->halo) return 0;
+    if (nvec != 1) FDFD_FAIL("slab operators apply one vector at a time");
+    return op_halo_exchange(op, const_cast<cplx*>(d_x));
+}
+
 int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
-    dim3 grid(ceil_div(op->n(), 256), nvec);
-    { stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny); ++g_fdfd_launches; }
+    if (slab_prepare(op, d_x, nvec)) return -1;
+    dim3 grid(ceil_div(op->n() - 2 * (size_t)op->halo * op->ny, 256), nvec);
+    { stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny, op->halo); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
 
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
-    dim3 grid(ceil_div(op->n(), 256), nvec);
-    { stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny); ++g_fdfd_launches; }
+    if (slab_prepare(op, d_x, nvec)) return -1;
+    dim3 grid(ceil_div(op->n() - 2 * (size_t)op->halo * op->ny, 256), nvec);
+    { stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny, op->halo); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
 
 int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
     if (op->pol != 0) return op_apply_planes(op, d_x, d_y, nvec);
+    if (slab_prepare(op, d_x, nvec)) return -1;
     AsmParams p = make_params(op);
-    dim3 grid(ceil_div(op->ny, 128), ceil_div(op->nx, FUSED_ROWS), nvec);
+    dim3 grid(ceil_div(op->ny, 128), ceil_div(op->nx - 2 * op->halo, FUSED_ROWS), nvec);
     { stencil_fused_ez_kernel<<<grid, 128, 0, op->stream>>>(
         op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, d_x, d_y,
-        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0); ++g_fdfd_launches; }
+        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0, op->halo); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }

@@ -1,5 +1,6 @@
 // Device-resident Maxwell operator: sc-PML factors, stencil planes, matrix-free apply.
 #pragma once
+#include "comm.cuh"
 #include "common.cuh"
 
 // fdfdpy/constants.py:3-6
@@ -23,12 +24,22 @@ struct FdfdOp {
     cplx *planes;
     // lazily allocated staging for the *_host entry points (4*nx*ny complex: b, x, f1, f2)
     cplx *io_buf;
+    // slab of a grid split over several GPUs (halo = 1): nx counts the slab's rows PLUS one halo row on each
+    // side, every vector has that extended layout, the stencil only writes rows 1..nx-2 and the halo rows of
+    // its input are filled from the neighbouring ranks (periodic in the rank index) before it runs
+    int halo, gnx, x0;
+    FdfdComm* comm;     // not owned; null with halo = 1 means a single slab wrapping onto itself
     size_t n() const { return (size_t)nx * ny; }
 };
 
 int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x, int npml_y,
               int pol, double L0);
+// slab operator: rows [x0, x0 + nxl) of a gnx x ny grid
+int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nxl, double omega, double dl,
+                   int npml_x, int npml_y, int pol, double L0);
 void op_destroy(FdfdOp* op);
+// fills the two halo rows of an extended-layout vector from the neighbouring slabs
+int op_halo_exchange(const FdfdOp* op, cplx* d_x_ext);
 // eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes
 int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging);
 // y = A x using the stored planes (any polarisation, nonlinearity included); nvec vectors back to back

@@ -68,3 +68,77 @@ class Communicator:
                 self.h = C.c_void_p()
         except Exception:
             pass
+
+
+def slab_rows(gnx, world, rank):
+    """Rows [x0, x1) of rank ``rank``: contiguous blocks whose sizes differ by at most one."""
+    base, extra = divmod(int(gnx), int(world))
+    x0 = rank * base + min(rank, extra)
+    return x0, x0 + base + (1 if rank < extra else 0)
+
+
+class SlabOperator:
+    """This rank's slab of the Maxwell operator (rows x0..x1 of the reference's (Nx, Ny) arrays) with
+    the matrix-free stencil and the Krylov solvers running across the ranks: halo rows travel over
+    NCCL send/recv, inner products are all-reduced on the device.
+
+    ``eps_r`` is the WHOLE permittivity array (every rank passes the same one; only its slab and the
+    two neighbouring rows go to the device).  Vectors are per-rank slabs of shape (x1 - x0, Ny).
+    ``comm=None`` builds a single slab that wraps onto itself (world size 1)."""
+
+    def __init__(self, omega, eps_r, dl, NPML, pol, L0, comm=None, rows=None):
+        from .core import POL
+        self.lib = _lib.load()
+        _lib.require_gpu()
+        eps_r = np.asarray(eps_r)
+        self.gnx, self.ny = eps_r.shape
+        self.comm = comm
+        world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
+        self.x0, self.x1 = rows if rows is not None else slab_rows(self.gnx, world, rank)
+        self.nxl = self.x1 - self.x0
+        self.pol = pol
+        self.h = C.c_void_p()
+        check(self.lib.fdfd_slab_op_create(C.byref(self.h), comm.h if comm is not None else None, self.gnx, self.ny,
+                                           self.x0, self.nxl, float(omega), float(dl), int(NPML[0]), int(NPML[1]),
+                                           POL[pol], float(L0)))
+        self.assemble(eps_r)
+
+    def _ext_rows(self):
+        return np.arange(self.x0 - 1, self.x1 + 1) % self.gnx
+
+    def assemble(self, eps_r, averaging=True):
+        ext = _lib.as_c128(np.asarray(eps_r)[self._ext_rows()])
+        check(self.lib.fdfd_op_assemble_host(self.h, _lib.ptr(ext), None, int(bool(averaging))))
+
+    def to_ext(self, v):
+        v = np.asarray(v)
+        if v.shape != (self.nxl, self.ny):
+            raise ValueError("slab vectors have shape {}".format((self.nxl, self.ny)))
+        ext = np.zeros((self.nxl + 2, self.ny), dtype=np.complex128)
+        ext[1:-1] = v
+        return ext
+
+    def dot(self, x, fused=False):
+        """y = A x on this rank's rows (collective: every rank must call it)."""
+        xe = self.to_ext(x)
+        ye = np.zeros_like(xe)
+        check(self.lib.fdfd_op_apply_host(self.h, _lib.ptr(xe), _lib.ptr(ye), 1, int(fused)))
+        return ye[1:-1]
+
+    def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10):
+        """Distributed BiCGSTAB / COCG on the slabs (collective)."""
+        be = self.to_ext(b)
+        xe = self.to_ext(np.zeros_like(be[1:-1]) if x0 is None else x0)
+        it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+        check(self.lib.fdfd_krylov_solve_host(self.h, None, _lib.ptr(be), _lib.ptr(xe), {"bicgstab": 0, "cocg": 1}[method],
+                                              float(tol), int(maxiter), int(fused and self.pol == "Ez"), int(check_every),
+                                              None, 0, C.byref(it), C.byref(rr), C.byref(conv)))
+        return xe[1:-1].copy(), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                self.lib.fdfd_op_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass

@@ -133,6 +133,16 @@ int fdfd_comm_allreduce_sum_dev(fdfd_comm* c, fdfd_op* op, void* d_buf, double c
  * exchange one Schur block / ring vector per level point to point, the solution is summed over
  * ranks (every cell is written by exactly one).  Operator, b and x are replicated on every rank. */
 int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c);
+/* slab operator: rows [x0, x0 + nxl) of a gnx x ny grid (rows = the slow index of the reference's
+ * C-ordered fields; a split along the other axis is the same call on the transposed problem).
+ * Every array of a slab operator -- eps_r for fdfd_op_assemble_*, x / y / b of fdfd_op_apply_* and
+ * fdfd_krylov_solve_* (precond and c12 must be NULL) -- has the EXTENDED layout (nxl + 2) x ny:
+ * row 0 and row nxl + 1 mirror the neighbouring slabs' boundary rows (periodic in the rank index).
+ * eps_r must be given with its halo rows filled; vector halos are exchanged by the library (NCCL
+ * send/recv on the operator's stream) before every stencil application, and inner products are
+ * summed over ranks on the device.  comm == NULL: a single slab that wraps onto itself.          */
+int fdfd_slab_op_create(fdfd_op** out, fdfd_comm* comm, int gnx, int ny, int x0, int nxl, double omega,
+                        double dl, int npml_x, int npml_y, int pol, double L0);
 
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).

@@ -100,3 +100,73 @@ def test_shard_plan_partitions_the_tree():
             assert sum(1 for lv in shards[0] if lv.recv_from >= 0) == int(np.log2(world))
     with pytest.raises(ValueError):
         shard_plan(levels, 3, 0)
+
+
+def _worker_slab(rank, world, port, shape, npml, pol, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        from fdfdpy_b200.distributed import slab_rows
+        from oracle import fdfd_oracle as orc
+        nx, ny = shape
+        rng = np.random.default_rng(2)
+        eps = 1 + 5 * rng.random((nx, ny))
+        x = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+        omega = 2 * np.pi * 200e12
+        c0, cxm, cxp, cym, cyp = orc.stencil_planes(omega, eps, 0.04, npml, pol, 1e-6)
+        x0, x1 = slab_rows(nx, world, rank)
+        # the slab in the library's extended layout: one halo row on each side, filled by the neighbours
+        ext = np.zeros((x1 - x0 + 2, ny), dtype=np.complex128)
+        ext[1:-1] = x[x0:x1]
+        lower, upper = (rank - 1) % world, (rank + 1) % world
+        comm = GlooComm(dist, torch)
+        # same order as op_halo_exchange: first row down / upper halo in, then last row up / lower halo in
+        reqs = [dist.isend(torch.from_numpy(ext[1].view(np.float64).copy()), lower)]
+        ext[-1] = comm.recv((ny,), upper)
+        reqs.append(dist.isend(torch.from_numpy(ext[-2].view(np.float64).copy()), upper))
+        ext[0] = comm.recv((ny,), lower)
+        for r in reqs:
+            r.wait()
+        sl = slice(x0, x1)
+        y = (c0[sl] * ext[1:-1] + cxm[sl] * ext[:-2] + cxp[sl] * ext[2:] +
+             cym[sl] * np.roll(ext[1:-1], 1, axis=1) + cyp[sl] * np.roll(ext[1:-1], -1, axis=1))
+        ref = orc.planes_to_csr((c0, cxm, cxp, cym, cyp)).dot(x.ravel()).reshape(nx, ny)[sl]
+        # inner product summed over the ranks equals the global one
+        part = np.array([np.vdot(x[sl], y)])
+        tot = comm.allreduce(part)[0]
+        gref = np.vdot(x, orc.planes_to_csr((c0, cxm, cxp, cym, cyp)).dot(x.ravel()).reshape(nx, ny))
+        q.put((rank, float(np.linalg.norm(y - ref) / np.linalg.norm(ref)), float(abs(tot - gref) / abs(gref))))
+    except Exception as e:
+        q.put((rank, repr(e), 0.0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,pol", [(2, (21, 16), "Ez"), (3, (20, 12), "Hz")])
+def test_slab_halo_exchange_gloo(world, shape, pol):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_slab, args=(r, world, port, shape, [3, 3], pol, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, derr in res:
+        assert isinstance(err, float), (rank, err)
+        assert err < 1e-13 and derr < 1e-12, (rank, err, derr)
+
+
+def test_slab_rows_cover_the_grid():
+    from fdfdpy_b200.distributed import slab_rows
+    for gnx in (7, 64, 100, 4096):
+        for world in (1, 2, 3, 8):
+            rows = [slab_rows(gnx, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == gnx
+            assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+            sizes = [b - a for a, b in rows]
+            assert max(sizes) - min(sizes) <= 1

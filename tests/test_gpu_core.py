@@ -214,3 +214,29 @@ def test_mode_solve_golden(core, golden):
         assert up_to_sign(vecs[0], g[pol + "_src"][15, 10:40]) < 1e-8, pol
         vals, vecs = core.mode_solve(epsT[8:52, 15], omega, dl, pol, L0, 3.5, order=2, averaged=True)
         assert up_to_sign(2 * vecs[1], g[pol + "_srcT"][8:52, 15]) < 1e-8, pol
+
+
+@pytest.mark.parametrize("pol", ["Ez", "Hz"])
+def test_single_slab_operator_matches_whole_grid(core, pol):
+    """The slab code path (extended layout, halo rows, interior-only kernels, padded Krylov vectors) with one
+    slab wrapping onto itself must reproduce the whole-grid operator."""
+    from fdfdpy_b200.distributed import SlabOperator
+    rng = np.random.default_rng(5)
+    nx, ny = 40, 36
+    eps = 1 + 2 * rng.random((nx, ny))
+    npml = [8, 8]
+    op = core.MaxwellOperator(OMEGA, eps, 0.05, npml, pol, 1e-6)
+    slab = SlabOperator(OMEGA, eps, 0.05, npml, pol, 1e-6)
+    x = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+    ref = orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6).dot(x.ravel()).reshape(nx, ny)
+    assert relerr(slab.dot(x), ref) < 1e-13
+    assert relerr(op.dot(x), ref) < 1e-13
+    if pol == "Ez":
+        assert relerr(slab.dot(x, fused=True), ref) < 1e-13
+    b = np.zeros((nx, ny), dtype=complex)
+    b[20, 18] = 1j * OMEGA
+    sol = orc.sparse_solve(orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6), b).reshape(nx, ny)
+    for method in ("bicgstab", "cocg"):
+        xs, info = slab.krylov(b, method=method, tol=1e-11, maxiter=20000, check_every=20)
+        assert info["relres"] < 1e-8, (method, info)
+        assert relerr(xs, sol) < 1e-6

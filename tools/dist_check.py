@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--pol", default="Ez")
+    ap.add_argument("--slab-parity", default="")
+    ap.add_argument("--slab-size", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=200)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -86,6 +89,87 @@ def main():
         fb, tb = C.c_double(0), C.c_double(0)
         lib.fdfd_mem_info(C.byref(fb), C.byref(tb))
         out["hbm_used_gb_this_rank"] = (tb.value - fb.value) / 1e9
+    if args.slab_parity:
+        from fdfdpy_b200.distributed import SlabOperator
+        from oracle import fdfd_oracle as orc
+        nx, ny = (int(v) for v in args.slab_parity.split("x"))
+        rng = np.random.default_rng(7)
+        eps = 1 + 2 * rng.random((nx, ny))
+        npml = [8, 8]
+        slab = SlabOperator(omega, eps, 0.05, npml, args.pol, 1e-6, comm=comm)
+        sl = slice(slab.x0, slab.x1)
+        xv = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+        A = orc.construct_A(omega, eps, 0.05, npml, args.pol, 1e-6)
+        ref = A.dot(xv.ravel()).reshape(nx, ny)[sl]
+        y = slab.dot(xv[sl])
+        out["slab_apply_rel_err"] = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
+        if args.pol == "Ez":
+            yf = slab.dot(xv[sl], fused=True)
+            out["slab_apply_fused_rel_err"] = float(np.linalg.norm(yf - ref) / np.linalg.norm(ref))
+        b = np.zeros((nx, ny), dtype=complex)
+        b[nx // 2, ny // 2] = 1j * omega
+        sol = orc.sparse_solve(A, b).reshape(nx, ny)[sl]
+        for method in ("bicgstab", "cocg"):
+            xs, info = slab.krylov(b[sl], method=method, tol=1e-11, maxiter=20000, check_every=20)
+            nrm = torch.tensor([np.linalg.norm(xs - sol) ** 2, np.linalg.norm(sol) ** 2], dtype=torch.float64)
+            dist.all_reduce(nrm)
+            out["slab_" + method] = dict(info, rel_l2_vs_oracle=float(np.sqrt(nrm[0] / nrm[1])))
+        del slab
+
+    if args.slab_size:
+        import ctypes as C
+        import bench
+        from fdfdpy_b200.distributed import SlabOperator
+        n = args.slab_size
+        eps = bench.synthetic_eps(n)
+        slab = SlabOperator(bench.OMEGA0, eps, bench.DL, bench.NPML, "Ez", bench.L0, comm=comm)
+        nloc = (slab.nxl + 2) * n
+        d_x, d_y = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.fdfd_malloc(C.byref(d_x), 16.0 * nloc))
+        _lib.check(lib.fdfd_malloc(C.byref(d_y), 16.0 * nloc))
+        xe = np.zeros((slab.nxl + 2, n), dtype=np.complex128)
+        xe[1:-1] = 1.0
+        _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(xe), 16.0 * nloc))
+        _lib.check(lib.fdfd_memcpy_h2d(d_y, _lib.ptr(xe), 16.0 * nloc))
+        res = {}
+        for fused in (1, 0):
+            for _ in range(5):
+                _lib.check(lib.fdfd_op_apply_dev(slab.h, d_x, d_y, 1, fused))
+            dist.barrier()
+            ms = C.c_double(0)
+            _lib.check(lib.fdfd_timer_start(slab.h))
+            for _ in range(args.iters):
+                _lib.check(lib.fdfd_op_apply_dev(slab.h, d_x, d_y, 1, fused))
+            _lib.check(lib.fdfd_timer_stop(slab.h, C.byref(ms)))
+            tt = torch.tensor([ms.value], dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            per = float(tt[0]) / args.iters
+            bytes_cell = 48 if fused else 112
+            res["fused" if fused else "planes"] = {"ms_per_apply": per, "agg_GBps": bytes_cell * n * n / (per * 1e-3) / 1e9,
+                                                   "Gcell_per_s": n * n / (per * 1e-3) / 1e9}
+        # a fixed number of BiCGSTAB iterations (2 stencils + 5 all-reduced inner products each)
+        it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+        be = np.zeros((slab.nxl + 2, n), dtype=np.complex128)
+        if slab.x0 <= n // 2 < slab.x1:
+            be[1 + n // 2 - slab.x0, n // 2] = 1j * bench.OMEGA0
+        _lib.check(lib.fdfd_memcpy_h2d(d_y, _lib.ptr(be), 16.0 * nloc))
+        _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(np.zeros_like(be)), 16.0 * nloc))
+        for warm in (1, 0):
+            dist.barrier()
+            ms = C.c_double(0)
+            _lib.check(lib.fdfd_timer_start(slab.h))
+            _lib.check(lib.fdfd_krylov_solve_dev(slab.h, None, d_y, d_x, 0, 1e-30, args.iters, 1, args.iters, None, 0,
+                                                 C.byref(it), C.byref(rr), C.byref(conv)))
+            _lib.check(lib.fdfd_timer_stop(slab.h, C.byref(ms)))
+        tt = torch.tensor([ms.value], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res["bicgstab"] = {"iters": it.value, "ms_per_iter": float(tt[0]) / max(it.value, 1), "relres_after": rr.value}
+        out["slab_size"] = n
+        out["slab_throughput"] = res
+        lib.fdfd_free(d_x)
+        lib.fdfd_free(d_y)
+        del slab
+
     per_rank = [None] * world
     dist.all_gather_object(per_rank, out)
     if rank == 0:
