@@ -345,7 +345,14 @@ def run_ours(args):
         "roofline": {
             "kernel": "zgemm_dmma_kernel<4,2,3> (rank-T sweep update, complex128 on DMMA m8n8k4)",
             "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+            "frac": achieved / fp64_peak if fp64_peak else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+            # (profiles/r01_full_capture_zgemm_persistent_and_planes_stencil.txt): the level-19 Schur update
+            # S(8192x8192, lower) -= G(8192x4094) F_RE^T, 1.108e12 flop, 2.15e9 algorithmic bytes; DRAM runs at 8 %
+            # of its peak there (tensor-bound kernel, 91.5 % tensor-pipe active), so the 10x re-read is not the limiter
+            "traffic": 2.197e10,
+            "traffic_note": "bytes of one captured launch (1.108e12 flop, 2.15e9 algorithmic bytes), not of the "
+                            "per-step average launch; see profiles/",
             "peak_source": "FP64 tensor pipe: 148 SMs x 128 flop/clk x the SM clock sampled under load "
                            "(MEASURED_PEAKS.json has no FP64 entry; vendor-nominal is 40 TFLOP/s)",
             "dmma_probe_tflops": dmma.value,
