@@ -89,6 +89,7 @@ SIGNATURES = {
                                         _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int]),
+    "fdfd_stencil_set_variant": (C.c_int, [C.c_int]),
     "fdfd_zgemm_set_variant": (C.c_int, [C.c_int]),
     "fdfd_direct_set_small_fronts": (C.c_int, [C.c_int]),
     "fdfd_zgemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),

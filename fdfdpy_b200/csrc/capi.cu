@@ -423,6 +423,12 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
     return 0;
 }
 
+extern int g_fused_rows;
+int fdfd_stencil_set_variant(int rows_per_thread) {
+    if (rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8) FDFD_FAIL("rows per thread: 2, 4 or 8");
+    g_fused_rows = rows_per_thread;
+    return 0;
+}
 int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }
 extern int g_small_front_enabled;
 int fdfd_direct_set_small_fronts(int enable) { g_small_front_enabled = enable != 0; return 0; }

@@ -98,11 +98,11 @@ __global__ void assemble_planes_kernel(cplx* __restrict__ planes, const cplx* __
 template <bool RESID>
 __global__ void __launch_bounds__(256)
 stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ x, const cplx* __restrict__ b,
-                      cplx* __restrict__ y, int nx, int ny, int halo) {
+                      cplx* __restrict__ y, int nx, int ny, int row0, int row1) {
     size_t n = (size_t)nx * ny;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n - 2 * (size_t)halo * ny) return;
-    idx += (size_t)halo * ny;                    // slab: rows 1..nx-2 only, the halo rows are inputs
+    if (idx >= (size_t)(row1 - row0) * ny) return;
+    idx += (size_t)row0 * ny;                    // rows [row0, row1): a slab never writes its halo rows
     size_t voff = (size_t)blockIdx.y * n;
     const cplx* xv = x + voff;
     int ix = (int)(idx / ny), iy = (int)(idx % ny);
@@ -124,29 +124,91 @@ stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ 
 // Algorithmic traffic 48 B/cell (x 16 + eps 16 + y 16) (+16 with eps_nl).  Each thread owns one
 // y column and marches ROWS consecutive rows keeping the x-neighbours in registers.
 // ------------------------------------------------------------------------------------------
-#define FUSED_ROWS 8
+int g_fused_rows = 4;          // A/B switch (fdfd_stencil_set_variant): rows marched per thread
+
+__device__ __forceinline__ cplx shfl_up_c(cplx v) {
+    return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ cplx shfl_down_c(cplx v) {
+    return make_double2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+
+// ax[ix] = (isxf[ix] isxb[ix], isxf[ix] isxb[ix+1]) / (mu0' dx^2): the two x-coupling coefficients of row ix
+// (and the same along y), built once per operator so the stencil only streams x, eps and y.
+__global__ void pml_products_kernel(cplx* __restrict__ am, cplx* __restrict__ ap, const cplx* __restrict__ isf,
+                                    const cplx* __restrict__ isb, int n, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ip = i + 1 == n ? 0 : i + 1;
+    am[i] = cscale(cmul(isf[i], isb[i]), scale);
+    ap[i] = cscale(cmul(isf[i], isb[ip]), scale);
+}
+
+// Each thread owns one y column and marches ROWS consecutive rows.  The x-neighbours stay in registers, the
+// y-neighbours come from the adjacent lanes by shuffle (only the two edge lanes of a warp load them), the
+// coupling coefficients are 1-D tables (warp-uniform loads).  There is no barrier and no early exit in the
+// full-CTA body, so every load of a thread is issued before the first one is consumed.
+template <int ROWS>
 __global__ void __launch_bounds__(128)
 stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__ eps_nl,
-                        const cplx* __restrict__ isxf, const cplx* __restrict__ isxb,
-                        const cplx* __restrict__ isyf, const cplx* __restrict__ isyb,
-                        const cplx* __restrict__ x, cplx* __restrict__ y, int nx, int ny,
-                        double inv_mu_dx2, double inv_mu_dy2, double w2e0, int halo) {
-    int iy = blockIdx.x * blockDim.x + threadIdx.x;
-    int ix0 = halo + blockIdx.y * FUSED_ROWS;
-    if (iy >= ny) return;
-    size_t n = (size_t)nx * ny;
-    size_t voff = (size_t)blockIdx.z * n;
+                        const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
+                        const cplx* __restrict__ aym_t, const cplx* __restrict__ ayp_t,
+                        const cplx* __restrict__ x, cplx* __restrict__ y, int nx, int ny, double w2e0, int row0,
+                        int row1) {
+    const int ix0 = row0 + blockIdx.y * ROWS;
+    const int rows = min(ROWS, row1 - ix0);
+    const int iy_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = iy_raw < ny;
+    const int iy = active ? iy_raw : ny - 1;            // inactive lanes shadow the last column (shuffles stay full-warp)
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)nx * ny;
+    const size_t voff = (size_t)blockIdx.z * n;
     const cplx* xv = x + voff;
-    int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
-    cplx aym = cscale(cmul(isyf[iy], isyb[iy]), inv_mu_dy2);
-    cplx ayp = cscale(cmul(isyf[iy], isyb[iyp]), inv_mu_dy2);
-    int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
-    cplx xl = ldg_c(xv + (size_t)ixm * ny + iy);
-    cplx xc = ldg_c(xv + (size_t)ix0 * ny + iy);
+    const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || iy_raw >= ny - 1;
+    const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
+    if (rows == ROWS) {
+        cplx xc[ROWS + 2], e[ROWS];
+        xc[0] = ldg_c(xv + (size_t)ixm * ny + iy);
 #pragma unroll
-    for (int r = 0; r < FUSED_ROWS; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
+            xc[r + 1] = ldg_c(xv + (size_t)(ix0 + r) * ny + iy);
+            e[r] = ldg_c(eps_r + (size_t)(ix0 + r) * ny + iy);
+        }
+        {
+            int ixl = ix0 + ROWS == nx ? 0 : ix0 + ROWS;
+            xc[ROWS + 1] = ldg_c(xv + (size_t)ixl * ny + iy);
+        }
+        const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
+        const cplx ay = cadd(aym, ayp);
+        if (eps_nl) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) e[r] = cadd(e[r], ldg_c(eps_nl + (size_t)(ix0 + r) * ny + iy));
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            // coefficient tables and the two edge-lane neighbours are cache hits (same lines as adjacent warps)
+            const cplx axm = ldg_c(axm_t + ix0 + r), axp = ldg_c(axp_t + ix0 + r);
+            cplx xd = shfl_up_c(xc[r + 1]), xu = shfl_down_c(xc[r + 1]);
+            if (load_dn) xd = ldg_c(xv + (size_t)(ix0 + r) * ny + iym);
+            if (load_up) xu = ldg_c(xv + (size_t)(ix0 + r) * ny + iyp);
+            cplx c0 = csub(csub(cscale(e[r], w2e0), cadd(axm, axp)), ay);
+            cplx acc = cmul(c0, xc[r + 1]);
+            cfma(acc, axm, xc[r]);
+            cfma(acc, axp, xc[r + 2]);
+            cfma(acc, aym, xd);
+            cfma(acc, ayp, xu);
+            if (active) y[voff + (size_t)(ix0 + r) * ny + iy] = acc;
+        }
+        return;
+    }
+    // ragged last CTA row of the grid
+    const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
+    const cplx ay = cadd(aym, ayp);
+    cplx xl = ldg_c(xv + (size_t)ixm * ny + iy);
+    cplx xcur = ldg_c(xv + (size_t)ix0 * ny + iy);
+    for (int r = 0; r < rows; ++r) {
         int ix = ix0 + r;
-        if (ix >= nx - halo) break;
         int ixp = ix + 1 == nx ? 0 : ix + 1;
         size_t row = (size_t)ix * ny;
         cplx xr = ldg_c(xv + (size_t)ixp * ny + iy);
@@ -154,17 +216,16 @@ stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__
         cplx xu = ldg_c(xv + row + iyp);
         cplx e = ldg_c(eps_r + row + iy);
         if (eps_nl) e = cadd(e, ldg_c(eps_nl + row + iy));
-        cplx axm = cscale(cmul(isxf[ix], isxb[ix]), inv_mu_dx2);
-        cplx axp = cscale(cmul(isxf[ix], isxb[ixp]), inv_mu_dx2);
-        cplx c0 = csub(csub(cscale(e, w2e0), cadd(axm, axp)), cadd(aym, ayp));
-        cplx acc = cmul(c0, xc);
+        const cplx axm = ldg_c(axm_t + ix), axp = ldg_c(axp_t + ix);
+        cplx c0 = csub(csub(cscale(e, w2e0), cadd(axm, axp)), ay);
+        cplx acc = cmul(c0, xcur);
         cfma(acc, axm, xl);
         cfma(acc, axp, xr);
         cfma(acc, aym, xd);
         cfma(acc, ayp, xu);
-        y[voff + row + iy] = acc;
-        xl = xc;
-        xc = xr;
+        if (active) y[voff + row + iy] = acc;
+        xl = xcur;
+        xcur = xr;
     }
 }
 
@@ -268,6 +329,16 @@ static int op_create_impl(FdfdOp** out, int nx, int ny, double omega, double dl,
         cudaFree(gf); cudaFree(gb);
     }
     { pml_axis_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->isyf, op->isyb, ny, npml_y, p.dy, omega, L0); ++g_fdfd_launches; }
+    if (halo && comm && comm->world > 1) {
+        FDFD_CHECK(cudaStreamCreateWithFlags(&op->comm_stream, cudaStreamNonBlocking));
+        FDFD_CHECK(cudaEventCreateWithFlags(&op->ev_in, cudaEventDisableTiming));
+        FDFD_CHECK(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
+    }
+    // coupling-coefficient tables of the matrix-free Ez stencil
+    FDFD_CHECK(cudaMalloc(&op->ax, sizeof(cplx) * 2 * nx));
+    FDFD_CHECK(cudaMalloc(&op->ay, sizeof(cplx) * 2 * ny));
+    { pml_products_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->ax, op->ax + nx, op->isxf, op->isxb, nx, 1.0 / (p.m0 * p.dx * p.dx)); ++g_fdfd_launches; }
+    { pml_products_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->ay, op->ay + ny, op->isyf, op->isyb, ny, 1.0 / (p.m0 * p.dy * p.dy)); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     *out = op;
@@ -284,19 +355,19 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
     return op_create_impl(out, nxl + 2, ny, omega, dl, npml_x, npml_y, pol, L0, 1, gnx, x0, comm);
 }
 
-int op_halo_exchange(const FdfdOp* op, cplx* x) {
+int op_halo_exchange(const FdfdOp* op, cplx* x, cudaStream_t st) {
     if (!op->halo) return 0;
     const size_t ny = op->ny, row = sizeof(cplx) * ny;
     cplx *first = x + ny, *last = x + (size_t)(op->nx - 2) * ny, *halo_lo = x, *halo_hi = x + (size_t)(op->nx - 1) * ny;
     if (!op->comm || op->comm->world == 1) {         // one slab: the grid wraps onto itself
-        FDFD_CHECK(cudaMemcpyAsync(halo_lo, last, row, cudaMemcpyDeviceToDevice, op->stream));
-        FDFD_CHECK(cudaMemcpyAsync(halo_hi, first, row, cudaMemcpyDeviceToDevice, op->stream));
+        FDFD_CHECK(cudaMemcpyAsync(halo_lo, last, row, cudaMemcpyDeviceToDevice, st));
+        FDFD_CHECK(cudaMemcpyAsync(halo_hi, first, row, cudaMemcpyDeviceToDevice, st));
         return 0;
     }
     const int w = op->comm->world, r = op->comm->rank, lower = (r + w - 1) % w, upper = (r + 1) % w;
     // my first row is the upper halo of the rank below, my last row the lower halo of the rank above
-    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, 2 * ny, op->stream)) return -1;
-    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, 2 * ny, op->stream)) return -1;
+    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, 2 * ny, st)) return -1;
+    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, 2 * ny, st)) return -1;
     return 0;
 }
 
@@ -305,6 +376,8 @@ void op_destroy(FdfdOp* op) {
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
     if (op->io_buf) cudaFree(op->io_buf);
+    cudaFree(op->ax); cudaFree(op->ay);
+    if (op->comm_stream) { cudaStreamDestroy(op->comm_stream); cudaEventDestroy(op->ev_in); cudaEventDestroy(op->ev_halo); }
     if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
     cudaStreamDestroy(op->stream);
     delete op;
@@ -351,36 +424,72 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     return 0;
 }
 
-static int slab_prepare(const FdfdOp* op, const cplx* d_x, int nvec) {
+// Row ranges one stencil application is launched over.  Whole grid: one range.  Slab on several ranks: the
+// halo exchange runs on the operator's communication stream WHILE the rows that do not touch a halo are
+// computed; the first and last owned row follow once the halos have landed.
+struct RowPlan {
+    int nranges;
+    int r0[3], r1[3];
+    bool wait_halo_before[3];
+};
+
+static int slab_begin(const FdfdOp* op, const cplx* d_x, int nvec, RowPlan* plan) {
+    plan->nranges = 1;
+    plan->r0[0] = op->halo; plan->r1[0] = op->nx - op->halo; plan->wait_halo_before[0] = false;
     if (!op->halo) return 0;
     if (nvec != 1) FDFD_FAIL("slab operators apply one vector at a time");
-    return op_halo_exchange(op, const_cast<cplx*>(d_x));
+    cplx* x = const_cast<cplx*>(d_x);
+    const bool overlap = op->comm && op->comm->world > 1 && op->comm_stream && op->nx - 2 >= 3;
+    if (!overlap) return op_halo_exchange(op, x, op->stream);
+    FDFD_CHECK(cudaEventRecord(op->ev_in, op->stream));
+    FDFD_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_in, 0));
+    if (op_halo_exchange(op, x, op->comm_stream)) return -1;
+    FDFD_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
+    plan->nranges = 3;
+    plan->r0[0] = 2; plan->r1[0] = op->nx - 2; plan->wait_halo_before[0] = false;
+    plan->r0[1] = 1; plan->r1[1] = 2; plan->wait_halo_before[1] = true;
+    plan->r0[2] = op->nx - 2; plan->r1[2] = op->nx - 1; plan->wait_halo_before[2] = false;
+    return 0;
+}
+
+template <bool RESID>
+static int launch_planes(const FdfdOp* op, const cplx* d_x, const cplx* d_b, cplx* d_y, int nvec) {
+    RowPlan plan;
+    if (slab_begin(op, d_x, nvec, &plan)) return -1;
+    for (int i = 0; i < plan.nranges; ++i) {
+        if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+        dim3 grid(ceil_div((size_t)(plan.r1[i] - plan.r0[i]) * op->ny, 256), nvec);
+        stencil_planes_kernel<RESID><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_y, op->nx, op->ny, plan.r0[i],
+                                                                  plan.r1[i]);
+        ++g_fdfd_launches;
+    }
+    FDFD_CHECK(cudaGetLastError());
+    return 0;
 }
 
 int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
-    if (slab_prepare(op, d_x, nvec)) return -1;
-    dim3 grid(ceil_div(op->n() - 2 * (size_t)op->halo * op->ny, 256), nvec);
-    { stencil_planes_kernel<false><<<grid, 256, 0, op->stream>>>(op->planes, d_x, nullptr, d_y, op->nx, op->ny, op->halo); ++g_fdfd_launches; }
-    FDFD_CHECK(cudaGetLastError());
-    return 0;
+    return launch_planes<false>(op, d_x, nullptr, d_y, nvec);
 }
 
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
-    if (slab_prepare(op, d_x, nvec)) return -1;
-    dim3 grid(ceil_div(op->n() - 2 * (size_t)op->halo * op->ny, 256), nvec);
-    { stencil_planes_kernel<true><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_r, op->nx, op->ny, op->halo); ++g_fdfd_launches; }
-    FDFD_CHECK(cudaGetLastError());
-    return 0;
+    return launch_planes<true>(op, d_x, d_b, d_r, nvec);
 }
 
 int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
     if (op->pol != 0) return op_apply_planes(op, d_x, d_y, nvec);
-    if (slab_prepare(op, d_x, nvec)) return -1;
+    RowPlan plan;
+    if (slab_begin(op, d_x, nvec, &plan)) return -1;
     AsmParams p = make_params(op);
-    dim3 grid(ceil_div(op->ny, 128), ceil_div(op->nx - 2 * op->halo, FUSED_ROWS), nvec);
-    { stencil_fused_ez_kernel<<<grid, 128, 0, op->stream>>>(
-        op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, d_x, d_y,
-        op->nx, op->ny, 1.0 / (p.m0 * p.dx * p.dx), 1.0 / (p.m0 * p.dy * p.dy), p.omega * p.omega * p.e0, op->halo); ++g_fdfd_launches; }
+    const int rows = g_fused_rows;
+    auto kern = rows == 8 ? stencil_fused_ez_kernel<8> : rows == 2 ? stencil_fused_ez_kernel<2> : stencil_fused_ez_kernel<4>;
+    for (int i = 0; i < plan.nranges; ++i) {
+        if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+        dim3 grid(ceil_div(op->ny, 128), ceil_div(plan.r1[i] - plan.r0[i], rows), nvec);
+        kern<<<grid, 128, 0, op->stream>>>(op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->ax, op->ax + op->nx, op->ay,
+                                           op->ay + op->ny, d_x, d_y, op->nx, op->ny, p.omega * p.omega * p.e0,
+                                           plan.r0[i], plan.r1[i]);
+        ++g_fdfd_launches;
+    }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }

@@ -18,6 +18,8 @@ struct FdfdOp {
     cudaEvent_t ev0, ev1;   // fdfd_timer_start/stop
     // 1-D inverse stretch factors 1/s (pml.py:63-76), device
     cplx *isxf, *isxb, *isyf, *isyb;
+    // coupling tables of the matrix-free Ez stencil: ax = [axm(nx) | axp(nx)], ay = [aym(ny) | ayp(ny)]
+    cplx *ax, *ay;
     // permittivity planes (device, nx*ny complex128)
     cplx *eps_r, *eps_nl;
     // five stencil planes c0,cxm,cxp,cym,cyp (device, 5*nx*ny)
@@ -28,6 +30,8 @@ struct FdfdOp {
     // side, every vector has that extended layout, the stencil only writes rows 1..nx-2 and the halo rows of
     // its input are filled from the neighbouring ranks (periodic in the rank index) before it runs
     int halo, gnx, x0;
+    cudaStream_t comm_stream;        // halo exchange runs here, overlapped with the interior rows
+    cudaEvent_t ev_in, ev_halo;
     FdfdComm* comm;     // not owned; null with halo = 1 means a single slab wrapping onto itself
     size_t n() const { return (size_t)nx * ny; }
 };
@@ -39,7 +43,7 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
                    int npml_x, int npml_y, int pol, double L0);
 void op_destroy(FdfdOp* op);
 // fills the two halo rows of an extended-layout vector from the neighbouring slabs
-int op_halo_exchange(const FdfdOp* op, cplx* d_x_ext);
+int op_halo_exchange(const FdfdOp* op, cplx* d_x_ext, cudaStream_t st);
 // eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes
 int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging);
 // y = A x using the stored planes (any polarisation, nonlinearity included); nvec vectors back to back

@@ -175,6 +175,8 @@ int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl,
 int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, int N, int K, int batch,
                             int mode, int transb, int lower);
 
+/* rows each thread of the fused Ez stencil marches (2, 4, 8): A/B measurements */
+int fdfd_stencil_set_variant(int rows_per_thread);
 /* kernel selection for A/B measurements: 0 = persistent kernel for large problems (default), 1 = tiled only */
 int fdfd_zgemm_set_variant(int v);
 /* 1 (default): levels of tiny fronts (k <= 32) run as one fused kernel each; 0: generic path everywhere */
