@@ -16,9 +16,14 @@ _plan_cache = {}
 
 
 def get_plan(nx, ny):
-    key = (int(nx), int(ny))
+    """Elimination plan of an nx x ny grid (cached).  FDFD_SPLIT_MIN / FDFD_SPLIT_PARTS override the separator
+    splitting of ndplan.build_plan for A/B measurements."""
+    import os
+    sm, sp = os.environ.get("FDFD_SPLIT_MIN"), os.environ.get("FDFD_SPLIT_PARTS")
+    key = (int(nx), int(ny), sm, sp)
     if key not in _plan_cache:
-        _plan_cache[key] = build_plan(*key)
+        _plan_cache[key] = build_plan(int(nx), int(ny), split_min=int(sm) if sm else None,
+                                      split_parts=int(sp) if sp else None)
     return _plan_cache[key]
 
 

@@ -22,6 +22,17 @@ This module is pure index bookkeeping (numpy, no arithmetic on field values).
 import numpy as np
 
 WMIN = 3          # smallest leaf interval (cells); leaves are WMIN..2*WMIN-1 cells wide
+SPLIT_MIN = 1000  # separators with at least this many nodes are eliminated in several steps
+SPLIT_PARTS = -512   # > 0: that many steps; < 0: pieces of about -SPLIT_PARTS nodes (at most 8 steps)
+
+
+def _parts(k, p):
+    """Cut points of k items into p nearly equal consecutive pieces: [s_0=0, s_1, ..., s_p=k]."""
+    base, extra = divmod(k, p)
+    cuts = [0]
+    for i in range(p):
+        cuts.append(cuts[-1] + base + (1 if i < extra else 0))
+    return cuts
 
 
 def _halve(n, depth):
@@ -64,8 +75,17 @@ class Level:
     pass
 
 
-def build_plan(nx, ny, wmin=WMIN):
-    """Return the list of levels, leaves first, root last."""
+def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
+    """Return the list of levels, leaves first, root last.
+
+    A merge whose separator has >= split_min nodes is emitted as a CHAIN of levels that eliminate the
+    separator piece by piece (first level: the merge proper, eliminating piece 0 with the rest of the
+    separator kept in the ring; then ``chain`` levels with a single child each).  Eliminating a block of k
+    nodes in p pieces is blocked LDL^T in disguise: the explicit inverse of the whole k x k block and the
+    full m x k coupling product are never formed (k^3/2 -> ~k^3/6 (1 + 1/p ...), m k^2 -> m k^2 (p+1)/2p),
+    while the solve phase still streams plain matrix-vector products."""
+    split_min = SPLIT_MIN if split_min is None else split_min
+    split_parts = SPLIT_PARTS if split_parts is None else split_parts
     ax, ay = _depth_for(nx, wmin), _depth_for(ny, wmin)
     levels = []
 
@@ -179,20 +199,44 @@ def build_plan(nx, ny, wmin=WMIN):
             elim = sorted(union - pset)
             fronts.append((elim, pring, p1, p2))
             new_rings[(pw, ph)] = pring
-        lv.k_cls = np.array([len(f[0]) for f in fronts], dtype=np.int32)
-        lv.m_cls = np.array([len(f[1]) for f in fronts], dtype=np.int32)
-        lv.kmax, lv.mmax = int(lv.k_cls.max()), int(lv.m_cls.max())
-        lv.nmax = lv.kmax + lv.mmax
+        kfull = max(len(f[0]) for f in fronts)
+        want = split_parts if split_parts > 0 else max(1, min(8, int(round(kfull / float(-split_parts)))))
+        nparts = want if (want > 1 and kfull >= split_min and min(len(f[0]) for f in fronts) >= want) else 1
+        cuts = [_parts(len(f[0]), nparts) for f in fronts]              # per class
         child_mmax = levels[-1].mmax
-        lv.child_mmax = child_mmax
-        lv.c1map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
-        lv.c2map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
-        for c, (elim, pring, p1, p2) in enumerate(fronts):
-            pos = {p: i for i, p in enumerate(elim)}
-            pos.update({p: lv.kmax + i for i, p in enumerate(pring)})
-            lv.c1map[c, :len(p1)] = [pos[p] for p in p1]
-            lv.c2map[c, :len(p2)] = [pos[p] for p in p2]
-        levels.append(lv)
+        for part in range(nparts):
+            if part > 0:
+                prev = lv
+                lv = Level()
+                lv.kind = "merge"
+                lv.chain = True
+                lv.axis = axis
+                lv.px, lv.py, lv.nb = prev.px, prev.py, prev.nb
+                lv.cls, lv.ncls = prev.cls, prev.ncls
+                lv.ch1 = np.arange(lv.nb, dtype=np.int32)
+                lv.ch2 = lv.ch1
+                child_mmax = prev.mmax
+            else:
+                lv.chain = False
+            els = [f[0][cuts[c][part]:cuts[c][part + 1]] for c, f in enumerate(fronts)]       # eliminated now
+            rings = [f[0][cuts[c][part + 1]:] + f[1] for c, f in enumerate(fronts)]            # kept for later
+            lv.k_cls = np.array([len(e) for e in els], dtype=np.int32)
+            lv.m_cls = np.array([len(r) for r in rings], dtype=np.int32)
+            lv.kmax, lv.mmax = int(lv.k_cls.max()), int(lv.m_cls.max())
+            lv.nmax = lv.kmax + lv.mmax
+            lv.child_mmax = child_mmax
+            lv.c1map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
+            lv.c2map = np.full((lv.ncls, max(child_mmax, 1)), -1, dtype=np.int32)
+            for c, (elim, pring, p1, p2) in enumerate(fronts):
+                pos = {p: i for i, p in enumerate(els[c])}
+                pos.update({p: lv.kmax + i for i, p in enumerate(rings[c])})
+                if part == 0:
+                    lv.c1map[c, :len(p1)] = [pos[p] for p in p1]
+                    lv.c2map[c, :len(p2)] = [pos[p] for p in p2]
+                else:                                        # single child: the previous step's ring
+                    cring = elim[cuts[c][part]:] + pring
+                    lv.c1map[c, :len(cring)] = [pos[p] for p in cring]
+            levels.append(lv)
         cur_rings = new_rings
         cur_xs, cur_ys = new_xs, new_ys
         xclosed, yclosed = new_xclosed, new_yclosed
@@ -226,7 +270,7 @@ def shard_plan(levels, world, rank):
     if world < 1 or world & (world - 1):
         raise ValueError("world size must be a power of two, got {}".format(world))
     nlev = len(levels)
-    if world > 1 and (nlev < 2 or levels[0].nb < world or world > (1 << (nlev - 1))):
+    if world > 1 and (nlev < 2 or levels[0].nb < world):
         raise ValueError("grid too small to split over {} ranks".format(world))
     owner = [None] * nlev
     group = [1] * nlev
@@ -235,6 +279,10 @@ def shard_plan(levels, world, rank):
     for l in range(nlev - 1, 0, -1):
         lv, g = levels[l], group[l]
         child = np.empty(levels[l - 1].nb, dtype=np.int64)
+        if getattr(lv, "chain", False):              # same front, next piece of its separator: same owner
+            child[lv.ch1] = owner[l]
+            owner[l - 1], group[l - 1] = child, g
+            continue
         child[lv.ch1] = owner[l]
         child[lv.ch2] = owner[l] + (g // 2 if g > 1 else 0)
         owner[l - 1], group[l - 1] = child, max(g // 2, 1)
@@ -255,7 +303,9 @@ def shard_plan(levels, world, rank):
             nl.x0, nl.y0 = lv.x0[mine], lv.y0[mine]
         else:
             nl.ch1 = loc_prev[lv.ch1[mine]].astype(np.int32)
-            if g > 1:
+            if getattr(lv, "chain", False):
+                nl.ch2 = nl.ch1
+            elif g > 1:
                 assert nl.nb <= 1
                 nl.ch2 = np.ones(nl.nb, dtype=np.int32)        # the slot after the single local child
                 if nl.nb == 1:

@@ -44,6 +44,8 @@ for n in sizes:
     op.lib.fdfd_phase_timing(0)
     print("   per level ms (" + " ".join(names) + "):")
     for li, lv in enumerate(d.levels):
+        if os.environ.get("DIAG_BRIEF") and li < len(d.levels) - 14:
+            continue
         print(f"   L{li:02d} nb={lv.nb:8d} k={lv.kmax:5d} m={lv.mmax:5d} | " + " ".join(f"{v:7.2f}" for v in pl[li]) +
               f" | sum {pl[li].sum():8.2f}", flush=True)
     print("   totals: " + " ".join(f"{k}={v:.1f}" for k, v in zip(names, pl.sum(0))), flush=True)
