@@ -681,6 +681,8 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->fws = nullptr;
     s->fws_cap = 0;
     s->comm = nullptr;
+    s->ws_refine = nullptr;
+    s->ws_refine_cap = 0;
     s->xchg = nullptr;
     s->xchg_cap = 0;
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
@@ -746,6 +748,7 @@ void nd_destroy(NdSolver* s) {
     cudaFree(s->d_info);
     if (s->fws) cudaFree(s->fws);
     if (s->xchg) cudaFree(s->xchg);
+    if (s->ws_refine) cudaFree(s->ws_refine);
     delete s;
 }
 

@@ -48,6 +48,8 @@ struct NdSolver {
     // solve workspace (grown on demand)
     cplx *ws_a, *ws_b, *ws_ring_a, *ws_ring_b, *ws_ye;
     size_t ws_vec_cap, ws_ring_cap, ws_ye_cap;
+    cplx* ws_refine;                  // iterative-refinement residual / correction vectors
+    size_t ws_refine_cap;
     // sharded tree: communicator (not owned) and the packed Schur block in flight between two ranks
     FdfdComm* comm;
     cplx* xchg;

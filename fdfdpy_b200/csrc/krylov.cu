@@ -320,9 +320,16 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
                  double* relres_out, int* steps_out) {
     const size_t n = op->n();
     cudaStream_t st = op->stream;
-    Scratch ws;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (2 * n * nrhs + RED_BLOCKS + 2)));
-    cplx *r = ws.base, *d = r + n * nrhs, *partial = d + n * nrhs, *sc = partial + RED_BLOCKS;
+    // residual / correction vectors live in the solver handle (grown on demand, never freed per call)
+    const size_t need = 2 * n * nrhs + RED_BLOCKS + 2;
+    if (need > nd->ws_refine_cap) {
+        if (nd->ws_refine) cudaFree(nd->ws_refine);
+        nd->ws_refine = nullptr;
+        nd->ws_refine_cap = 0;
+        FDFD_CHECK(cudaMalloc(&nd->ws_refine, sizeof(cplx) * need));
+        nd->ws_refine_cap = need;
+    }
+    cplx *r = nd->ws_refine, *d = r + n * nrhs, *partial = d + n * nrhs, *sc = partial + RED_BLOCKS;
     std::vector<double> bn(nrhs);
     cplx h;
     for (int j = 0; j < nrhs; ++j) {
