@@ -87,9 +87,15 @@ SIGNATURES = {
                                          _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                         _vp, C.c_int, _ip, _dp, _ip]),
+    "fdfd_op_apply_host_c64": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "fdfd_op_apply_dev_c64": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "fdfd_krylov_solve_host_c64": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _ip, _dp,
+                                             _ip]),
+    "fdfd_krylov_solve_dev_c64": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _ip, _dp,
+                                            _ip]),
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int]),
-    "fdfd_stencil_set_variant": (C.c_int, [C.c_int]),
+    "fdfd_stencil_set_variant": (C.c_int, [C.c_int, C.c_int]),
     "fdfd_zgemm_set_variant": (C.c_int, [C.c_int]),
     "fdfd_direct_set_small_fronts": (C.c_int, [C.c_int]),
     "fdfd_zgemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
@@ -156,6 +162,8 @@ def as_i32(a):
 # copy runs at full PCIe rate and skips the first-touch page faults of a fresh np.empty.  A buffer
 # returns to the free list when the last array viewing it is garbage collected, so an optimisation
 # loop that overwrites its fields every iteration keeps re-using the same few buffers.
+PINNED_RESULTS = True               # False: plain numpy result arrays (a program that KEEPS every result pays
+#                                     ~0.13 s per 268 MB to page-lock a fresh buffer; recycled buffers are free)
 PINNED_MIN_BYTES = 1 << 20          # smaller arrays are ordinary numpy memory
 PINNED_KEEP_BYTES = 8 << 30         # free-list cap; beyond it released buffers go back to the driver
 _pool_lock = threading.Lock()
@@ -182,7 +190,7 @@ def pinned_empty(shape, dtype=c128):
     global _pool_free_bytes
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-    if nbytes < PINNED_MIN_BYTES:
+    if nbytes < PINNED_MIN_BYTES or not PINNED_RESULTS:
         return np.empty(shape, dtype=dtype)
     lib = load()
     addr = None

@@ -81,6 +81,13 @@ class MaxwellOperator:
 
     # ---- matrix-like surface
     def dot(self, x, fused=False):
+        if np.asarray(x).dtype == np.complex64:          # complex64 storage, fp64 arithmetic
+            x = np.ascontiguousarray(x)
+            if x.size != self.nx * self.ny:
+                raise ValueError("complex64 apply takes one vector")
+            y = np.empty_like(x)
+            check(self.lib.fdfd_op_apply_host_c64(self.h, ptr(x), ptr(y), int(fused and self.pol == "Ez")))
+            return y
         x = as_c128(x)
         nvec = x.size // (self.nx * self.ny)
         y = pinned_empty(x.shape)
@@ -131,7 +138,18 @@ class MaxwellOperator:
     def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10,
                precondition=False, c12=None, real_inner=False):
         """Krylov solve of A x (+ c12 conj(x)) = b.  ``precondition=True`` uses whatever factorisation
-        the direct-solver handle currently caches (it may belong to a nearby operator)."""
+        the direct-solver handle currently caches (it may belong to a nearby operator).
+        A complex64 ``b`` selects complex64 vector storage (fp64 arithmetic and scalars)."""
+        if np.asarray(b).dtype == np.complex64:
+            if precondition or c12 is not None:
+                raise ValueError("the complex64 solver takes neither a preconditioner nor an anti-linear term")
+            b = np.ascontiguousarray(b)
+            x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, dtype=np.complex64).copy()
+            it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+            check(self.lib.fdfd_krylov_solve_host_c64(self.h, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
+                                                      float(tol), int(maxiter), int(fused and self.pol == "Ez"),
+                                                      int(check_every), C.byref(it), C.byref(rr), C.byref(conv)))
+            return x.reshape(b.shape), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
         b = as_c128(b)
         x = np.zeros_like(b) if x0 is None else as_c128(x0).copy()
         it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)

@@ -405,6 +405,56 @@ int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b, d
     return 0;
 }
 
+/* ---- complex64 storage (fp64 arithmetic): stencil and Krylov loop ---- */
+int fdfd_op_apply_dev_c64(fdfd_op* op, const void* d_x, void* d_y, int fused) {
+    return fused ? op_apply_fused_t<cplx32>(op, (const cplx32*)d_x, (cplx32*)d_y, 1)
+                 : op_apply_planes_t<cplx32>(op, (const cplx32*)d_x, (cplx32*)d_y, 1);
+}
+int fdfd_op_apply_host_c64(fdfd_op* op, const float* x, float* y, int fused) {
+    size_t cnt = op->n();
+    cplx32 *dx = nullptr, *dy = nullptr;
+    FDFD_CHECK(cudaMalloc(&dx, sizeof(cplx32) * cnt));
+    FDFD_CHECK(cudaMalloc(&dy, sizeof(cplx32) * cnt));
+    int rc = 0;
+    if (cudaMemcpyAsync(dx, x, sizeof(cplx32) * cnt, cudaMemcpyHostToDevice, op->stream) != cudaSuccess) rc = -1;
+    if (!rc && cudaMemsetAsync(dy, 0, sizeof(cplx32) * cnt, op->stream) != cudaSuccess) rc = -1;
+    if (!rc) rc = fdfd_op_apply_dev_c64(op, dx, dy, fused);
+    if (!rc && cudaMemcpyAsync(y, dy, sizeof(cplx32) * cnt, cudaMemcpyDeviceToHost, op->stream) != cudaSuccess) rc = -1;
+    if (cudaStreamSynchronize(op->stream) != cudaSuccess) rc = -1;
+    cudaFree(dx); cudaFree(dy);
+    if (rc && !g_fdfd_err[0]) snprintf(g_fdfd_err, sizeof(g_fdfd_err), "complex64 apply failed");
+    return rc;
+}
+int fdfd_krylov_solve_dev_c64(fdfd_op* op, const void* d_b, void* d_x, int method, double tol, int maxiter, int fused,
+                              int check_every, int* iters, double* relres, int* converged) {
+    KrylovResult r;
+    int rc;
+    if (method == 0) rc = krylov_bicgstab_c64(op, (const cplx32*)d_b, (cplx32*)d_x, tol, maxiter, fused, check_every, &r);
+    else if (method == 1) rc = krylov_cocg_c64(op, (const cplx32*)d_b, (cplx32*)d_x, tol, maxiter, fused, check_every, &r);
+    else FDFD_FAIL("unknown Krylov method %d", method);
+    if (rc) return -1;
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    if (iters) *iters = r.iters;
+    if (relres) *relres = r.relres;
+    if (converged) *converged = r.converged;
+    return 0;
+}
+int fdfd_krylov_solve_host_c64(fdfd_op* op, const float* b, float* x, int method, double tol, int maxiter, int fused,
+                               int check_every, int* iters, double* relres, int* converged) {
+    size_t n = op->n();
+    cplx32 *db = nullptr, *dx = nullptr;
+    FDFD_CHECK(cudaMalloc(&db, sizeof(cplx32) * n));
+    FDFD_CHECK(cudaMalloc(&dx, sizeof(cplx32) * n));
+    int rc = 0;
+    if (cudaMemcpyAsync(db, b, sizeof(cplx32) * n, cudaMemcpyHostToDevice, op->stream) != cudaSuccess) rc = -1;
+    if (!rc && cudaMemcpyAsync(dx, x, sizeof(cplx32) * n, cudaMemcpyHostToDevice, op->stream) != cudaSuccess) rc = -1;
+    if (!rc) rc = fdfd_krylov_solve_dev_c64(op, db, dx, method, tol, maxiter, fused, check_every, iters, relres, converged);
+    if (!rc && cudaMemcpy(x, dx, sizeof(cplx32) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+    cudaFree(db); cudaFree(dx);
+    if (rc && !g_fdfd_err[0]) snprintf(g_fdfd_err, sizeof(g_fdfd_err), "complex64 Krylov solve failed");
+    return rc;
+}
+
 int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M, int N, int K, int batch, int mode,
                             int transb, int lower) {
     // test hook: C[b] = A[b] op(B[b]) (mode 0) or C[b] -= A[b] op(B[b]) (mode 1), dense row-major, packed batches
@@ -423,10 +473,11 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
     return 0;
 }
 
-extern int g_fused_rows;
-int fdfd_stencil_set_variant(int rows_per_thread) {
+extern int g_fused_rows, g_fused_rows32;
+int fdfd_stencil_set_variant(int rows_per_thread, int complex64) {
     if (rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8) FDFD_FAIL("rows per thread: 2, 4 or 8");
-    g_fused_rows = rows_per_thread;
+    if (complex64) g_fused_rows32 = rows_per_thread;
+    else g_fused_rows = rows_per_thread;
     return 0;
 }
 int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }

@@ -59,6 +59,13 @@ __host__ __device__ __forceinline__ cplx crecip(cplx b) { return cdiv(make_doubl
 
 __device__ __forceinline__ cplx ldg_c(const cplx* p) { return __ldg(p); }
 
+// Field vectors are stored as complex128 (cplx) or complex64 (cplx32); arithmetic is always fp64.
+typedef float2 cplx32;
+__device__ __forceinline__ cplx vload(const cplx* p) { return __ldg(p); }
+__device__ __forceinline__ cplx vload(const cplx32* p) { float2 v = __ldg(p); return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ void vstore(cplx* p, cplx v) { *p = v; }
+__device__ __forceinline__ void vstore(cplx32* p, cplx v) { *p = make_float2((float)v.x, (float)v.y); }
+
 // ---- optional live phase timing (CUDA events on the launching stream), read by bench.py ----
 enum FdfdPhase { PH_ASSEMBLE = 0, PH_PIVOT, PH_PANEL, PH_ROWGEMM, PH_COPY, PH_UPDATE, PH_EXTRACT, PH_SOLVE_FWD,
                  PH_SOLVE_BWD, PH_STENCIL, PH_GGEMM, PH_SCHUR, PH_SMALL, PH_COUNT };

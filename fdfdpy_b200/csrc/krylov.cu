@@ -1,132 +1,221 @@
 // Krylov drivers on top of the matrix-free stencil: BiCGSTAB (optionally right-preconditioned by
 // the cached direct factorisation), COCG on the symmetrised operator, and iterative refinement.
-// All iteration scalars live on the device; the host only enqueues kernels and looks at the
-// residual norm every `check_every` iterations.
+//
+// * All iteration scalars live on the device; the host only enqueues kernels and looks at the residual
+//   norm every `check_every` iterations.
+// * Vector updates and the inner products that follow them are FUSED: x/r update + (r0.r, r.r) in one
+//   pass, (t.s, t.t) in one pass, scalar recurrences folded into the last reduction stage.  Reductions are
+//   warp shuffles -> one partial per CTA -> one finishing CTA (fixed order: deterministic).
+// * Vectors are stored as complex128 or complex64 (template parameter V); arithmetic, inner products and
+//   the iteration scalars are fp64 in both cases.
+// * Slab operators (one grid over several GPUs): the partial sums are all-reduced on the device between the
+//   two reduction stages, halo rows are exchanged inside the stencil application.
 #include <algorithm>
+#include <type_traits>
 #include "krylov.cuh"
 
-#define RED_BLOCKS 592   // 148 SMs x 4
+#define RED_BLOCKS 1184   // 148 SMs x 8
 #define RED_THREADS 256
 
-template <bool CONJ_A>
-__global__ void __launch_bounds__(RED_THREADS)
-dot_partial_kernel(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, cplx* __restrict__ partial) {
-    __shared__ double sx[RED_THREADS / 32], sy[RED_THREADS / 32];
-    double ax = 0.0, ay = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        cplx u = a[i], v = b[i];
-        if (CONJ_A) u.y = -u.y;
-        ax += u.x * v.x - u.y * v.y;
-        ay += u.x * v.y + u.y * v.x;
-    }
+// scalar slots
+enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_R0V, S_TS, S_TT, S_RR, S_PQ, S_TMP0, S_TMP1, S_COUNT };
+// what the finishing stage of a reduction does with its sums (a, b)
+enum { POST_STORE = 0,      // sc[o0] = a (; sc[o1] = b)
+       POST_BICG_ALPHA,     // R0V = a; ALPHA = RHO / R0V
+       POST_BICG_OMEGA,     // TS = a, TT = b; OMEGA = TS / TT
+       POST_BICG_RHO,       // RHO_OLD = RHO; RHO = a; RR = b; BETA = (RHO / RHO_OLD) (ALPHA / OMEGA)
+       POST_COCG_ALPHA,     // PQ = a; ALPHA = RHO / PQ
+       POST_COCG_BETA };    // BETA = a / RHO; RHO = a; RR = b
+
+__device__ __forceinline__ void block_reduce2(cplx& a, cplx& b) {
+    __shared__ double sh[4][RED_THREADS / 32];
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        ax += __shfl_down_sync(0xffffffffu, ax, o);
-        ay += __shfl_down_sync(0xffffffffu, ay, o);
+        a.x += __shfl_down_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_down_sync(0xffffffffu, a.y, o);
+        b.x += __shfl_down_sync(0xffffffffu, b.x, o);
+        b.y += __shfl_down_sync(0xffffffffu, b.y, o);
     }
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sx[w] = ax; sy[w] = ay; }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a.x; sh[1][w] = a.y; sh[2][w] = b.x; sh[3][w] = b.y; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double tx = 0, ty = 0;
-        for (int i = 0; i < RED_THREADS / 32; ++i) { tx += sx[i]; ty += sy[i]; }
-        partial[blockIdx.x] = make_double2(tx, ty);
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        for (int i = 0; i < RED_THREADS / 32; ++i) { t0 += sh[0][i]; t1 += sh[1][i]; t2 += sh[2][i]; t3 += sh[3][i]; }
+        a = make_double2(t0, t1);
+        b = make_double2(t2, t3);
     }
 }
 
+__device__ __forceinline__ void dot_acc(cplx& acc, cplx u, cplx v, bool conj_u) {
+    if (conj_u) u.y = -u.y;
+    acc.x += u.x * v.x - u.y * v.y;
+    acc.y += u.x * v.y + u.y * v.x;
+}
+
+// partial[2 * blk] = sum op(a1) b1,  partial[2 * blk + 1] = sum op(a2) b2  (second pair optional)
+template <class V>
 __global__ void __launch_bounds__(RED_THREADS)
-dot_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__ out, int real_only) {
-    __shared__ double sx[RED_THREADS], sy[RED_THREADS];
-    double ax = 0, ay = 0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) { ax += partial[i].x; ay += partial[i].y; }
-    sx[threadIdx.x] = ax; sy[threadIdx.x] = ay;
-    __syncthreads();
-    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { sx[threadIdx.x] += sx[threadIdx.x + s]; sy[threadIdx.x] += sy[threadIdx.x + s]; }
-        __syncthreads();
+dot2_partial_kernel(const V* __restrict__ a1, const V* __restrict__ b1, const V* __restrict__ a2,
+                    const V* __restrict__ b2, size_t n, int conj1, int conj2, cplx* __restrict__ partial) {
+    cplx s1 = make_double2(0.0, 0.0), s2 = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cplx u = vload(a1 + i), v = (b1 == a1) ? u : vload(b1 + i);
+        dot_acc(s1, u, v, conj1);
+        if (a2) {
+            cplx p = (a2 == a1) ? u : ((a2 == b1) ? v : vload(a2 + i));
+            cplx q = (b2 == a1) ? u : ((b2 == b1) ? v : vload(b2 + i));
+            dot_acc(s2, p, q, conj2);
+        }
     }
-    if (threadIdx.x == 0) *out = make_double2(sx[0], real_only ? 0.0 : sy[0]);
+    block_reduce2(s1, s2);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s1; partial[2 * blockIdx.x + 1] = s2; }
 }
 
-int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
-            int real_only, FdfdComm* comm) {
-    if (conj_a) { dot_partial_kernel<true><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
-    else { dot_partial_kernel<false><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a, b, n, partial); ++g_fdfd_launches; }
-    { dot_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, out, real_only); ++g_fdfd_launches; }
+__device__ __forceinline__ void post_op(cplx* sc, int post, int o0, int o1, cplx a, cplx b) {
+    switch (post) {
+    case POST_STORE: sc[o0] = a; if (o1 >= 0) sc[o1] = b; break;
+    case POST_BICG_ALPHA: sc[S_R0V] = a; sc[S_ALPHA] = cdiv(sc[S_RHO], a); break;
+    case POST_BICG_OMEGA: sc[S_TS] = a; sc[S_TT] = b; sc[S_OMEGA] = cdiv(a, b); break;
+    case POST_BICG_RHO: {
+        cplx rho_old = sc[S_RHO];
+        sc[S_RHO_OLD] = rho_old; sc[S_RHO] = a; sc[S_RR] = b;
+        sc[S_BETA] = cmul(cdiv(a, rho_old), cdiv(sc[S_ALPHA], sc[S_OMEGA]));
+        break;
+    }
+    case POST_COCG_ALPHA: sc[S_PQ] = a; sc[S_ALPHA] = cdiv(sc[S_RHO], a); break;
+    case POST_COCG_BETA: sc[S_BETA] = cdiv(a, sc[S_RHO]); sc[S_RHO] = a; sc[S_RR] = b; break;
+    }
+}
+
+// finishing stage: sums the per-CTA partials; post >= 0 applies the scalar recurrence right away,
+// post < 0 leaves the two sums in sc[S_TMP0..1] (they are all-reduced over the ranks first)
+__global__ void __launch_bounds__(RED_THREADS)
+dot2_final_kernel(const cplx* __restrict__ partial, int count, cplx* __restrict__ sc, int post, int o0, int o1,
+                  int real1, int real2) {
+    cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < count; i += blockDim.x) { a = cadd(a, partial[2 * i]); b = cadd(b, partial[2 * i + 1]); }
+    block_reduce2(a, b);
+    if (threadIdx.x == 0) {
+        if (real1) a.y = 0.0;
+        if (real2) b.y = 0.0;
+        if (post < 0) { sc[S_TMP0] = a; sc[S_TMP1] = b; }
+        else post_op(sc, post, o0, o1, a, b);
+    }
+}
+__global__ void post_kernel(cplx* sc, int post, int o0, int o1) { post_op(sc, post, o0, o1, sc[S_TMP0], sc[S_TMP1]); }
+
+// second stage (+ all-reduce over the ranks of a slab operator) of a reduction whose partials are in place
+static int finish_dots(cudaStream_t st, cplx* partial, cplx* sc, int post, int o0, int o1, int real1, int real2,
+                       FdfdComm* comm) {
+    const bool dist = comm && comm->world > 1;
+    dot2_final_kernel<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, sc, dist ? -1 : post, o0, o1, real1, real2);
+    ++g_fdfd_launches;
+    if (dist) {
+        // the scalars are summed over the ranks on the same stream; they never visit the host
+        if (comm_allreduce_sum(comm, sc + S_TMP0, 4, st)) return -1;
+        post_kernel<<<1, 1, 0, st>>>(sc, post, o0, o1);
+        ++g_fdfd_launches;
+    }
     FDFD_CHECK(cudaGetLastError());
-    // slabs: the scalar is summed over the ranks on the same stream, it never visits the host
-    if (comm && comm->world > 1 && comm_allreduce_sum(comm, out, 2, st)) return -1;
     return 0;
 }
 
-// scalar slots
-enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_R0V, S_TS, S_TT, S_RR, S_PQ, S_COUNT };
-
-__global__ void bicg_beta_kernel(cplx* sc) {   // beta = (rho/rho_old) * (alpha/omega); rho_old = rho
-    cplx beta = cmul(cdiv(sc[S_RHO], sc[S_RHO_OLD]), cdiv(sc[S_ALPHA], sc[S_OMEGA]));
-    sc[S_BETA] = beta;
-    sc[S_RHO_OLD] = sc[S_RHO];
+template <class V>
+static int dots(cudaStream_t st, const V* a1, const V* b1, int conj1, const V* a2, const V* b2, int conj2, size_t n,
+                cplx* partial, cplx* sc, int post, int o0, int o1, int real_only, FdfdComm* comm) {
+    dot2_partial_kernel<V><<<RED_BLOCKS, RED_THREADS, 0, st>>>(a1, b1, a2, b2, n, conj1, conj2, partial);
+    ++g_fdfd_launches;
+    return finish_dots(st, partial, sc, post, o0, o1, real_only, real_only, comm);
 }
-__global__ void bicg_alpha_kernel(cplx* sc) { sc[S_ALPHA] = cdiv(sc[S_RHO], sc[S_R0V]); }
-__global__ void bicg_omega_kernel(cplx* sc) { sc[S_OMEGA] = cdiv(sc[S_TS], sc[S_TT]); }
-__global__ void cocg_alpha_kernel(cplx* sc) { sc[S_ALPHA] = cdiv(sc[S_RHO], sc[S_PQ]); }
-__global__ void cocg_beta_kernel(cplx* sc) {   // on entry S_RR holds the new r^T r
-    sc[S_BETA] = cdiv(sc[S_RR], sc[S_RHO]);
-    sc[S_RHO] = sc[S_RR];
+
+// one inner product into sc[0]; `partial` holds 2 * RED_BLOCKS entries, `sc` S_COUNT entries
+int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* sc,
+            int real_only, FdfdComm* comm) {
+    return dots<cplx>(st, a, b, conj_a, nullptr, nullptr, 0, n, partial, sc, POST_STORE, 0, -1, real_only, comm);
 }
 
 // p = r + beta (p - omega v)
-__global__ void bicg_p_kernel(cplx* __restrict__ p, const cplx* __restrict__ r, const cplx* __restrict__ v,
+template <class V>
+__global__ void bicg_p_kernel(V* __restrict__ p, const V* __restrict__ r, const V* __restrict__ v,
                               const cplx* __restrict__ sc, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     cplx beta = sc[S_BETA], om = sc[S_OMEGA];
-    cplx t = csub(p[i], cmul(om, v[i]));
-    p[i] = cadd(r[i], cmul(beta, t));
+    cplx t = csub(vload(p + i), cmul(om, vload(v + i)));
+    vstore(p + i, cadd(vload(r + i), cmul(beta, t)));
 }
 // s = r - alpha v
-__global__ void bicg_s_kernel(cplx* __restrict__ s, const cplx* __restrict__ r, const cplx* __restrict__ v,
+template <class V>
+__global__ void bicg_s_kernel(V* __restrict__ s, const V* __restrict__ r, const V* __restrict__ v,
                               const cplx* __restrict__ sc, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    s[i] = csub(r[i], cmul(sc[S_ALPHA], v[i]));
+    vstore(s + i, csub(vload(r + i), cmul(sc[S_ALPHA], vload(v + i))));
 }
-// x += alpha ph + omega sh ; r = s - omega t
-__global__ void bicg_xr_kernel(cplx* __restrict__ x, cplx* __restrict__ r, const cplx* __restrict__ ph,
-                               const cplx* __restrict__ sh, const cplx* __restrict__ s, const cplx* __restrict__ t,
-                               const cplx* __restrict__ sc, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cplx al = sc[S_ALPHA], om = sc[S_OMEGA];
-    cplx xv = x[i];
-    cfma(xv, al, ph[i]);
-    cfma(xv, om, sh[i]);
-    x[i] = xv;
-    r[i] = csub(s[i], cmul(om, t[i]));
+__device__ __forceinline__ cplx as_stored(cplx v, const cplx*) { return v; }
+__device__ __forceinline__ cplx as_stored(cplx v, const cplx32*) {
+    return make_double2((double)(float)v.x, (double)(float)v.y);
 }
-// x += alpha p ; r -= alpha q
-__global__ void cocg_xr_kernel(cplx* __restrict__ x, cplx* __restrict__ r, const cplx* __restrict__ p,
-                               const cplx* __restrict__ q, const cplx* __restrict__ sc, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cplx al = sc[S_ALPHA];
-    cplx xv = x[i];
-    cfma(xv, al, p[i]);
-    x[i] = xv;
-    r[i] = csub(r[i], cmul(al, q[i]));
+// x += alpha ph + omega sh ; r = s - omega t ; partial sums of conj(r0).r and conj(r).r of the NEW r
+template <class V>
+__global__ void __launch_bounds__(RED_THREADS)
+bicg_xr_dots_kernel(V* __restrict__ x, V* __restrict__ r, const V* __restrict__ ph, const V* __restrict__ sh,
+                    const V* __restrict__ s, const V* __restrict__ t, const V* __restrict__ r0,
+                    const cplx* __restrict__ sc, size_t n, cplx* __restrict__ partial) {
+    const cplx al = sc[S_ALPHA], om = sc[S_OMEGA];
+    cplx d1 = make_double2(0.0, 0.0), d2 = make_double2(0.0, 0.0);
+#pragma unroll 2
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cplx sv = vload(s + i);
+        cplx xv = vload(x + i);
+        cfma(xv, al, vload(ph + i));
+        cfma(xv, om, (sh == s) ? sv : vload(sh + i));
+        vstore(x + i, xv);
+        cplx rn = as_stored(csub(sv, cmul(om, vload(t + i))), r);   // inner products of the value as stored
+        vstore(r + i, rn);
+        dot_acc(d1, vload(r0 + i), rn, true);
+        dot_acc(d2, rn, rn, true);
+    }
+    block_reduce2(d1, d2);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = d1; partial[2 * blockIdx.x + 1] = d2; }
+}
+// x += alpha p ; r -= alpha q ; partial sums of r.r (unconjugated: COCG) and conj(r).r (norm) of the NEW r
+template <class V>
+__global__ void __launch_bounds__(RED_THREADS)
+cocg_xr_dots_kernel(V* __restrict__ x, V* __restrict__ r, const V* __restrict__ p, const V* __restrict__ q,
+                    const cplx* __restrict__ sc, size_t n, cplx* __restrict__ partial) {
+    const cplx al = sc[S_ALPHA];
+    cplx d1 = make_double2(0.0, 0.0), d2 = make_double2(0.0, 0.0);
+#pragma unroll 2
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cplx xv = vload(x + i);
+        cfma(xv, al, vload(p + i));
+        vstore(x + i, xv);
+        cplx rn = as_stored(csub(vload(r + i), cmul(al, vload(q + i))), r);
+        vstore(r + i, rn);
+        dot_acc(d1, rn, rn, false);
+        dot_acc(d2, rn, rn, true);
+    }
+    block_reduce2(d1, d2);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = d1; partial[2 * blockIdx.x + 1] = d2; }
 }
 // p = r + beta p
-__global__ void cocg_p_kernel(cplx* __restrict__ p, const cplx* __restrict__ r, const cplx* __restrict__ sc, size_t n) {
+template <class V>
+__global__ void cocg_p_kernel(V* __restrict__ p, const V* __restrict__ r, const cplx* __restrict__ sc, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    p[i] = cadd(r[i], cmul(sc[S_BETA], p[i]));
+    vstore(p + i, cadd(vload(r + i), cmul(sc[S_BETA], vload(p + i))));
 }
 // v[i] *= sxf[ix] * syf[iy]  = v / (isxf isyf): left scaling that makes A complex symmetric
-__global__ void sym_scale_kernel(cplx* __restrict__ v, const cplx* __restrict__ isxf, const cplx* __restrict__ isyf,
+template <class V>
+__global__ void sym_scale_kernel(V* __restrict__ v, const cplx* __restrict__ isxf, const cplx* __restrict__ isyf,
                                  int nx, int ny) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nx * ny) return;
     int ix = (int)(i / ny), iy = (int)(i % ny);
-    v[i] = cdiv(v[i], cmul(isxf[ix], isyf[iy]));
+    vstore(v + i, cdiv(vload(v + i), cmul(isxf[ix], isyf[iy])));
 }
 __global__ void axpy_one_kernel(cplx* __restrict__ x, const cplx* __restrict__ d, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,7 +223,7 @@ __global__ void axpy_one_kernel(cplx* __restrict__ x, const cplx* __restrict__ d
 }
 
 struct Scratch {
-    cplx* base = nullptr;
+    void* base = nullptr;
     ~Scratch() { if (base) cudaFree(base); }
 };
 
@@ -159,161 +248,180 @@ __global__ void conj_couple_kernel(cplx* __restrict__ y, const cplx* __restrict_
 static inline size_t kpad(const FdfdOp* op) { return op->halo ? (size_t)op->ny : 0; }
 static inline size_t kn(const FdfdOp* op) { return (size_t)(op->nx - 2 * op->halo) * op->ny; }
 
-static int apply_A(const FdfdOp* op, const cplx* x, cplx* y, int fused, const cplx* c12) {
-    const size_t pad = kpad(op);
-    if (fused ? op_apply_fused(op, x - pad, y - pad, 1) : op_apply_planes(op, x - pad, y - pad, 1)) return -1;
-    if (c12) {
-        { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), 0); ++g_fdfd_launches; }
-        FDFD_CHECK(cudaGetLastError());
-    }
+static int couple(const FdfdOp* op, cplx* y, const cplx* c12, const cplx* x, int subtract) {
+    { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(y, c12, x, op->n(), subtract); ++g_fdfd_launches; }
+    FDFD_CHECK(cudaGetLastError());
     return 0;
 }
+static int couple(const FdfdOp*, cplx32*, const cplx*, const cplx32*, int) { return 0; }   // rejected at entry
 
-static int residual_A(const FdfdOp* op, const cplx* b, const cplx* x, cplx* r, const cplx* c12) {
+template <class V>
+static int apply_A(const FdfdOp* op, const V* x, V* y, int fused, const cplx* c12) {
     const size_t pad = kpad(op);
-    if (op_residual(op, b - pad, x - pad, r - pad, 1)) return -1;
-    if (c12) {
-        { conj_couple_kernel<<<ceil_div(op->n(), 256), 256, 0, op->stream>>>(r, c12, x, op->n(), 1); ++g_fdfd_launches; }
-        FDFD_CHECK(cudaGetLastError());
-    }
-    return 0;
+    if (fused ? op_apply_fused_t<V>(op, x - pad, y - pad, 1) : op_apply_planes_t<V>(op, x - pad, y - pad, 1)) return -1;
+    return c12 ? couple(op, y, c12, x, 0) : 0;
 }
 
-int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
-                    int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
+template <class V>
+static int residual_A(const FdfdOp* op, const V* b, const V* x, V* r, const cplx* c12) {
+    const size_t pad = kpad(op);
+    if (op_residual_t<V>(op, b - pad, x - pad, r - pad, 1)) return -1;
+    return c12 ? couple(op, r, c12, x, 1) : 0;
+}
+
+static int precond_solve(NdSolver* nd, const FdfdOp* op, const cplx* in, cplx* out) { return nd_solve(nd, op, in, out, 1); }
+static int precond_solve(NdSolver*, const FdfdOp*, const cplx32*, cplx32*) { return 0; }   // rejected at entry
+
+template <class V>
+int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond, const V* d_b, V* d_x, double tol, int maxiter, int fused,
+                      int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
     const int RI = (real_inner || c12) ? 1 : 0;   // an R-linear operator needs the real inner product
     const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
     if (op->halo && (precond || c12)) FDFD_FAIL("slab operators take neither a preconditioner nor an anti-linear term");
+    if (!std::is_same<V, cplx>::value && (precond || c12))
+        FDFD_FAIL("the complex64 solver takes neither a preconditioner nor an anti-linear term");
     FdfdComm* comm = op->comm;
     d_b += pad; d_x += pad;
     cudaStream_t st = op->stream;
     const int nvec = precond ? 8 : 6;
-    Scratch ws;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (vs * nvec + RED_BLOCKS + S_COUNT)));
-    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(cplx) * vs * nvec, st));
-    cplx *r = ws.base + pad, *r0 = r + vs, *p = r0 + vs, *v = p + vs, *s = v + vs, *t = s + vs;
-    cplx *ph = precond ? t + vs : p, *sh = precond ? ph + vs : s;
-    cplx* partial = ws.base + vs * nvec;
-    cplx* sc = partial + RED_BLOCKS;
+    Scratch ws, wsc;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(V) * vs * nvec));
+    FDFD_CHECK(cudaMalloc(&wsc.base, sizeof(cplx) * (2 * RED_BLOCKS + S_COUNT)));
+    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(V) * vs * nvec, st));
+    V *r = static_cast<V*>(ws.base) + pad, *r0 = r + vs, *p = r0 + vs, *v = p + vs, *s = v + vs, *t = s + vs;
+    V *ph = precond ? t + vs : p, *sh = precond ? ph + vs : s;
+    cplx* partial = static_cast<cplx*>(wsc.base);
+    cplx* sc = partial + 2 * RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
     cplx h;
     if (check_every < 1) check_every = 1;
     // r = b - A x
-    if (residual_A(op, d_b, d_x, r, c12)) return -1;
-    FDFD_CHECK(cudaMemcpyAsync(r0, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    FDFD_CHECK(cudaMemsetAsync(p, 0, sizeof(cplx) * n, st));
-    FDFD_CHECK(cudaMemsetAsync(v, 0, sizeof(cplx) * n, st));
+    if (residual_A<V>(op, d_b, d_x, r, c12)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(r0, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+    FDFD_CHECK(cudaMemsetAsync(p, 0, sizeof(V) * n, st));
+    FDFD_CHECK(cudaMemsetAsync(v, 0, sizeof(V) * n, st));
     cplx init[S_COUNT];
     for (int i = 0; i < S_COUNT; ++i) init[i] = make_double2(1.0, 0.0);
     FDFD_CHECK(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, RI, comm)) return -1;
+    if (dots<V>(st, d_b, d_b, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
     if (bnorm == 0.0) {
-        FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(cplx) * n, st));
+        FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(V) * n, st));
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
+    // rho = r0.r and ||r||^2 of the starting residual; beta of the first step is (rho / 1) (1 / 1)
+    if (dots<V>(st, r0, r, 1, r, r, 1, n, partial, sc, POST_BICG_RHO, 0, 0, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     if (res->relres <= tol) { res->converged = 1; return 0; }
     for (int it = 1; it <= maxiter; ++it) {
-        if (dev_dot(st, r0, r, n, true, partial, sc + S_RHO, RI, comm)) return -1;
-        { bicg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
-        { bicg_p_kernel<<<nblk, 256, 0, st>>>(p, r, v, sc, n); ++g_fdfd_launches; }
-        if (precond) { if (nd_solve(precond, op, p, ph, 1)) return -1; }
-        if (apply_A(op, ph, v, fused, c12)) return -1;
-        if (dev_dot(st, r0, v, n, true, partial, sc + S_R0V, RI, comm)) return -1;
-        { bicg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
-        { bicg_s_kernel<<<nblk, 256, 0, st>>>(s, r, v, sc, n); ++g_fdfd_launches; }
-        if (precond) { if (nd_solve(precond, op, s, sh, 1)) return -1; }
-        if (apply_A(op, sh, t, fused, c12)) return -1;
-        if (dev_dot(st, t, s, n, true, partial, sc + S_TS, RI, comm)) return -1;
-        if (dev_dot(st, t, t, n, true, partial, sc + S_TT, RI, comm)) return -1;
-        { bicg_omega_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
-        { bicg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, ph, sh, s, t, sc, n); ++g_fdfd_launches; }
+        { bicg_p_kernel<V><<<nblk, 256, 0, st>>>(p, r, v, sc, n); ++g_fdfd_launches; }
+        if (precond && precond_solve(precond, op, p, ph)) return -1;
+        if (apply_A<V>(op, ph, v, fused, c12)) return -1;
+        if (dots<V>(st, r0, v, 1, nullptr, nullptr, 0, n, partial, sc, POST_BICG_ALPHA, 0, 0, RI, comm)) return -1;
+        { bicg_s_kernel<V><<<nblk, 256, 0, st>>>(s, r, v, sc, n); ++g_fdfd_launches; }
+        if (precond && precond_solve(precond, op, s, sh)) return -1;
+        if (apply_A<V>(op, sh, t, fused, c12)) return -1;
+        if (dots<V>(st, t, s, 1, t, t, 1, n, partial, sc, POST_BICG_OMEGA, 0, 0, RI, comm)) return -1;
+        { bicg_xr_dots_kernel<V><<<RED_BLOCKS, RED_THREADS, 0, st>>>(d_x, r, ph, sh, s, t, r0, sc, n, partial); ++g_fdfd_launches; }
+        if (finish_dots(st, partial, sc, POST_BICG_RHO, 0, 0, RI, 1, comm)) return -1;
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
-            if (host_scalar(st, sc + S_RR, &h)) return -1;
+            if (host_scalar(st, sc + S_RR, &h)) return -1;       // ||r||^2 came with the fused update
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;           // NaN: breakdown
             if (res->relres <= tol) { res->converged = 1; break; }
         }
     }
     // report the TRUE residual of the returned iterate
-    if (residual_A(op, d_b, d_x, r, c12)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, RI, comm)) return -1;
+    if (residual_A<V>(op, d_b, d_x, r, c12)) return -1;
+    if (dots<V>(st, r, r, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, RI, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     res->relres = sqrt(h.x) / bnorm;
     res->converged = res->relres <= tol * 10 ? res->converged : 0;
     return 0;
 }
 
-int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,
-                KrylovResult* res) {
+template <class V>
+int krylov_cocg_t(const FdfdOp* op, const V* d_b, V* d_x, double tol, int maxiter, int fused, int check_every,
+                  KrylovResult* res) {
     const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
     FdfdComm* comm = op->comm;
     d_b += pad; d_x += pad;
     const cplx *sxf = op->isxf + op->halo, *syf = op->isyf;
     const int nxo = op->nx - 2 * op->halo;
     cudaStream_t st = op->stream;
-    Scratch ws;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (vs * 4 + RED_BLOCKS + S_COUNT)));
-    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(cplx) * vs * 4, st));
-    cplx *r = ws.base + pad, *p = r + vs, *q = p + vs, *bs = q + vs;
-    cplx* partial = ws.base + vs * 4;
-    cplx* sc = partial + RED_BLOCKS;
+    Scratch ws, wsc;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(V) * vs * 4));
+    FDFD_CHECK(cudaMalloc(&wsc.base, sizeof(cplx) * (2 * RED_BLOCKS + S_COUNT)));
+    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(V) * vs * 4, st));
+    V *r = static_cast<V*>(ws.base) + pad, *p = r + vs, *q = p + vs, *bs = q + vs;
+    cplx* partial = static_cast<cplx*>(wsc.base);
+    cplx* sc = partial + 2 * RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
     cplx h;
     if (check_every < 1) check_every = 1;
     // symmetrised system  D A x = D b,  D = diag(sxf[ix] syf[iy])
-    FDFD_CHECK(cudaMemcpyAsync(bs, d_b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    { sym_scale_kernel<<<nblk, 256, 0, st>>>(bs, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
-    if (residual_A(op, d_b, d_x, r, nullptr)) return -1;
-    { sym_scale_kernel<<<nblk, 256, 0, st>>>(r, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
-    FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
-    if (dev_dot(st, bs, bs, n, true, partial, sc + S_RR, 0, comm)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(bs, d_b, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+    { sym_scale_kernel<V><<<nblk, 256, 0, st>>>(bs, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+    if (residual_A<V>(op, d_b, d_x, r, nullptr)) return -1;
+    { sym_scale_kernel<V><<<nblk, 256, 0, st>>>(r, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+    FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+    if (dots<V>(st, bs, bs, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
     res->iters = 0; res->converged = 0; res->relres = 1.0;
     if (bnorm == 0.0) {
-        FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(cplx) * n, st));
+        FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(V) * n, st));
         res->converged = 1; res->relres = 0.0;
         return 0;
     }
-    if (dev_dot(st, r, r, n, false, partial, sc + S_RHO, 0, comm)) return -1;
+    if (dots<V>(st, r, r, 0, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RHO, -1, 0, comm)) return -1;
     for (int it = 1; it <= maxiter; ++it) {
-        if (apply_A(op, p, q, fused, nullptr)) return -1;
-        { sym_scale_kernel<<<nblk, 256, 0, st>>>(q, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
-        if (dev_dot(st, p, q, n, false, partial, sc + S_PQ, 0, comm)) return -1;
-        { cocg_alpha_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
-        { cocg_xr_kernel<<<nblk, 256, 0, st>>>(d_x, r, p, q, sc, n); ++g_fdfd_launches; }
-        if (dev_dot(st, r, r, n, false, partial, sc + S_RR, 0, comm)) return -1;
-        { cocg_beta_kernel<<<1, 1, 0, st>>>(sc); ++g_fdfd_launches; }
-        { cocg_p_kernel<<<nblk, 256, 0, st>>>(p, r, sc, n); ++g_fdfd_launches; }
+        if (apply_A<V>(op, p, q, fused, nullptr)) return -1;
+        { sym_scale_kernel<V><<<nblk, 256, 0, st>>>(q, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+        if (dots<V>(st, p, q, 0, nullptr, nullptr, 0, n, partial, sc, POST_COCG_ALPHA, 0, 0, 0, comm)) return -1;
+        { cocg_xr_dots_kernel<V><<<RED_BLOCKS, RED_THREADS, 0, st>>>(d_x, r, p, q, sc, n, partial); ++g_fdfd_launches; }
+        if (finish_dots(st, partial, sc, POST_COCG_BETA, 0, 0, 0, 1, comm)) return -1;
+        { cocg_p_kernel<V><<<nblk, 256, 0, st>>>(p, r, sc, n); ++g_fdfd_launches; }
         FDFD_CHECK(cudaGetLastError());
         res->iters = it;
         if (it % check_every == 0 || it == maxiter) {
-            if (dev_dot(st, r, r, n, true, partial, sc + S_TT, 0, comm)) return -1;
-            if (host_scalar(st, sc + S_TT, &h)) return -1;
+            if (host_scalar(st, sc + S_RR, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
             if (!(res->relres == res->relres)) break;
             if (res->relres <= tol) { res->converged = 1; break; }
         }
     }
     // true residual in the ORIGINAL (unscaled) system
-    if (residual_A(op, d_b, d_x, r, nullptr)) return -1;
-    if (dev_dot(st, r, r, n, true, partial, sc + S_RR, 0, comm)) return -1;
+    if (residual_A<V>(op, d_b, d_x, r, nullptr)) return -1;
+    if (dots<V>(st, r, r, 1, d_b, d_b, 1, n, partial, sc, POST_STORE, S_RR, S_TT, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     double rn = sqrt(h.x);
-    if (dev_dot(st, d_b, d_b, n, true, partial, sc + S_RR, 0, comm)) return -1;
-    if (host_scalar(st, sc + S_RR, &h)) return -1;
+    if (host_scalar(st, sc + S_TT, &h)) return -1;
     res->relres = rn / sqrt(h.x);
     return 0;
+}
+
+int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
+                    int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
+    return krylov_bicgstab_t<cplx>(op, precond, d_b, d_x, tol, maxiter, fused, check_every, c12, real_inner, res);
+}
+int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,
+                KrylovResult* res) {
+    return krylov_cocg_t<cplx>(op, d_b, d_x, tol, maxiter, fused, check_every, res);
+}
+int krylov_bicgstab_c64(const FdfdOp* op, const cplx32* d_b, cplx32* d_x, double tol, int maxiter, int fused,
+                        int check_every, KrylovResult* res) {
+    return krylov_bicgstab_t<cplx32>(op, nullptr, d_b, d_x, tol, maxiter, fused, check_every, nullptr, 0, res);
+}
+int krylov_cocg_c64(const FdfdOp* op, const cplx32* d_b, cplx32* d_x, double tol, int maxiter, int fused,
+                    int check_every, KrylovResult* res) {
+    return krylov_cocg_t<cplx32>(op, d_b, d_x, tol, maxiter, fused, check_every, res);
 }
 
 int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs, int max_refine, double tol,
@@ -321,7 +429,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
     const size_t n = op->n();
     cudaStream_t st = op->stream;
     // residual / correction vectors live in the solver handle (grown on demand, never freed per call)
-    const size_t need = 2 * n * nrhs + RED_BLOCKS + 2;
+    const size_t need = 2 * n * nrhs + 2 * RED_BLOCKS + S_COUNT;
     if (need > nd->ws_refine_cap) {
         if (nd->ws_refine) cudaFree(nd->ws_refine);
         nd->ws_refine = nullptr;
@@ -329,7 +437,7 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
         FDFD_CHECK(cudaMalloc(&nd->ws_refine, sizeof(cplx) * need));
         nd->ws_refine_cap = need;
     }
-    cplx *r = nd->ws_refine, *d = r + n * nrhs, *partial = d + n * nrhs, *sc = partial + RED_BLOCKS;
+    cplx *r = nd->ws_refine, *d = r + n * nrhs, *partial = d + n * nrhs, *sc = partial + 2 * RED_BLOCKS;
     std::vector<double> bn(nrhs);
     cplx h;
     for (int j = 0; j < nrhs; ++j) {

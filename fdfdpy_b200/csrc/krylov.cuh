@@ -9,8 +9,13 @@ struct KrylovResult {
     double relres;     // ||b - A x|| / ||b|| of the returned iterate (true residual)
 };
 
-int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* out,
+int dev_dot(cudaStream_t st, const cplx* a, const cplx* b, size_t n, bool conj_a, cplx* partial, cplx* sc,
             int real_only, FdfdComm* comm = nullptr);
+// complex64 vectors (fp64 arithmetic and scalars): no preconditioner, no anti-linear term
+int krylov_bicgstab_c64(const FdfdOp* op, const cplx32* d_b, cplx32* d_x, double tol, int maxiter, int fused,
+                        int check_every, KrylovResult* res);
+int krylov_cocg_c64(const FdfdOp* op, const cplx32* d_b, cplx32* d_x, double tol, int maxiter, int fused,
+                    int check_every, KrylovResult* res);
 int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter,
                     int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res);
 int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,

@@ -95,28 +95,28 @@ __global__ void assemble_planes_kernel(cplx* __restrict__ planes, const cplx* __
 // ------------------------------------------------------------------------------------------
 // stencil application from stored planes:  y = A x   or   r = b - A x
 // ------------------------------------------------------------------------------------------
-template <bool RESID>
+template <bool RESID, class V>
 __global__ void __launch_bounds__(256)
-stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ x, const cplx* __restrict__ b,
-                      cplx* __restrict__ y, int nx, int ny, int row0, int row1) {
+stencil_planes_kernel(const cplx* __restrict__ planes, const V* __restrict__ x, const V* __restrict__ b,
+                      V* __restrict__ y, int nx, int ny, int row0, int row1) {
     size_t n = (size_t)nx * ny;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)(row1 - row0) * ny) return;
     idx += (size_t)row0 * ny;                    // rows [row0, row1): a slab never writes its halo rows
     size_t voff = (size_t)blockIdx.y * n;
-    const cplx* xv = x + voff;
+    const V* xv = x + voff;
     int ix = (int)(idx / ny), iy = (int)(idx % ny);
     size_t xm = (size_t)(ix == 0 ? nx - 1 : ix - 1) * ny + iy;
     size_t xp = (size_t)(ix + 1 == nx ? 0 : ix + 1) * ny + iy;
     size_t ym = (size_t)ix * ny + (iy == 0 ? ny - 1 : iy - 1);
     size_t yp = (size_t)ix * ny + (iy + 1 == ny ? 0 : iy + 1);
-    cplx acc = cmul(ldg_c(planes + idx), ldg_c(xv + idx));
-    cfma(acc, ldg_c(planes + n + idx), ldg_c(xv + xm));
-    cfma(acc, ldg_c(planes + 2 * n + idx), ldg_c(xv + xp));
-    cfma(acc, ldg_c(planes + 3 * n + idx), ldg_c(xv + ym));
-    cfma(acc, ldg_c(planes + 4 * n + idx), ldg_c(xv + yp));
-    if (RESID) acc = csub(ldg_c(b + voff + idx), acc);
-    y[voff + idx] = acc;
+    cplx acc = cmul(ldg_c(planes + idx), vload(xv + idx));
+    cfma(acc, ldg_c(planes + n + idx), vload(xv + xm));
+    cfma(acc, ldg_c(planes + 2 * n + idx), vload(xv + xp));
+    cfma(acc, ldg_c(planes + 3 * n + idx), vload(xv + ym));
+    cfma(acc, ldg_c(planes + 4 * n + idx), vload(xv + yp));
+    if (RESID) acc = csub(vload(b + voff + idx), acc);
+    vstore(y + voff + idx, acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -125,6 +125,7 @@ stencil_planes_kernel(const cplx* __restrict__ planes, const cplx* __restrict__ 
 // y column and marches ROWS consecutive rows keeping the x-neighbours in registers.
 // ------------------------------------------------------------------------------------------
 int g_fused_rows = 4;          // A/B switch (fdfd_stencil_set_variant): rows marched per thread
+int g_fused_rows32 = 8;        // the same for complex64 vectors (half the bytes per load: more rows in flight)
 
 __device__ __forceinline__ cplx shfl_up_c(cplx v) {
     return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
@@ -148,12 +149,12 @@ __global__ void pml_products_kernel(cplx* __restrict__ am, cplx* __restrict__ ap
 // y-neighbours come from the adjacent lanes by shuffle (only the two edge lanes of a warp load them), the
 // coupling coefficients are 1-D tables (warp-uniform loads).  There is no barrier and no early exit in the
 // full-CTA body, so every load of a thread is issued before the first one is consumed.
-template <int ROWS>
+template <int ROWS, class V>
 __global__ void __launch_bounds__(128)
-stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__ eps_nl,
+stencil_fused_ez_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_nl,
                         const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
                         const cplx* __restrict__ aym_t, const cplx* __restrict__ ayp_t,
-                        const cplx* __restrict__ x, cplx* __restrict__ y, int nx, int ny, double w2e0, int row0,
+                        const V* __restrict__ x, V* __restrict__ y, int nx, int ny, double w2e0, int row0,
                         int row1) {
     const int ix0 = row0 + blockIdx.y * ROWS;
     const int rows = min(ROWS, row1 - ix0);
@@ -163,59 +164,59 @@ stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__
     const int lane = threadIdx.x & 31;
     const size_t n = (size_t)nx * ny;
     const size_t voff = (size_t)blockIdx.z * n;
-    const cplx* xv = x + voff;
+    const V* xv = x + voff;
     const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
     const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || iy_raw >= ny - 1;
     const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
     if (rows == ROWS) {
         cplx xc[ROWS + 2], e[ROWS];
-        xc[0] = ldg_c(xv + (size_t)ixm * ny + iy);
+        xc[0] = vload(xv + (size_t)ixm * ny + iy);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            xc[r + 1] = ldg_c(xv + (size_t)(ix0 + r) * ny + iy);
-            e[r] = ldg_c(eps_r + (size_t)(ix0 + r) * ny + iy);
+            xc[r + 1] = vload(xv + (size_t)(ix0 + r) * ny + iy);
+            e[r] = vload(eps_r + (size_t)(ix0 + r) * ny + iy);
         }
         {
             int ixl = ix0 + ROWS == nx ? 0 : ix0 + ROWS;
-            xc[ROWS + 1] = ldg_c(xv + (size_t)ixl * ny + iy);
+            xc[ROWS + 1] = vload(xv + (size_t)ixl * ny + iy);
         }
         const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
         const cplx ay = cadd(aym, ayp);
         if (eps_nl) {
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) e[r] = cadd(e[r], ldg_c(eps_nl + (size_t)(ix0 + r) * ny + iy));
+            for (int r = 0; r < ROWS; ++r) e[r] = cadd(e[r], vload(eps_nl + (size_t)(ix0 + r) * ny + iy));
         }
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             // coefficient tables and the two edge-lane neighbours are cache hits (same lines as adjacent warps)
             const cplx axm = ldg_c(axm_t + ix0 + r), axp = ldg_c(axp_t + ix0 + r);
             cplx xd = shfl_up_c(xc[r + 1]), xu = shfl_down_c(xc[r + 1]);
-            if (load_dn) xd = ldg_c(xv + (size_t)(ix0 + r) * ny + iym);
-            if (load_up) xu = ldg_c(xv + (size_t)(ix0 + r) * ny + iyp);
+            if (load_dn) xd = vload(xv + (size_t)(ix0 + r) * ny + iym);
+            if (load_up) xu = vload(xv + (size_t)(ix0 + r) * ny + iyp);
             cplx c0 = csub(csub(cscale(e[r], w2e0), cadd(axm, axp)), ay);
             cplx acc = cmul(c0, xc[r + 1]);
             cfma(acc, axm, xc[r]);
             cfma(acc, axp, xc[r + 2]);
             cfma(acc, aym, xd);
             cfma(acc, ayp, xu);
-            if (active) y[voff + (size_t)(ix0 + r) * ny + iy] = acc;
+            if (active) vstore(y + voff + (size_t)(ix0 + r) * ny + iy, acc);
         }
         return;
     }
     // ragged last CTA row of the grid
     const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
     const cplx ay = cadd(aym, ayp);
-    cplx xl = ldg_c(xv + (size_t)ixm * ny + iy);
-    cplx xcur = ldg_c(xv + (size_t)ix0 * ny + iy);
+    cplx xl = vload(xv + (size_t)ixm * ny + iy);
+    cplx xcur = vload(xv + (size_t)ix0 * ny + iy);
     for (int r = 0; r < rows; ++r) {
         int ix = ix0 + r;
         int ixp = ix + 1 == nx ? 0 : ix + 1;
         size_t row = (size_t)ix * ny;
-        cplx xr = ldg_c(xv + (size_t)ixp * ny + iy);
-        cplx xd = ldg_c(xv + row + iym);
-        cplx xu = ldg_c(xv + row + iyp);
-        cplx e = ldg_c(eps_r + row + iy);
-        if (eps_nl) e = cadd(e, ldg_c(eps_nl + row + iy));
+        cplx xr = vload(xv + (size_t)ixp * ny + iy);
+        cplx xd = vload(xv + row + iym);
+        cplx xu = vload(xv + row + iyp);
+        cplx e = vload(eps_r + row + iy);
+        if (eps_nl) e = cadd(e, vload(eps_nl + row + iy));
         const cplx axm = ldg_c(axm_t + ix), axp = ldg_c(axp_t + ix);
         cplx c0 = csub(csub(cscale(e, w2e0), cadd(axm, axp)), ay);
         cplx acc = cmul(c0, xcur);
@@ -223,7 +224,7 @@ stencil_fused_ez_kernel(const cplx* __restrict__ eps_r, const cplx* __restrict__
         cfma(acc, axp, xr);
         cfma(acc, aym, xd);
         cfma(acc, ayp, xu);
-        if (active) y[voff + row + iy] = acc;
+        if (active) vstore(y + voff + row + iy, acc);
         xl = xcur;
         xcur = xr;
     }
@@ -355,10 +356,11 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
     return op_create_impl(out, nxl + 2, ny, omega, dl, npml_x, npml_y, pol, L0, 1, gnx, x0, comm);
 }
 
-int op_halo_exchange(const FdfdOp* op, cplx* x, cudaStream_t st) {
+int op_halo_exchange(const FdfdOp* op, void* xv, size_t elem, cudaStream_t st) {
     if (!op->halo) return 0;
-    const size_t ny = op->ny, row = sizeof(cplx) * ny;
-    cplx *first = x + ny, *last = x + (size_t)(op->nx - 2) * ny, *halo_lo = x, *halo_hi = x + (size_t)(op->nx - 1) * ny;
+    const size_t row = elem * op->ny;                 // bytes per row (elem = 16: complex128, 8: complex64)
+    char* x = static_cast<char*>(xv);
+    char *first = x + row, *last = x + (size_t)(op->nx - 2) * row, *halo_lo = x, *halo_hi = x + (size_t)(op->nx - 1) * row;
     if (!op->comm || op->comm->world == 1) {         // one slab: the grid wraps onto itself
         FDFD_CHECK(cudaMemcpyAsync(halo_lo, last, row, cudaMemcpyDeviceToDevice, st));
         FDFD_CHECK(cudaMemcpyAsync(halo_hi, first, row, cudaMemcpyDeviceToDevice, st));
@@ -366,8 +368,8 @@ int op_halo_exchange(const FdfdOp* op, cplx* x, cudaStream_t st) {
     }
     const int w = op->comm->world, r = op->comm->rank, lower = (r + w - 1) % w, upper = (r + 1) % w;
     // my first row is the upper halo of the rank below, my last row the lower halo of the rank above
-    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, 2 * ny, st)) return -1;
-    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, 2 * ny, st)) return -1;
+    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, row / 8, st)) return -1;
+    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, row / 8, st)) return -1;
     return 0;
 }
 
@@ -377,6 +379,7 @@ void op_destroy(FdfdOp* op) {
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
     if (op->io_buf) cudaFree(op->io_buf);
     cudaFree(op->ax); cudaFree(op->ay);
+    if (op->eps32) cudaFree(op->eps32);
     if (op->comm_stream) { cudaStreamDestroy(op->comm_stream); cudaEventDestroy(op->ev_in); cudaEventDestroy(op->ev_halo); }
     if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
     cudaStreamDestroy(op->stream);
@@ -413,6 +416,7 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     size_t n = op->n();
     op->averaging = averaging;
     op->has_nl = d_eps_nl != nullptr;
+    op->eps32_valid = 0;
     if (d_eps_r != op->eps_r)
         FDFD_CHECK(cudaMemcpyAsync(op->eps_r, d_eps_r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
     if (d_eps_nl && d_eps_nl != op->eps_nl)
@@ -433,17 +437,18 @@ struct RowPlan {
     bool wait_halo_before[3];
 };
 
-static int slab_begin(const FdfdOp* op, const cplx* d_x, int nvec, RowPlan* plan) {
+template <class V>
+static int slab_begin(const FdfdOp* op, const V* d_x, int nvec, RowPlan* plan) {
     plan->nranges = 1;
     plan->r0[0] = op->halo; plan->r1[0] = op->nx - op->halo; plan->wait_halo_before[0] = false;
     if (!op->halo) return 0;
     if (nvec != 1) FDFD_FAIL("slab operators apply one vector at a time");
-    cplx* x = const_cast<cplx*>(d_x);
+    V* x = const_cast<V*>(d_x);
     const bool overlap = op->comm && op->comm->world > 1 && op->comm_stream && op->nx - 2 >= 3;
-    if (!overlap) return op_halo_exchange(op, x, op->stream);
+    if (!overlap) return op_halo_exchange(op, x, sizeof(V), op->stream);
     FDFD_CHECK(cudaEventRecord(op->ev_in, op->stream));
     FDFD_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_in, 0));
-    if (op_halo_exchange(op, x, op->comm_stream)) return -1;
+    if (op_halo_exchange(op, x, sizeof(V), op->comm_stream)) return -1;
     FDFD_CHECK(cudaEventRecord(op->ev_halo, op->comm_stream));
     plan->nranges = 3;
     plan->r0[0] = 2; plan->r1[0] = op->nx - 2; plan->wait_halo_before[0] = false;
@@ -452,47 +457,88 @@ static int slab_begin(const FdfdOp* op, const cplx* d_x, int nvec, RowPlan* plan
     return 0;
 }
 
-template <bool RESID>
-static int launch_planes(const FdfdOp* op, const cplx* d_x, const cplx* d_b, cplx* d_y, int nvec) {
+// complex64 copy of eps_r for the complex64 stencil (24 B/cell); rebuilt lazily after every assembly
+__global__ void narrow_kernel(const cplx* __restrict__ in, cplx32* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
+}
+static int eps32(const FdfdOp* cop, const cplx32** er, const cplx32** enl) {
+    FdfdOp* op = const_cast<FdfdOp*>(cop);
+    const size_t n = op->n();
+    if (!op->eps32) FDFD_CHECK(cudaMalloc(&op->eps32, sizeof(cplx32) * 2 * n));
+    if (!op->eps32_valid) {
+        narrow_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(op->eps_r, op->eps32, n);
+        ++g_fdfd_launches;
+        if (op->has_nl) { narrow_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(op->eps_nl, op->eps32 + n, n); ++g_fdfd_launches; }
+        FDFD_CHECK(cudaGetLastError());
+        op->eps32_valid = 1;
+    }
+    *er = op->eps32;
+    *enl = op->has_nl ? op->eps32 + n : nullptr;
+    return 0;
+}
+static int eps_of(const FdfdOp* op, const cplx** er, const cplx** enl) {
+    *er = op->eps_r;
+    *enl = op->has_nl ? op->eps_nl : nullptr;
+    return 0;
+}
+static int eps_of(const FdfdOp* op, const cplx32** er, const cplx32** enl) { return eps32(op, er, enl); }
+
+template <bool RESID, class V>
+static int launch_planes(const FdfdOp* op, const V* d_x, const V* d_b, V* d_y, int nvec) {
     RowPlan plan;
     if (slab_begin(op, d_x, nvec, &plan)) return -1;
     for (int i = 0; i < plan.nranges; ++i) {
         if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
         dim3 grid(ceil_div((size_t)(plan.r1[i] - plan.r0[i]) * op->ny, 256), nvec);
-        stencil_planes_kernel<RESID><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_y, op->nx, op->ny, plan.r0[i],
-                                                                  plan.r1[i]);
+        stencil_planes_kernel<RESID, V><<<grid, 256, 0, op->stream>>>(op->planes, d_x, d_b, d_y, op->nx, op->ny,
+                                                                     plan.r0[i], plan.r1[i]);
         ++g_fdfd_launches;
     }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
 
-int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
-    return launch_planes<false>(op, d_x, nullptr, d_y, nvec);
+template <class V>
+int op_apply_planes_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
+    return launch_planes<false, V>(op, d_x, (const V*)nullptr, d_y, nvec);
 }
-
-int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
-    return launch_planes<true>(op, d_x, d_b, d_r, nvec);
+template <class V>
+int op_residual_t(const FdfdOp* op, const V* d_b, const V* d_x, V* d_r, int nvec) {
+    return launch_planes<true, V>(op, d_x, d_b, d_r, nvec);
 }
-
-int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) {
-    if (op->pol != 0) return op_apply_planes(op, d_x, d_y, nvec);
+template <class V>
+int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
+    if (op->pol != 0) return op_apply_planes_t<V>(op, d_x, d_y, nvec);
+    const V *er, *enl;
+    if (eps_of(op, &er, &enl)) return -1;
     RowPlan plan;
     if (slab_begin(op, d_x, nvec, &plan)) return -1;
     AsmParams p = make_params(op);
-    const int rows = g_fused_rows;
-    auto kern = rows == 8 ? stencil_fused_ez_kernel<8> : rows == 2 ? stencil_fused_ez_kernel<2> : stencil_fused_ez_kernel<4>;
+    const int rows = sizeof(V) == sizeof(cplx32) ? g_fused_rows32 : g_fused_rows;
+    auto kern = rows == 8 ? stencil_fused_ez_kernel<8, V> : rows == 2 ? stencil_fused_ez_kernel<2, V> : stencil_fused_ez_kernel<4, V>;
     for (int i = 0; i < plan.nranges; ++i) {
         if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
         dim3 grid(ceil_div(op->ny, 128), ceil_div(plan.r1[i] - plan.r0[i], rows), nvec);
-        kern<<<grid, 128, 0, op->stream>>>(op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->ax, op->ax + op->nx, op->ay,
-                                           op->ay + op->ny, d_x, d_y, op->nx, op->ny, p.omega * p.omega * p.e0,
-                                           plan.r0[i], plan.r1[i]);
+        kern<<<grid, 128, 0, op->stream>>>(er, enl, op->ax, op->ax + op->nx, op->ay, op->ay + op->ny, d_x, d_y, op->nx,
+                                           op->ny, p.omega * p.omega * p.e0, plan.r0[i], plan.r1[i]);
         ++g_fdfd_launches;
     }
     FDFD_CHECK(cudaGetLastError());
     return 0;
 }
+template int op_apply_planes_t<cplx>(const FdfdOp*, const cplx*, cplx*, int);
+template int op_apply_planes_t<cplx32>(const FdfdOp*, const cplx32*, cplx32*, int);
+template int op_residual_t<cplx>(const FdfdOp*, const cplx*, const cplx*, cplx*, int);
+template int op_residual_t<cplx32>(const FdfdOp*, const cplx32*, const cplx32*, cplx32*, int);
+template int op_apply_fused_t<cplx>(const FdfdOp*, const cplx*, cplx*, int);
+template int op_apply_fused_t<cplx32>(const FdfdOp*, const cplx32*, cplx32*, int);
+
+int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) { return op_apply_planes_t<cplx>(op, d_x, d_y, nvec); }
+int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec) {
+    return op_residual_t<cplx>(op, d_b, d_x, d_r, nvec);
+}
+int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec) { return op_apply_fused_t<cplx>(op, d_x, d_y, nvec); }
 
 int op_derive_fields(const FdfdOp* op, const cplx* d_x, cplx* d_f1, cplx* d_f2, int averaging) {
     AsmParams p = make_params(op);

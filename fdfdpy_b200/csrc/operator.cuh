@@ -26,6 +26,8 @@ struct FdfdOp {
     cplx *planes;
     // lazily allocated staging for the *_host entry points (4*nx*ny complex: b, x, f1, f2)
     cplx *io_buf;
+    cplx32* eps32;      // complex64 copy of eps_r (| eps_nl) for the complex64 stencil, built on first use
+    int eps32_valid;
     // slab of a grid split over several GPUs (halo = 1): nx counts the slab's rows PLUS one halo row on each
     // side, every vector has that extended layout, the stencil only writes rows 1..nx-2 and the halo rows of
     // its input are filled from the neighbouring ranks (periodic in the rank index) before it runs
@@ -43,13 +45,17 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
                    int npml_x, int npml_y, int pol, double L0);
 void op_destroy(FdfdOp* op);
 // fills the two halo rows of an extended-layout vector from the neighbouring slabs
-int op_halo_exchange(const FdfdOp* op, cplx* d_x_ext, cudaStream_t st);
+int op_halo_exchange(const FdfdOp* op, void* d_x_ext, size_t elem_bytes, cudaStream_t st);
 // eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes
 int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int averaging);
 // y = A x using the stored planes (any polarisation, nonlinearity included); nvec vectors back to back
 int op_apply_planes(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
 // y = A x recomputing the coefficients from eps and the 1-D PML factors (Ez hot path, 48 B/cell)
 int op_apply_fused(const FdfdOp* op, const cplx* d_x, cplx* d_y, int nvec);
+// the same three for complex128 (cplx) or complex64 (cplx32) vectors; arithmetic is fp64 either way
+template <class V> int op_apply_planes_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec);
+template <class V> int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec);
+template <class V> int op_residual_t(const FdfdOp* op, const V* d_b, const V* d_x, V* d_r, int nvec);
 // r = b - A x (planes), returns nothing; used by iterative refinement
 int op_residual(const FdfdOp* op, const cplx* d_b, const cplx* d_x, cplx* d_r, int nvec);
 // staging buffer of the host entry points (allocated on first use, kept until op_destroy)

@@ -160,6 +160,16 @@ int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, vo
                           double tol, int maxiter, int fused, int check_every, const void* d_c12,
                           int real_inner, int* iters, double* relres, int* converged);
 
+/* complex64 storage for the matrix-free path (interleaved float re, im = numpy complex64): vectors and eps_r
+ * stream as 8-byte values (24 B/cell for the fused Ez stencil), arithmetic, inner products and iteration
+ * scalars stay fp64.  Parity bar: relative L2 error <= 1e-4 against the fp64 reference.           */
+int fdfd_op_apply_host_c64(fdfd_op* op, const float* x_c64, float* y_c64, int fused);
+int fdfd_op_apply_dev_c64(fdfd_op* op, const void* d_x, void* d_y, int fused);
+int fdfd_krylov_solve_host_c64(fdfd_op* op, const float* b_c64, float* x_c64, int method, double tol, int maxiter,
+                               int fused, int check_every, int* iters, double* relres, int* converged);
+int fdfd_krylov_solve_dev_c64(fdfd_op* op, const void* d_b, void* d_x, int method, double tol, int maxiter,
+                              int fused, int check_every, int* iters, double* relres, int* converged);
+
 /* ---- modal source: replaces source/mode.py:64-108 insert_mode's eigensolve (linalg.py:104
  * solver_eigs -> ARPACK shift-invert).  eps_line: n real relative permittivities along the
  * source plane; averaged != 0 applies the edge average of mode.py:82 (planes normal to y).
@@ -175,8 +185,8 @@ int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl,
 int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, int N, int K, int batch,
                             int mode, int transb, int lower);
 
-/* rows each thread of the fused Ez stencil marches (2, 4, 8): A/B measurements */
-int fdfd_stencil_set_variant(int rows_per_thread);
+/* rows each thread of the fused Ez stencil marches (2, 4, 8; defaults 4 for complex128, 8 for complex64) */
+int fdfd_stencil_set_variant(int rows_per_thread, int complex64);
 /* kernel selection for A/B measurements: 0 = persistent kernel for large problems (default), 1 = tiled only */
 int fdfd_zgemm_set_variant(int v);
 /* 1 (default): levels of tiny fronts (k <= 32) run as one fused kernel each; 0: generic path everywhere */

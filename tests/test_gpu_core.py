@@ -240,3 +240,29 @@ def test_single_slab_operator_matches_whole_grid(core, pol):
         xs, info = slab.krylov(b, method=method, tol=1e-11, maxiter=20000, check_every=20)
         assert info["relres"] < 1e-8, (method, info)
         assert relerr(xs, sol) < 1e-6
+
+
+def test_complex64_stencil_and_krylov(core):
+    """complex64 storage of the matrix-free path (fp64 arithmetic): north_star's tolerance is a relative L2
+    error <= 1e-4 against the fp64 reference."""
+    rng = np.random.default_rng(21)
+    nx, ny = 48, 40
+    eps = 1 + 2 * rng.random((nx, ny))
+    npml = [8, 8]
+    for pol in ("Ez", "Hz"):
+        op = core.MaxwellOperator(OMEGA, eps, 0.05, npml, pol, 1e-6)
+        A = orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6)
+        x = (rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))).astype(np.complex64)
+        ref = A.dot(x.astype(np.complex128).ravel()).reshape(nx, ny)
+        for fused in (False, True):
+            y = op.dot(x, fused=fused)
+            assert y.dtype == np.complex64
+            assert relerr(y, ref) < 5e-7, (pol, fused)
+        b = np.zeros((nx, ny), dtype=np.complex64)
+        b[24, 20] = 1j * OMEGA
+        sol = orc.sparse_solve(A, b.astype(np.complex128)).reshape(nx, ny)
+        for method in ("bicgstab", "cocg"):
+            xs, info = op.krylov(b, method=method, tol=2e-6, maxiter=20000, check_every=20)
+            assert xs.dtype == np.complex64
+            assert info["relres"] < 1e-4, (pol, method, info)
+            assert relerr(xs, sol) < 1e-4, (pol, method, relerr(xs, sol))

@@ -20,7 +20,7 @@ for n in sizes:
     _lib.check(lib.fdfd_malloc(C.byref(d_y), 16.0 * n * n))
     _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(x), 16.0 * n * n))
     for rows in (2, 4, 8):
-        _lib.check(lib.fdfd_stencil_set_variant(rows))
+        _lib.check(lib.fdfd_stencil_set_variant(rows, 0))
         err = np.linalg.norm(op.dot(x, fused=True) - ref) / np.linalg.norm(ref)
         for _ in range(5):
             _lib.check(lib.fdfd_op_apply_dev(op.h, d_x, d_y, 1, 1))
@@ -32,7 +32,36 @@ for n in sizes:
         _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms)))
         print(f"n={n} rows={rows}: {ms.value / reps * 1e3:.1f} us  {48.0 * n * n * reps / ms.value / 1e6:.0f} GB/s  "
               f"rel diff vs planes kernel {err:.2e}", flush=True)
-    _lib.check(lib.fdfd_stencil_set_variant(8))
+    _lib.check(lib.fdfd_stencil_set_variant(4, 0))
+    # complex64 storage (24 B/cell) and one BiCGSTAB iteration in both storage types
+    x32 = x.astype(np.complex64)
+    err32 = np.linalg.norm(op.dot(x32, fused=True) - ref) / np.linalg.norm(ref)
+    for rows in (2, 4, 8):
+        _lib.check(lib.fdfd_stencil_set_variant(rows, 1))
+        for _ in range(5):
+            _lib.check(lib.fdfd_op_apply_dev_c64(op.h, d_x, d_y, 1))
+        ms = C.c_double(0)
+        _lib.check(lib.fdfd_timer_start(op.h))
+        for _ in range(50):
+            _lib.check(lib.fdfd_op_apply_dev_c64(op.h, d_x, d_y, 1))
+        _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms)))
+        print(f"n={n} complex64 fused rows={rows}: {ms.value / 50 * 1e3:.1f} us  {24.0 * n * n * 50 / ms.value / 1e6:.0f} GB/s  "
+              f"rel diff vs fp64 planes kernel {err32:.2e}", flush=True)
+    _lib.check(lib.fdfd_stencil_set_variant(8, 1))
+    it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+    b = np.zeros((n, n), dtype=np.complex128)
+    b[n // 2, n // 2] = 1j * bench.OMEGA0
+    for name, fn, arr in (("complex128", lib.fdfd_krylov_solve_dev, b), ("complex64", lib.fdfd_krylov_solve_dev_c64, b.astype(np.complex64))):
+        for rep in range(2):
+            _lib.check(lib.fdfd_memcpy_h2d(d_y, _lib.ptr(arr), float(arr.nbytes)))
+            _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(np.zeros_like(arr)), float(arr.nbytes)))
+            _lib.check(lib.fdfd_timer_start(op.h))
+            if name == "complex128":
+                _lib.check(fn(op.h, None, d_y, d_x, 0, 1e-30, 200, 1, 200, None, 0, C.byref(it), C.byref(rr), C.byref(conv)))
+            else:
+                _lib.check(fn(op.h, d_y, d_x, 0, 1e-30, 200, 1, 200, C.byref(it), C.byref(rr), C.byref(conv)))
+            _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms)))
+        print(f"n={n} BiCGSTAB {name}: {ms.value / max(it.value, 1):.3f} ms/iteration ({it.value} iterations)", flush=True)
     lib.fdfd_free(d_x)
     lib.fdfd_free(d_y)
     del op
