@@ -57,34 +57,41 @@ leaf_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ planes, cons
     }
 }
 
+// One CTA assembles ASM_ROWS consecutive rows of one front (a warp per row, lanes along the row up to the
+// diagonal): no integer division per element, no threads parked on the unused upper triangle, the row's own
+// map entries are loaded once and the children's Schur rows are read along their fast index.
+#define ASM_ROWS 32
 __global__ void __launch_bounds__(256)
 merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const int* __restrict__ cls,
                       const int* __restrict__ k_cls, const int* __restrict__ ch1, const int* __restrict__ ch2,
                       const int* __restrict__ inv1, const int* __restrict__ inv2, int kmax, int nmax,
                       int kc, int nc, int chunks) {
     const long long b = blockIdx.x / chunks;
-    const int chunk = blockIdx.x % chunks;
+    const int r0 = (int)(blockIdx.x % chunks) * ASM_ROWS;
     const int c = cls[b];
     const int* i1 = inv1 + (size_t)c * nmax;
     const int* i2 = inv2 + (size_t)c * nmax;
-    const cplx* S1 = Fc + (long long)ch1[b] * nc * nc;
-    const cplx* S2 = Fc + (long long)ch2[b] * nc * nc;
+    const cplx* S1 = Fc + (long long)ch1[b] * nc * nc + (size_t)kc * nc + kc;
+    const cplx* S2 = Fc + (long long)ch2[b] * nc * nc + (size_t)kc * nc + kc;
     cplx* Fb = F + b * (long long)nmax * nmax;
     const int kcls = k_cls[c];
-    const long long total = (long long)nmax * nmax;
-    const long long per = (total + chunks - 1) / chunks;
-    const long long e0 = chunk * per, e1 = min(total, e0 + per);
-    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        int p = (int)(e / nmax), q = (int)(e % nmax);
-        if (q > p) continue;                       // lower triangle only
-        cplx v = make_double2(0.0, 0.0);
-        int a = i1[p], bq = i1[q];
-        if (a >= 0 && bq >= 0) v = S1[(size_t)(kc + max(a, bq)) * nc + kc + min(a, bq)];
-        a = i2[p];
-        bq = i2[q];
-        if (a >= 0 && bq >= 0) v = cadd(v, S2[(size_t)(kc + max(a, bq)) * nc + kc + min(a, bq)]);
-        if (p == q && p >= kcls && p < kmax) v = make_double2(1.0, 0.0);
-        Fb[e] = v;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = r0 + w; p < min(r0 + ASM_ROWS, nmax); p += 8) {
+        const int a1 = i1[p], a2 = i2[p];
+        cplx* row = Fb + (size_t)p * nmax;
+        for (int q = lane; q <= p; q += 32) {
+            cplx v = make_double2(0.0, 0.0);
+            if (a1 >= 0) {
+                int bq = i1[q];
+                if (bq >= 0) v = S1[(size_t)max(a1, bq) * nc + min(a1, bq)];
+            }
+            if (a2 >= 0) {
+                int bq = i2[q];
+                if (bq >= 0) v = cadd(v, S2[(size_t)max(a2, bq) * nc + min(a2, bq)]);
+            }
+            if (p == q && p >= kcls && p < kmax) v = make_double2(1.0, 0.0);
+            row[q] = v;
+        }
     }
 }
 
@@ -964,7 +971,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                                                                   L.x0, L.y0, L.slot_lx, L.slot_ly, L.slot_right,
                                                                   L.slot_up, kmax, nmax, s->nx, s->ny);
             } else {
-                int chunks = chunks_for((long long)nmax * nmax, nb);
+                int chunks = (nmax + ASM_ROWS - 1) / ASM_ROWS;
                 merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
                                                                                L.inv1, L.inv2, kmax, nmax, prev_k,
                                                                                prev_n, chunks);
