@@ -197,7 +197,7 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned tile, unsigned tiles_p
 template <int STAGES, bool TB>
 __global__ void __launch_bounds__(256, 1)
 zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles) {
-    constexpr int WN = 2, BM = 64, BN = 64, BK = 16, NT = 256;
+    constexpr int WN = 2, BM = 64, BN = 64, BK = 16;
     constexpr int LDA = BK + 4, LDB = TB ? BK + 4 : BN + 2;
     constexpr int A_ELEMS = BM * LDA, B_ELEMS = TB ? BN * LDB : BK * LDB;
     extern __shared__ __align__(16) unsigned char zg_smem[];
