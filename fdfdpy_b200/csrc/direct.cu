@@ -666,6 +666,60 @@ backward_mvt_kernel(const cplx* __restrict__ G, const cplx* __restrict__ yE, cpl
     }
 }
 
+// The same product for levels with FEW fronts and long rings (the top of the tree): the ring rows are also
+// split over gridDim.y CTAs, each writes its partial sums, a second kernel adds them in a fixed order.
+template <int NR>
+__global__ void __launch_bounds__(256)
+backward_mvt_split_kernel(const cplx* __restrict__ G, const cplx* __restrict__ u, cplx* __restrict__ tmp, int kmax,
+                          int mmax, int nmax, long long nb, int rows_per_split) {
+    __shared__ cplx part[8][32][NR];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long gid = (long long)blockIdx.x * 32 + lane;       // (front, E slot)
+    const bool ok = gid < nb * kmax;
+    const long long b = ok ? gid / kmax : 0;
+    const int r = ok ? (int)(gid % kmax) : 0;
+    const int c0 = blockIdx.y * rows_per_split, c1 = min(mmax, c0 + rows_per_split);
+    cplx acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
+    if (ok) {
+        const cplx* col = G + b * (long long)mmax * kmax + r;
+        const cplx* v = u + (b * nmax + kmax) * NR;
+#pragma unroll 4
+        for (int c = c0 + w; c < c1; c += 8) {
+            cplx m = ldg_c(col + (size_t)c * kmax);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) part[w][lane][j] = acc[j];
+    __syncthreads();
+    if (w == 0 && ok) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            cplx t = part[0][lane][j];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) t = cadd(t, part[q][lane][j]);
+            tmp[((long long)blockIdx.y * nb * kmax + gid) * NR + j] = t;
+        }
+    }
+}
+template <int NR>
+__global__ void backward_mvt_reduce_kernel(const cplx* __restrict__ tmp, const cplx* __restrict__ yE,
+                                           cplx* __restrict__ u, int kmax, int nmax, long long nb, int nsplit) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nb * kmax) return;
+    const long long b = gid / kmax;
+    const int r = (int)(gid % kmax);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        cplx t = make_double2(0.0, 0.0);
+        for (int q = 0; q < nsplit; ++q) t = cadd(t, tmp[((long long)q * nb * kmax + gid) * NR + j]);
+        u[(b * nmax + r) * NR + j] = csub(yE[gid * NR + j], t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -690,6 +744,8 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->comm = nullptr;
     s->ws_refine = nullptr;
     s->ws_refine_cap = 0;
+    s->ws_bsplit = nullptr;
+    s->ws_bsplit_cap = 0;
     s->xchg = nullptr;
     s->xchg_cap = 0;
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
@@ -756,6 +812,7 @@ void nd_destroy(NdSolver* s) {
     if (s->fws) cudaFree(s->fws);
     if (s->xchg) cudaFree(s->xchg);
     if (s->ws_refine) cudaFree(s->ws_refine);
+    if (s->ws_bsplit) cudaFree(s->ws_bsplit);
     delete s;
 }
 
@@ -1118,8 +1175,27 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         if (remote_child && comm_send(s->comm, u + vec_cnt, 2 * vec_cnt, Pp->recv_from, st)) return -1;
         if (from_parent && comm_recv(s->comm, u, 2 * vec_cnt, Pp->send_to, st)) return -1;
         if (nb == 0) { std::swap(u, u_par); continue; }
-        { backward_mvt_kernel<NR><<<ceil_div(nb * L.kmax, 32), 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
-                                                                           L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        const int ecta = ceil_div(nb * L.kmax, 32);
+        int nsplit = std::min(592 / ecta, L.mmax / 64);
+        if (nsplit >= 2) {
+            // few fronts, long rings: also split the ring rows over CTAs (two-pass, fixed summation order)
+            const size_t need = (size_t)nsplit * nb * L.kmax * NR;
+            if (need > s->ws_bsplit_cap) {
+                if (s->ws_bsplit) cudaFree(s->ws_bsplit);
+                s->ws_bsplit = nullptr;
+                s->ws_bsplit_cap = 0;
+                FDFD_CHECK(cudaMalloc(&s->ws_bsplit, sizeof(cplx) * need));
+                s->ws_bsplit_cap = need;
+            }
+            const int rows_per = ceil_div(L.mmax, nsplit);
+            dim3 grid(ecta, nsplit);
+            { backward_mvt_split_kernel<NR><<<grid, 256, 0, st>>>(L.G, u, s->ws_bsplit, L.kmax, L.mmax, L.nmax, nb, rows_per); ++g_fdfd_launches; }
+            { backward_mvt_reduce_kernel<NR><<<ceil_div(nb * L.kmax, 128), 128, 0, st>>>(s->ws_bsplit, s->ws_ye + L.ye_off, u,
+                                                                                          L.kmax, L.nmax, nb, nsplit); ++g_fdfd_launches; }
+        } else {
+            { backward_mvt_kernel<NR><<<ecta, 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
+                                                            L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        }
         if (L.kind == 0) {
             long long tot = nb * L.nmax;
             { leaf_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, d_x, L.cls, L.x0, L.y0, L.slot_lx, L.slot_ly,

@@ -50,6 +50,8 @@ struct NdSolver {
     size_t ws_vec_cap, ws_ring_cap, ws_ye_cap;
     cplx* ws_refine;                  // iterative-refinement residual / correction vectors
     size_t ws_refine_cap;
+    cplx* ws_bsplit;                  // partial sums of the ring-split backward product (top levels)
+    size_t ws_bsplit_cap;
     // sharded tree: communicator (not owned) and the packed Schur block in flight between two ranks
     FdfdComm* comm;
     cplx* xchg;
