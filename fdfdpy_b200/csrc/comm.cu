@@ -99,6 +99,20 @@ int comm_sendrecv(FdfdComm* c, const void* sbuf, int send_peer, void* rbuf, int 
     NCCL_CHECK(r2);
     return 0;
 }
+int comm_halo_exchange(FdfdComm* c, const void* first, const void* last, void* halo_lo, void* halo_hi, int lower,
+                       int upper, size_t count, cudaStream_t st) {
+    // one NCCL group = one fused kernel for all four transfers.  Per peer the posting order pairs the
+    // messages: with two ranks (lower == upper) the peer's first row meets the halo_hi receive, its last row
+    // the halo_lo receive.
+    NCCL_CHECK(g_nccl.GroupStart());
+    ncclResult_t r1 = g_nccl.Send(first, count, ncclDouble, lower, (ncclComm_t)c->nccl, st);
+    ncclResult_t r2 = g_nccl.Send(last, count, ncclDouble, upper, (ncclComm_t)c->nccl, st);
+    ncclResult_t r3 = g_nccl.Recv(halo_hi, count, ncclDouble, upper, (ncclComm_t)c->nccl, st);
+    ncclResult_t r4 = g_nccl.Recv(halo_lo, count, ncclDouble, lower, (ncclComm_t)c->nccl, st);
+    NCCL_CHECK(g_nccl.GroupEnd());
+    NCCL_CHECK(r1); NCCL_CHECK(r2); NCCL_CHECK(r3); NCCL_CHECK(r4);
+    return 0;
+}
 int comm_allreduce_sum(FdfdComm* c, void* buf, size_t count, cudaStream_t st) {
     NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)c->nccl, st));
     return 0;

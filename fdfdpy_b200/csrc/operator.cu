@@ -368,9 +368,7 @@ int op_halo_exchange(const FdfdOp* op, void* xv, size_t elem, cudaStream_t st) {
     }
     const int w = op->comm->world, r = op->comm->rank, lower = (r + w - 1) % w, upper = (r + 1) % w;
     // my first row is the upper halo of the rank below, my last row the lower halo of the rank above
-    if (comm_sendrecv(op->comm, first, lower, halo_hi, upper, row / 8, st)) return -1;
-    if (comm_sendrecv(op->comm, last, upper, halo_lo, lower, row / 8, st)) return -1;
-    return 0;
+    return comm_halo_exchange(op->comm, first, last, halo_lo, halo_hi, lower, upper, row / 8, st);
 }
 
 void op_destroy(FdfdOp* op) {
