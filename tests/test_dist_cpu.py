@@ -37,7 +37,7 @@ class GlooComm:
         return t.numpy().view(np.complex128)
 
 
-def _worker_direct(rank, world, port, shape, npml, pol, q):
+def _worker_direct(rank, world, port, shape, npml, pol, q, split=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -53,7 +53,8 @@ def _worker_direct(rank, world, port, shape, npml, pol, q):
         planes = orc.stencil_planes(omega, eps, 0.04, npml, pol, 1e-6)
         isxf, _, isyf, _ = orc.pml_inverse_factors(omega, 1e-6, (nx, ny), npml, 0.04)
         d = row_scale(isxf, isyf)
-        levels = shard_plan(build_plan(nx, ny), world, rank)
+        full = build_plan(nx, ny) if split is None else build_plan(nx, ny, split_min=split[0], split_parts=split[1])
+        levels = shard_plan(full, world, rank)
         comm = GlooComm(dist, torch)
         store = factor(levels, planes, nx, ny, d, tile=8, comm=comm)
         b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
@@ -67,14 +68,16 @@ def _worker_direct(rank, world, port, shape, npml, pol, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,npml,pol", [(2, (24, 20), [3, 3], "Ez"), (2, (19, 33), [0, 4], "Hz"),
-                                                  (4, (32, 28), [3, 3], "Ez")])
-def test_sharded_elimination_tree_gloo(world, shape, npml, pol):
+@pytest.mark.parametrize("world,shape,npml,pol,split", [(2, (24, 20), [3, 3], "Ez", None), (2, (19, 33), [0, 4], "Hz", None),
+                                                        (4, (32, 28), [3, 3], "Ez", None),
+                                                        (4, (32, 28), [3, 3], "Ez", (6, 3))])
+def test_sharded_elimination_tree_gloo(world, shape, npml, pol, split):
+    """split: separators eliminated piece by piece (chain levels) also on the levels shared between ranks"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_direct, args=(r, world, port, shape, npml, pol, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_direct, args=(r, world, port, shape, npml, pol, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]

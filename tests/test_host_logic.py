@@ -81,6 +81,29 @@ def test_elimination_plan_numpy_model(shape, npml, pol):
     assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-11
 
 
+@pytest.mark.parametrize("split_min,split_parts", [(6, 2), (6, 3), (5, -4)])
+def test_separator_splitting_chain_levels(split_min, split_parts):
+    """Separators eliminated piece by piece (chain levels, the production setting for >= 1000-node separators)
+    give the same solution as the one-step elimination; exercised here with tiny thresholds."""
+    from fdfdpy_b200.ndplan import build_plan
+    from tests.nd_model import factor, solve, row_scale
+    nx, ny, npml = 37, 29, [4, 3]
+    rng = np.random.default_rng(4)
+    eps = 1 + 5 * rng.random((nx, ny))
+    omega = 2 * np.pi * 200e12
+    planes = orc.stencil_planes(omega, eps, 0.04, npml, "Hz", 1e-6)
+    isxf, _, isyf, _ = orc.pml_inverse_factors(omega, 1e-6, (nx, ny), npml, 0.04)
+    d = row_scale(isxf, isyf)
+    plain = build_plan(nx, ny, split_min=10 ** 9)
+    levels = build_plan(nx, ny, split_min=split_min, split_parts=split_parts)
+    assert len(levels) > len(plain) and any(getattr(lv, "chain", False) for lv in levels)
+    assert sum(int(lv.k_cls[c]) for lv in levels for c in lv.cls) == nx * ny      # every node eliminated once
+    b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+    u = solve(levels, factor(levels, planes, nx, ny, d, tile=8), b, nx, ny, d)
+    ref = orc.sparse_solve(orc.planes_to_csr(planes), b).reshape(nx, ny)
+    assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-11
+
+
 def test_plan_structure_invariants():
     from fdfdpy_b200.ndplan import build_plan, plan_stats
     for nx, ny in [(200, 200), (300, 100), (125, 87), (64, 1000)]:
