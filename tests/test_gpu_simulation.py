@@ -220,3 +220,29 @@ def test_fused_solve_fields_call_and_pinned_pool(Simulation):
     sim.fields = {k: None for k in sim.fields}
     gc.collect()
     assert any(addr in lst for lst in _lib._pool_free.values())
+
+
+def test_input_layouts_and_lossy_media(Simulation):
+    """Inputs the reference accepts because numpy does: integer / Fortran-ordered / strided eps_r, complex
+    (lossy) eps_r, a source given as a list-built array; both polarisations, ragged (odd, non-square) grid."""
+    rng = np.random.default_rng(11)
+    omega, dl, npml = 2 * np.pi * 200e12, 0.04, [7, 9]
+    shape = (61, 47)
+    base = 1 + 4 * (rng.random(shape) > 0.5)
+    src = np.zeros(shape)
+    src[30, 20] = 1.0
+    variants = {
+        "int": base.astype(np.int64),
+        "fortran": np.asfortranarray(base),
+        "strided": np.repeat(base, 2, axis=1)[:, ::2],
+        "lossy": base * (1 + 0.05j),
+    }
+    for pol in ("Ez", "Hz"):
+        for name, eps in variants.items():
+            sim = Simulation(omega, eps, dl, npml, pol)
+            sim.src = src
+            f = sim.solve_fields()
+            ref = orc.solve_fields(omega, np.asarray(eps), dl, npml, pol, 1e-6, src)
+            for mine, theirs in zip(f, ref):
+                assert relerr(mine, theirs) < 1e-8, (pol, name)
+            assert sim.last_solve["relres"] < 1e-10
