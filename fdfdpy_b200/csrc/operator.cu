@@ -2,6 +2,7 @@
 // stencil planes of A (linalg.py:39-114), matrix-free application and the derived in-plane
 // fields (simulation.py:138-176).  All kernels are plain HBM-bound streaming kernels: the y
 // index is the fastest one in memory (derivatives.py:9-11), so threads run along y.
+#include <type_traits>
 #include "operator.cuh"
 
 thread_local char g_fdfd_err[512] = {0};
@@ -125,7 +126,7 @@ stencil_planes_kernel(const cplx* __restrict__ planes, const V* __restrict__ x, 
 // y column and marches ROWS consecutive rows keeping the x-neighbours in registers.
 // ------------------------------------------------------------------------------------------
 int g_fused_rows = 4;          // A/B switch (fdfd_stencil_set_variant): rows marched per thread
-int g_fused_rows32 = 8;        // the same for complex64 vectors (half the bytes per load: more rows in flight)
+int g_fused_rows32 = 4;        // complex64 vectors: 4 or 8 rows with two columns per thread (float4); 2 = one column per thread
 
 __device__ __forceinline__ cplx shfl_up_c(cplx v) {
     return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
@@ -227,6 +228,92 @@ stencil_fused_ez_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
         if (active) vstore(y + voff + row + iy, acc);
         xl = xcur;
         xcur = xr;
+    }
+}
+
+// complex64 variant with TWO adjacent y columns per thread: every access is a 16-byte float4 (the same bytes
+// in flight per thread as the complex128 kernel), the pair's inner y-neighbours are the thread's own values,
+// the outer ones come from the adjacent lanes.  Arithmetic is fp32 here (float coefficient tables): at
+// 24 B/cell the fp64 version was bound by the float<->double conversion rate, not by HBM; the rounding is that
+// of the complex64 storage itself.  Needs an even ny (16-byte alignment of every row).
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void cfmaf(float2& a, float2 b, float2 c) {
+    a.x = fmaf(b.x, c.x, a.x);
+    a.x = fmaf(-b.y, c.y, a.x);
+    a.y = fmaf(b.x, c.y, a.y);
+    a.y = fmaf(b.y, c.x, a.y);
+}
+__global__ void narrow_table_kernel(const cplx* __restrict__ in, cplx32* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
+}
+template <int ROWS>
+__global__ void __launch_bounds__(128)
+stencil_fused_ez_c64x2_kernel(const cplx32* __restrict__ eps_r, const cplx32* __restrict__ eps_nl,
+                              const cplx32* __restrict__ axm_t, const cplx32* __restrict__ axp_t,
+                              const cplx32* __restrict__ aym_t, const cplx32* __restrict__ ayp_t,
+                              const cplx32* __restrict__ x, cplx32* __restrict__ y, int nx, int ny, float w2e0,
+                              int row0, int row1) {
+    const int ix0 = row0 + blockIdx.y * ROWS;
+    const int rows = min(ROWS, row1 - ix0);
+    const int pair_raw = blockIdx.x * blockDim.x + threadIdx.x;          // column pair index
+    const int npair = ny >> 1;
+    const bool active = pair_raw < npair;
+    const int pr = active ? pair_raw : npair - 1;
+    const int iy = 2 * pr;                                               // columns iy, iy + 1
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)nx * ny;
+    const size_t voff = (size_t)blockIdx.z * n;
+    const cplx32* xv = x + voff;
+    const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 2 == ny ? 0 : iy + 2;
+    const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || pair_raw >= npair - 1;
+    const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
+    const float4 aym = __ldg(reinterpret_cast<const float4*>(aym_t + iy)), ayp = __ldg(reinterpret_cast<const float4*>(ayp_t + iy));
+    const float2 aym0 = make_float2(aym.x, aym.y), aym1 = make_float2(aym.z, aym.w);
+    const float2 ayp0 = make_float2(ayp.x, ayp.y), ayp1 = make_float2(ayp.z, ayp.w);
+    auto ld4 = [&](const cplx32* base, int ix) { return __ldg(reinterpret_cast<const float4*>(base + (size_t)ix * ny + iy)); };
+    float4 xc[ROWS + 2], e[ROWS];
+    xc[0] = ld4(xv, ixm);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int ix = min(ix0 + r, row1 - 1);                           // ragged last CTA: re-read the last row
+        xc[r + 1] = ld4(xv, ix);
+        e[r] = ld4(eps_r, ix);
+        if (eps_nl) { float4 t = ld4(eps_nl, ix); e[r].x += t.x; e[r].y += t.y; e[r].z += t.z; e[r].w += t.w; }
+    }
+    {
+        int ixl = ix0 + rows == nx ? 0 : ix0 + rows;
+        float4 nxt = ld4(xv, ixl);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) if (r + 1 == rows) xc[r + 2] = nxt;       // the row after the last computed one
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (r < rows) {
+            const int ix = ix0 + r;
+            const float2 axm = __ldg(axm_t + ix), axp = __ldg(axp_t + ix);
+            const float2 c_lo = make_float2(xc[r + 1].x, xc[r + 1].y), c_hi = make_float2(xc[r + 1].z, xc[r + 1].w);
+            // outer neighbours: previous lane's upper column / next lane's lower column
+            float2 dn = make_float2(__shfl_up_sync(0xffffffffu, c_hi.x, 1), __shfl_up_sync(0xffffffffu, c_hi.y, 1));
+            float2 up = make_float2(__shfl_down_sync(0xffffffffu, c_lo.x, 1), __shfl_down_sync(0xffffffffu, c_lo.y, 1));
+            if (load_dn) dn = __ldg(xv + (size_t)ix * ny + iym);
+            if (load_up) up = __ldg(xv + (size_t)ix * ny + iyp);
+            const float sx = axm.x + axp.x, sy = axm.y + axp.y;
+            float2 c0 = make_float2(e[r].x * w2e0 - sx - (aym0.x + ayp0.x), e[r].y * w2e0 - sy - (aym0.y + ayp0.y));
+            float2 acc0 = cmulf(c0, c_lo);
+            cfmaf(acc0, axm, make_float2(xc[r].x, xc[r].y));
+            cfmaf(acc0, axp, make_float2(xc[r + 2].x, xc[r + 2].y));
+            cfmaf(acc0, aym0, dn);
+            cfmaf(acc0, ayp0, c_hi);
+            float2 c1 = make_float2(e[r].z * w2e0 - sx - (aym1.x + ayp1.x), e[r].w * w2e0 - sy - (aym1.y + ayp1.y));
+            float2 acc1 = cmulf(c1, c_hi);
+            cfmaf(acc1, axm, make_float2(xc[r].z, xc[r].w));
+            cfmaf(acc1, axp, make_float2(xc[r + 2].z, xc[r + 2].w));
+            cfmaf(acc1, aym1, c_lo);
+            cfmaf(acc1, ayp1, up);
+            if (active)
+                *reinterpret_cast<float4*>(y + voff + (size_t)ix * ny + iy) = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
+        }
     }
 }
 
@@ -340,6 +427,10 @@ static int op_create_impl(FdfdOp** out, int nx, int ny, double omega, double dl,
     FDFD_CHECK(cudaMalloc(&op->ay, sizeof(cplx) * 2 * ny));
     { pml_products_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->ax, op->ax + nx, op->isxf, op->isxb, nx, 1.0 / (p.m0 * p.dx * p.dx)); ++g_fdfd_launches; }
     { pml_products_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->ay, op->ay + ny, op->isyf, op->isyb, ny, 1.0 / (p.m0 * p.dy * p.dy)); ++g_fdfd_launches; }
+    FDFD_CHECK(cudaMalloc(&op->ax32, sizeof(cplx32) * 2 * nx));
+    FDFD_CHECK(cudaMalloc(&op->ay32, sizeof(cplx32) * 2 * ny));
+    { narrow_table_kernel<<<ceil_div(2 * nx, 128), 128, 0, op->stream>>>(op->ax, op->ax32, 2 * nx); ++g_fdfd_launches; }
+    { narrow_table_kernel<<<ceil_div(2 * ny, 128), 128, 0, op->stream>>>(op->ay, op->ay32, 2 * ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
     FDFD_CHECK(cudaStreamSynchronize(op->stream));
     *out = op;
@@ -376,7 +467,7 @@ void op_destroy(FdfdOp* op) {
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
     if (op->io_buf) cudaFree(op->io_buf);
-    cudaFree(op->ax); cudaFree(op->ay);
+    cudaFree(op->ax); cudaFree(op->ay); cudaFree(op->ax32); cudaFree(op->ay32);
     if (op->eps32) cudaFree(op->eps32);
     if (op->comm_stream) { cudaStreamDestroy(op->comm_stream); cudaEventDestroy(op->ev_in); cudaEventDestroy(op->ev_halo); }
     if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
@@ -513,6 +604,21 @@ int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
     RowPlan plan;
     if (slab_begin(op, d_x, nvec, &plan)) return -1;
     AsmParams p = make_params(op);
+    if constexpr (std::is_same<V, cplx32>::value) {
+        if ((op->ny & 1) == 0 && g_fused_rows32 != 2) {              // two columns per thread, float4 accesses
+            const int rows32 = g_fused_rows32 == 8 ? 8 : 4;
+            auto k2 = rows32 == 8 ? stencil_fused_ez_c64x2_kernel<8> : stencil_fused_ez_c64x2_kernel<4>;
+            for (int i = 0; i < plan.nranges; ++i) {
+                if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+                dim3 grid(ceil_div(op->ny / 2, 128), ceil_div(plan.r1[i] - plan.r0[i], rows32), nvec);
+                k2<<<grid, 128, 0, op->stream>>>(er, enl, op->ax32, op->ax32 + op->nx, op->ay32, op->ay32 + op->ny, d_x, d_y,
+                                                 op->nx, op->ny, (float)(p.omega * p.omega * p.e0), plan.r0[i], plan.r1[i]);
+                ++g_fdfd_launches;
+            }
+            FDFD_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
     const int rows = sizeof(V) == sizeof(cplx32) ? g_fused_rows32 : g_fused_rows;
     auto kern = rows == 8 ? stencil_fused_ez_kernel<8, V> : rows == 2 ? stencil_fused_ez_kernel<2, V> : stencil_fused_ez_kernel<4, V>;
     for (int i = 0; i < plan.nranges; ++i) {

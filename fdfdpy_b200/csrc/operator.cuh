@@ -20,6 +20,7 @@ struct FdfdOp {
     cplx *isxf, *isxb, *isyf, *isyb;
     // coupling tables of the matrix-free Ez stencil: ax = [axm(nx) | axp(nx)], ay = [aym(ny) | ayp(ny)]
     cplx *ax, *ay;
+    cplx32 *ax32, *ay32;   // the same tables in complex64 for the fp32 complex64 stencil
     // permittivity planes (device, nx*ny complex128)
     cplx *eps_r, *eps_nl;
     // five stencil planes c0,cxm,cxp,cym,cyp (device, 5*nx*ny)
