@@ -565,38 +565,33 @@ child_scatter_kernel(cplx* __restrict__ uc, const cplx* __restrict__ up, const i
     for (int j = 0; j < NR; ++j) uc[(ch * nc + kc + i) * NR + j] = up[(b * nmax + slot) * NR + j];
 }
 
-// forward: yE = Einv f_E ; ring = f_R - G f_E.   One warp per output row.
+// forward: yE = Einv f_E ; ring = f_R - G f_E.   One warp per output row; the 32 lanes are 32 / NR groups of
+// NR lanes: a group walks every (32 / NR)-th column, its lanes take one right-hand side each (the matrix entry
+// is one broadcast load per group, the NR vector entries one contiguous load), groups are summed by shuffles.
 template <int NR>
 __global__ void __launch_bounds__(256)
 forward_mv_kernel(const cplx* __restrict__ Einv, const cplx* __restrict__ G, const cplx* __restrict__ f,
                   cplx* __restrict__ yE, cplx* __restrict__ ring, int kmax, int mmax, int nmax, long long nb) {
+    constexpr int NG = 32 / NR;
     long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     if (gw >= nb * nmax) return;
-    long long b = gw / nmax;
-    int r = (int)(gw % nmax);
+    const long long b = gw / nmax;
+    const int r = (int)(gw % nmax);
+    const int g = lane / NR, j = lane % NR;
     const cplx* row = r < kmax ? Einv + (b * kmax + r) * kmax : G + (b * mmax + (r - kmax)) * kmax;
     const cplx* v = f + b * nmax * NR;
-    cplx acc[NR];
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int c = g; c < kmax; c += NG) cfma(acc, ldg_c(row + c), v[c * NR + j]);
 #pragma unroll
-    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
-    for (int c = lane; c < kmax; c += 32) {
-        cplx m = ldg_c(row + c);
-#pragma unroll
-        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+    for (int o = 16; o >= NR; o >>= 1) {
+        acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
     }
-#pragma unroll
-    for (int j = 0; j < NR; ++j)
-        for (int o = 16; o > 0; o >>= 1) {
-            acc[j].x += __shfl_down_sync(0xffffffffu, acc[j].x, o);
-            acc[j].y += __shfl_down_sync(0xffffffffu, acc[j].y, o);
-        }
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            if (r < kmax) yE[(b * kmax + r) * NR + j] = acc[j];
-            else ring[(b * mmax + (r - kmax)) * NR + j] = csub(v[r * NR + j], acc[j]);
-        }
+    if (g == 0) {
+        if (r < kmax) yE[(b * kmax + r) * NR + j] = acc;
+        else ring[(b * mmax + (r - kmax)) * NR + j] = csub(v[r * NR + j], acc);
     }
 }
 
@@ -664,6 +659,30 @@ backward_mvt_kernel(const cplx* __restrict__ G, const cplx* __restrict__ yE, cpl
             u[(b * nmax + r) * NR + j] = csub(yE[(b * kmax + r) * NR + j], t);
         }
     }
+}
+
+// the same with one THREAD per E slot, for the levels of tiny fronts (k <= 16, short rings): no shared memory,
+// no barriers; the threads of a front read consecutive entries of a G row and the same ring entries.
+template <int NR>
+__global__ void __launch_bounds__(128)
+backward_mvt_thread_kernel(const cplx* __restrict__ G, const cplx* __restrict__ yE, cplx* __restrict__ u, int kmax,
+                           int mmax, int nmax, long long nb) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (front, E slot)
+    if (gid >= nb * kmax) return;
+    const long long b = gid / kmax;
+    const int r = (int)(gid % kmax);
+    const cplx* col = G + b * (long long)mmax * kmax + r;
+    const cplx* v = u + (b * nmax + kmax) * NR;
+    cplx acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
+    for (int c = 0; c < mmax; ++c) {
+        const cplx m = ldg_c(col + (size_t)c * kmax);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) cfma(acc[j], m, v[c * NR + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) u[(b * nmax + r) * NR + j] = csub(yE[gid * NR + j], acc[j]);
 }
 
 // The same product for levels with FEW fronts and long rings (the top of the tree): the ring rows are also
@@ -1177,7 +1196,10 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         if (nb == 0) { std::swap(u, u_par); continue; }
         const int ecta = ceil_div(nb * L.kmax, 32);
         int nsplit = std::min(592 / ecta, L.mmax / 64);
-        if (nsplit >= 2) {
+        if (L.kmax <= 16 && L.mmax <= 128) {
+            { backward_mvt_thread_kernel<NR><<<ceil_div(nb * L.kmax, 128), 128, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
+                                                                                       L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        } else if (nsplit >= 2) {
             // few fronts, long rings: also split the ring rows over CTAs (two-pass, fixed summation order)
             const size_t need = (size_t)nsplit * nb * L.kmax * NR;
             if (need > s->ws_bsplit_cap) {
