@@ -138,7 +138,7 @@ def run_reference(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    n_s = 256 if total > 6 else (384 if total > 2 else 512)
+    n_s = args.cpu_sample or (256 if total > 6 else (384 if total > 2 else 512))
     for _ in range(args.warmup):
         cpu_solve_sample(n_s, args.size)
     times = [cpu_solve_sample(n_s, args.size) for _ in range(args.steps)]
@@ -469,6 +469,8 @@ def main():
     ap.add_argument("--tile", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the public-API arm")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="reference arm: side of the sub-grid sample (default: chosen from steps + warmup)")
     ap.add_argument("--workload", default="solve", choices=["solve", "sweep"],
                     help="solve: the headline 4096^2 Ez solve (default); sweep: BASELINE config 4")
     args = ap.parse_args()

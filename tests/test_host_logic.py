@@ -118,3 +118,18 @@ def test_plan_structure_invariants():
         assert stored > 0 and transient > 0 and macs > 0
     with pytest.raises(ValueError):
         build_plan(3, 50)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample", "96"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mcell/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("Ez 4096x4096")
