@@ -33,3 +33,24 @@ def test_sharded_direct_solver_vs_oracle(world, pol):
     assert out["rank0"]["parity_relres"] < 1e-10
     for o in [out["rank0"]] + out["others"]:
         assert o["ranks_agree"]
+
+
+@pytest.mark.parametrize("world,pol", [(2, "Ez"), (2, "Hz")])
+def test_slab_stencil_and_krylov_vs_oracle(world, pol):
+    """Slab operator over NCCL: halo exchange (overlapped with the interior rows), distributed BiCGSTAB / COCG
+    with all-reduced inner products, against the oracle's matrix and sparse solve."""
+    if _gpu_count() < world:
+        pytest.skip("needs {} GPUs".format(world))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29560 + world), os.path.join(ROOT, "tools", "dist_check.py"),
+           "--parity", "", "--slab-parity", "40x36", "--pol", pol]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    for o in [out["rank0"]] + out["others"]:
+        assert o["slab_apply_rel_err"] < 1e-13
+        if pol == "Ez":
+            assert o["slab_apply_fused_rel_err"] < 1e-13
+        for method in ("slab_bicgstab", "slab_cocg"):
+            assert o[method]["relres"] < 1e-8, (method, o[method])
+            assert o[method]["rel_l2_vs_oracle"] < 1e-6, (method, o[method])
