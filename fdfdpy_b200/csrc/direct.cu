@@ -341,10 +341,12 @@ __device__ __forceinline__ cplx small_front_gather(const SmallFrontArgs& a, cons
     return v;
 }
 
-template <int KMAX>
+// KT / MT > 0: front sizes known at compile time (the levels of a power-of-two grid), so the index arithmetic
+// folds to constants and the short inner products unroll; 0: taken from the arguments.
+template <int KMAX, int KT = 0, int MT = 0>
 __global__ void small_front_kernel(SmallFrontArgs a) {
     extern __shared__ __align__(16) unsigned char sf_smem[];
-    const int k = a.kmax, m = a.mmax, n = k + m, w2 = 2 * k;
+    const int k = KT ? KT : a.kmax, m = MT ? MT : a.mmax, n = k + m, w2 = 2 * k;
     cplx* W = reinterpret_cast<cplx*>(sf_smem);      // [k][2k]: row r = [ E[r][:] | Einv[r][:] ]
     cplx* R = W + (size_t)k * w2;                     // [m][k]   F_RE
     cplx* Gs = R + (size_t)m * k;                     // [m][k]   G
@@ -406,7 +408,8 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
     for (int e = tid; e < m * k; e += nt) {
         int i = e / k, cc = e - i * k;
         cplx acc = zero;
-        for (int l = 0; l < k; ++l) cfma(acc, R[i * k + l], W[l * w2 + k + cc]);
+#pragma unroll
+        for (int l = 0; l < (KT ? KT : k); ++l) cfma(acc, R[i * k + l], W[l * w2 + k + cc]);
         Gs[e] = acc;
         Go[e] = acc;
     }
@@ -417,8 +420,8 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
         int i = e / m, j = e - i * m;
         if (j > i) continue;
         cplx acc = leaf ? Sm[e] : small_front_gather(a, S1, S2, s_i1, s_i2, k + i, k + j);
-#pragma unroll 5
-        for (int l = 0; l < k; ++l) {
+#pragma unroll
+        for (int l = 0; l < (KT ? KT : k); ++l) {
             cplx g = Gs[i * k + l], r = R[j * k + l];
             acc.x -= g.x * r.x - g.y * r.y;
             acc.y -= g.x * r.y + g.y * r.x;
@@ -1020,10 +1023,17 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
             size_t smem = small_front_smem(kmax, mmax, L.kind == 0);
             int threads = nmax <= 40 ? 64 : (nmax <= 64 ? 128 : 256);
-            auto kern = kmax <= 3 ? small_front_kernel<3>
-                        : kmax <= 7 ? small_front_kernel<7>
-                        : kmax <= 9 ? small_front_kernel<9>
-                        : kmax <= 12 ? small_front_kernel<12> : small_front_kernel<16>;
+            void (*kern)(SmallFrontArgs) = kmax <= 3 ? small_front_kernel<3>
+                                           : kmax <= 7 ? small_front_kernel<7>
+                                           : kmax <= 9 ? small_front_kernel<9>
+                                           : kmax <= 12 ? small_front_kernel<12> : small_front_kernel<16>;
+            // the bottom levels of a power-of-two grid (4-cell leaves): sizes as compile-time constants
+            if (kmax == 9 && mmax == 16) kern = small_front_kernel<9, 9, 16>;
+            else if (kmax == 3 && mmax == 24) kern = small_front_kernel<3, 3, 24>;
+            else if (kmax == 7 && mmax == 32) kern = small_front_kernel<7, 7, 32>;
+            else if (kmax == 7 && mmax == 48) kern = small_front_kernel<7, 7, 48>;
+            else if (kmax == 15 && mmax == 64) kern = small_front_kernel<16, 15, 64>;
+            else if (kmax == 15 && mmax == 96) kern = small_front_kernel<16, 15, 96>;
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
