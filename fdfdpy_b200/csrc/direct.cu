@@ -65,14 +65,15 @@ __global__ void __launch_bounds__(256)
 merge_assemble_kernel(cplx* __restrict__ F, const cplx* __restrict__ Fc, const int* __restrict__ cls,
                       const int* __restrict__ k_cls, const int* __restrict__ ch1, const int* __restrict__ ch2,
                       const int* __restrict__ inv1, const int* __restrict__ inv2, int kmax, int nmax,
-                      int kc, int nc, int chunks) {
+                      int kc, int nc, long long cstride, int chunks) {
+    // children's Schur blocks: batch stride cstride, leading dimension nc, first ring entry at (kc, kc)
     const long long b = blockIdx.x / chunks;
     const int r0 = (int)(blockIdx.x % chunks) * ASM_ROWS;
     const int c = cls[b];
     const int* i1 = inv1 + (size_t)c * nmax;
     const int* i2 = inv2 + (size_t)c * nmax;
-    const cplx* S1 = Fc + (long long)ch1[b] * nc * nc + (size_t)kc * nc + kc;
-    const cplx* S2 = Fc + (long long)ch2[b] * nc * nc + (size_t)kc * nc + kc;
+    const cplx* S1 = Fc + (long long)ch1[b] * cstride + (size_t)kc * nc + kc;
+    const cplx* S2 = Fc + (long long)ch2[b] * cstride + (size_t)kc * nc + kc;
     cplx* Fb = F + b * (long long)nmax * nmax;
     const int kcls = k_cls[c];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -461,17 +462,17 @@ transpose_kernel(const cplx* src, long long s_stride, int s_ld, cplx* dst, long 
 
 // Einv[b] (kmax x kmax, full) = symmetric expansion of the lower triangle of F[b][0:kmax, 0:kmax]
 __global__ void __launch_bounds__(256)
-sym_expand_kernel(const cplx* __restrict__ F, cplx* __restrict__ E, int kmax, int nmax, int chunks) {
+sym_expand_kernel(const cplx* __restrict__ F, cplx* __restrict__ E, int kmax, int ld, long long fstride, int chunks) {
     const long long b = blockIdx.x / chunks;
     const int chunk = blockIdx.x % chunks;
-    const cplx* Fb = F + b * (long long)nmax * nmax;
+    const cplx* Fb = F + b * fstride;
     cplx* Eb = E + b * (long long)kmax * kmax;
     const long long total = (long long)kmax * kmax;
     const long long per = (total + chunks - 1) / chunks;
     const long long e0 = chunk * per, e1 = min(total, e0 + per);
     for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         int p = (int)(e / kmax), q = (int)(e % kmax);
-        Eb[e] = Fb[(size_t)max(p, q) * nmax + min(p, q)];
+        Eb[e] = Fb[(size_t)max(p, q) * ld + min(p, q)];
     }
 }
 
@@ -775,6 +776,13 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     return 0;
 }
 
+// Switch (environment FDFD_INPLACE_CHAINS=1): chain levels work in place on the previous Schur blocks instead of
+// re-assembling their fronts.  Off by default until it has been measured on the GPU.
+static bool inplace_chains_enabled() {
+    const char* e = getenv("FDFD_INPLACE_CHAINS");
+    return e && e[0] == '1';
+}
+
 int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
     NdLevel L;
     memset(&L, 0, sizeof(L));
@@ -808,6 +816,20 @@ int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
                 if (b >= 0) i2[(size_t)c * L.nmax + b] = i;
             }
         if (upload_i32(&L.inv1, i1.data(), i1.size()) || upload_i32(&L.inv2, i2.data(), i2.size())) return -1;
+        // chain level whose front IS the previous level's Schur block, slot for slot (same fronts, one child,
+        // identity map, no padded pivots): it is factorised in place, without an assembly pass
+        const NdLevel& P = s->levels.back();
+        bool ip = inplace_chains_enabled() && d->nb == P.nb && L.nmax == d->child_mmax && d->child_mmax == P.mmax &&
+                  L.send_to < 0 && L.recv_from < 0 && P.kmax > 16;
+        for (int b = 0; ip && b < d->nb; ++b) ip = d->ch1[b] == b && d->ch2[b] == b;
+        for (int c = 0; ip && c < d->ncls; ++c) {
+            ip = d->k_cls[c] == d->kmax;
+            for (int i = 0; ip && i < d->child_mmax; ++i) {
+                const int a = d->c1map[(size_t)c * d->child_mmax + i], b2 = d->c2map[(size_t)c * d->child_mmax + i];
+                ip = b2 < 0 && (a == i || a < 0);
+            }
+        }
+        L.inplace = ip ? 1 : 0;
     }
     s->levels.push_back(L);
     s->factored = false;
@@ -945,7 +967,10 @@ static int ensure_factor_workspace(NdSolver* s) {
     for (size_t li = 0; li < s->levels.size(); ++li) {
         NdLevel& L = s->levels[li];
         // one extra slot where the parent level receives its second child from another rank
-        const bool extra = li + 1 < s->levels.size() && s->levels[li + 1].recv_from >= 0;
+        // (levels factorised in place live in the buffer of the level that started their chain)
+        size_t lj = li + 1;
+        while (lj < s->levels.size() && s->levels[lj].inplace) ++lj;
+        const bool extra = lj < s->levels.size() && s->levels[lj].recv_from >= 0;
         const size_t nb = L.nb + (extra ? 1 : 0), nmax = L.nmax;
         maxF = std::max(maxF, nb * nmax * nmax);
         maxW = std::max(maxW, (size_t)L.nb * inv_ws_need(L.kmax));
@@ -979,8 +1004,11 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     s->factored = false;
     if (ensure_factor_workspace(s)) return -1;
     FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
+    // the previous level's Schur blocks: batch base, first ring entry at (prev_k, prev_k), leading dimension
+    // prev_n, batch stride prev_stride, ring size prev_m
     cplx* Fprev = nullptr;
-    int prev_k = 0, prev_n = 0;
+    int prev_k = 0, prev_n = 0, prev_m = 0, cur = 1;
+    long long prev_stride = 0;
     s->factor_bytes = 0;
     s->factor_flops = 0;
     for (size_t li = 0; li < s->levels.size(); ++li) {
@@ -988,12 +1016,26 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         g_phase_timing.level = (int)li;
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
-        cplx* F = s->fws_F[li & 1];
+        // A chain level that continues the elimination of the same fronts works IN PLACE on the previous Schur
+        // blocks (its front is that block, slot for slot); every other level assembles into the other buffer.
+        cplx* F;
+        int ld;
+        long long fstride;
+        if (L.inplace && nb > 0) {
+            F = Fprev + (size_t)prev_k * prev_n + prev_k;
+            ld = prev_n;
+            fstride = prev_stride;
+        } else {
+            cur ^= 1;
+            F = s->fws_F[cur];
+            ld = nmax;
+            fstride = (long long)nmax * nmax;
+        }
         if (L.send_to >= 0 || L.recv_from >= 0) {
             // sharded tree: the second child's Schur block crosses NVLink as a packed m x m square and lands
             // in slot 1 of the child batch, in the layout the local child has (ch2 of this level points there)
             if (!s->comm) FDFD_FAIL("sharded elimination plan without a communicator (fdfd_direct_set_comm)");
-            const size_t m = (size_t)(prev_n - prev_k), pitch_f = sizeof(cplx) * prev_n, pitch_x = sizeof(cplx) * m;
+            const size_t m = (size_t)prev_m, pitch_f = sizeof(cplx) * prev_n, pitch_x = sizeof(cplx) * m;
             if ((int)m != L.child_mmax || !Fprev) FDFD_FAIL("sharded plan: child block size mismatch");
             PhaseScope ph(PH_COPY, st);
             if (L.send_to >= 0) {
@@ -1002,7 +1044,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                 if (comm_send(s->comm, s->xchg, 2 * m * m, L.send_to, st)) return -1;
             } else {
                 if (comm_recv(s->comm, s->xchg, 2 * m * m, L.recv_from, st)) return -1;
-                FDFD_CHECK(cudaMemcpy2DAsync(Fprev + (size_t)prev_n * prev_n + (size_t)prev_k * prev_n + prev_k, pitch_f,
+                FDFD_CHECK(cudaMemcpy2DAsync(Fprev + prev_stride + (size_t)prev_k * prev_n + prev_k, pitch_f,
                                              s->xchg, pitch_x, pitch_x, m, cudaMemcpyDeviceToDevice, st));
             }
         }
@@ -1019,7 +1061,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             a.slot_right = L.slot_right; a.slot_up = L.slot_up;
             a.ch1 = L.ch1; a.ch2 = L.ch2; a.inv1 = L.inv1; a.inv2 = L.inv2;
             a.planes = op->planes; a.isxf = op->isxf; a.isyf = op->isyf;
-            a.Sc = Fprev; a.sc = (long long)prev_n * prev_n; a.kc = prev_k; a.nc = prev_n;
+            a.Sc = Fprev; a.sc = prev_stride; a.kc = prev_k; a.nc = prev_n;
             a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
             size_t smem = small_front_smem(kmax, mmax, L.kind == 0);
             int threads = nmax <= 40 ? 64 : (nmax <= 64 ? 128 : 256);
@@ -1048,9 +1090,11 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             Fprev = F;
             prev_k = 0;
             prev_n = mmax;
+            prev_m = mmax;
+            prev_stride = (long long)mmax * mmax;
             continue;
         }
-        {
+        if (!L.inplace) {
             PhaseScope ph(PH_ASSEMBLE, st);
             if (L.kind == 0) {
                 leaf_assemble_kernel<<<(unsigned)nb, 64, 0, st>>>(F, op->planes, op->isxf, op->isyf, L.cls, L.k_cls,
@@ -1060,7 +1104,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                 int chunks = (nmax + ASM_ROWS - 1) / ASM_ROWS;
                 merge_assemble_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, Fprev, L.cls, L.k_cls, L.ch1, L.ch2,
                                                                                L.inv1, L.inv2, kmax, nmax, prev_k,
-                                                                               prev_n, chunks);
+                                                                               prev_n, prev_stride, chunks);
             }
             ++g_fdfd_launches;
         }
@@ -1068,13 +1112,12 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         // ---- Einv = F_EE^-1
         if (kmax <= 64) {
             PhaseScope ph(PH_PIVOT, st);
-            launch_tile_inverse(F, (long long)nmax * nmax, nmax, kmax, L.Einv, (long long)kmax * kmax, kmax, s->d_info,
-                                1, nb, st);
+            launch_tile_inverse(F, fstride, ld, kmax, L.Einv, (long long)kmax * kmax, kmax, s->d_info, 1, nb, st);
         } else {
             {
                 PhaseScope ph(PH_EXTRACT, st);
                 int chunks = chunks_for((long long)kmax * kmax, nb);
-                sym_expand_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.Einv, kmax, nmax, chunks);
+                sym_expand_kernel<<<(unsigned)(nb * chunks), 256, 0, st>>>(F, L.Einv, kmax, ld, fstride, chunks);
                 ++g_fdfd_launches;
             }
             if (sym_invert_batch(s, L.Einv, (long long)kmax * kmax, kmax, kmax, nb, s->fws_W, st)) return -1;
@@ -1084,7 +1127,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             GemmBatch g;
             // ---- G = F_RE Einv = F_RE Einv^T (Einv is symmetric: both operands k-contiguous)
             g.transb = 1; g.lower = 0; g.mode = 0; g.batch = (int)nb;
-            g.A = F + (size_t)kmax * nmax; g.sA = (long long)nmax * nmax; g.lda = nmax;
+            g.A = F + (size_t)kmax * ld; g.sA = fstride; g.lda = ld;
             g.B = L.Einv; g.sB = (long long)kmax * kmax; g.ldb = kmax;
             g.C = L.G; g.sC = (long long)mmax * kmax; g.ldc = kmax;
             g.M = mmax; g.N = kmax; g.K = kmax;
@@ -1095,8 +1138,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             // ---- S = F_RR - G F_RE^T, lower tiles only, in place (the parent assembles from it)
             g.transb = 1; g.lower = 1; g.mode = 1;
             g.A = L.G; g.sA = (long long)mmax * kmax; g.lda = kmax;
-            g.B = F + (size_t)kmax * nmax; g.sB = (long long)nmax * nmax; g.ldb = nmax;
-            g.C = F + (size_t)kmax * nmax + kmax; g.sC = (long long)nmax * nmax; g.ldc = nmax;
+            g.B = F + (size_t)kmax * ld; g.sB = fstride; g.ldb = ld;
+            g.C = F + (size_t)kmax * ld + kmax; g.sC = fstride; g.ldc = ld;
             g.M = mmax; g.N = mmax; g.K = kmax;
             {
                 PhaseScope ph(PH_SCHUR, st);
@@ -1107,7 +1150,9 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         s->factor_bytes += sizeof(cplx) * ((size_t)nb * kmax * kmax + (size_t)nb * mmax * kmax);
         Fprev = F;
         prev_k = kmax;
-        prev_n = nmax;
+        prev_n = ld;
+        prev_m = mmax;
+        prev_stride = fstride;
     }
     g_phase_timing.level = -1;
     int info = 0;

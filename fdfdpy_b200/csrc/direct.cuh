@@ -32,6 +32,7 @@ struct NdLevel {
     cplx* yE;     // solve workspace [nb][kmax][nrhs]
     size_t ye_off;
     int send_to, recv_from;
+    int inplace;  // chain level factorised in place on the previous level's Schur blocks (no assembly pass)
 };
 
 struct NdSolver {

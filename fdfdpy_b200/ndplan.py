@@ -202,7 +202,10 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
         kfull = max(len(f[0]) for f in fronts)
         want = split_parts if split_parts > 0 else max(1, min(8, int(round(kfull / float(-split_parts)))))
         nparts = want if (want > 1 and kfull >= split_min and min(len(f[0]) for f in fronts) >= want) else 1
-        cuts = [_parts(len(f[0]), nparts) for f in fronts]              # per class
+        # pieces are identical for every shape class except the last one, which absorbs the (<= 2 node) size
+        # differences: the intermediate chain levels then have no padded pivots and are factorised in place
+        base = _parts(min(len(f[0]) for f in fronts), nparts)
+        cuts = [base[:-1] + [len(f[0])] for f in fronts]                  # per class
         child_mmax = levels[-1].mmax
         for part in range(nparts):
             if part > 0:
