@@ -776,11 +776,11 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     return 0;
 }
 
-// Switch (environment FDFD_INPLACE_CHAINS=1): chain levels work in place on the previous Schur blocks instead of
-// re-assembling their fronts.  Off by default until it has been measured on the GPU.
+// A/B switch (environment FDFD_INPLACE_CHAINS=0): chain levels re-assemble their fronts instead of working in
+// place on the previous Schur blocks
 static bool inplace_chains_enabled() {
     const char* e = getenv("FDFD_INPLACE_CHAINS");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 int nd_add_level(NdSolver* s, const NdLevelDesc* d) {
