@@ -70,6 +70,15 @@ def _ring(w, h, xclosed, yclosed, nx, ny):
     return pts
 
 
+def _class_table(sid, xs, ys):
+    """Shape class of every leaf box (i, j) -> sid[(xs[i], ys[j])], without a Python loop over the boxes."""
+    ux, uy = sorted(set(xs.tolist())), sorted(set(ys.tolist()))
+    table = np.array([[sid[(w, h)] for h in uy] for w in ux], dtype=np.int32)
+    xi = np.array([ux.index(w) for w in xs.tolist()])
+    yi = np.array([uy.index(h) for h in ys.tolist()])
+    return table[xi[:, None], yi[None, :]].ravel()
+
+
 class Level:
     """One batch of fronts.  Attribute names are the ones the C ABI takes (include/fdfd_b200.h)."""
     pass
@@ -101,7 +110,7 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
     lv.px, lv.py, lv.nb = px, py, px * py
     W, H = np.meshgrid(xs, ys, indexing="ij")
     X0, Y0 = np.meshgrid(x0, y0, indexing="ij")
-    lv.cls = np.array([sid[(int(w), int(h))] for w, h in zip(W.ravel(), H.ravel())], dtype=np.int32)
+    lv.cls = _class_table(sid, xs, ys)
     lv.x0 = X0.ravel().astype(np.int32)
     lv.y0 = Y0.ravel().astype(np.int32)
     lv.k_cls = np.array([(w - 1) * (h - 1) for w, h in shapes], dtype=np.int32)
@@ -157,21 +166,24 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
         lv.axis = axis
         lv.px, lv.py, lv.nb = npx, npy, npx * npy
         I, J = np.meshgrid(np.arange(npx), np.arange(npy), indexing="ij")
+        # shape key of front (i, j): (first child's extent, second child's extent, extent along the other axis)
         if axis == 0:
             c1 = (2 * I) * child_py + J
             c2 = (2 * I + 1) * child_py + J
-            key = [(int(cur_xs[2 * i]), int(cur_xs[2 * i + 1]), int(cur_ys[j]))
-                   for i, j in zip(I.ravel(), J.ravel())]
+            pairs, other = list(zip(cur_xs[0::2].tolist(), cur_xs[1::2].tolist())), cur_ys.tolist()
         else:
             c1 = I * child_py + 2 * J
             c2 = I * child_py + 2 * J + 1
-            key = [(int(cur_ys[2 * j]), int(cur_ys[2 * j + 1]), int(cur_xs[i]))
-                   for i, j in zip(I.ravel(), J.ravel())]
+            pairs, other = list(zip(cur_ys[0::2].tolist(), cur_ys[1::2].tolist())), cur_xs.tolist()
         lv.ch1 = c1.ravel().astype(np.int32)
         lv.ch2 = c2.ravel().astype(np.int32)
-        pshapes = sorted(set(key))
+        pshapes = sorted({(a, b, o) for a, b in set(pairs) for o in set(other)})
         psid = {s: i for i, s in enumerate(pshapes)}
-        lv.cls = np.array([psid[k] for k in key], dtype=np.int32)
+        upairs, uother = sorted(set(pairs)), sorted(set(other))
+        table = np.array([[psid[(a, b, o)] for o in uother] for a, b in upairs], dtype=np.int32)
+        pcode = np.array([upairs.index(pr) for pr in pairs])
+        ocode = np.array([uother.index(o) for o in other])
+        lv.cls = (table[pcode[:, None], ocode[None, :]] if axis == 0 else table[pcode[None, :], ocode[:, None]]).ravel()
         lv.ncls = len(pshapes)
 
         fronts = []
