@@ -1179,20 +1179,28 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         ye_need += (size_t)L.nb * L.kmax * NR;
     }
     ye_need = std::max(ye_need, (size_t)1);
+    // grow-only workspaces: pointer and capacity are reset BEFORE the new allocation, so a failed cudaMalloc
+    // (out of memory is realistic next to tens of GB of factors) leaves a consistent, empty workspace behind
     if (vec_need > s->ws_vec_cap) {
         cudaFree(s->ws_a); cudaFree(s->ws_b);
+        s->ws_a = s->ws_b = nullptr;
+        s->ws_vec_cap = 0;
         FDFD_CHECK(cudaMalloc(&s->ws_a, sizeof(cplx) * vec_need));
         FDFD_CHECK(cudaMalloc(&s->ws_b, sizeof(cplx) * vec_need));
         s->ws_vec_cap = vec_need;
     }
     if (ring_need > s->ws_ring_cap) {
         cudaFree(s->ws_ring_a); cudaFree(s->ws_ring_b);
+        s->ws_ring_a = s->ws_ring_b = nullptr;
+        s->ws_ring_cap = 0;
         FDFD_CHECK(cudaMalloc(&s->ws_ring_a, sizeof(cplx) * ring_need));
         FDFD_CHECK(cudaMalloc(&s->ws_ring_b, sizeof(cplx) * ring_need));
         s->ws_ring_cap = ring_need;
     }
     if (ye_need > s->ws_ye_cap) {
         cudaFree(s->ws_ye);
+        s->ws_ye = nullptr;
+        s->ws_ye_cap = 0;
         FDFD_CHECK(cudaMalloc(&s->ws_ye, sizeof(cplx) * ye_need));
         s->ws_ye_cap = ye_need;
     }

@@ -45,7 +45,9 @@ class Simulation:
         self.xrange = [0, float(self.Nx * self.dl)]
         self.yrange = [0, float(self.Ny * self.dl)]
         self.timings = {}
+        self.last_solve = None  # residual / iteration record of the most recent linear solve
         self._op = None        # linear operator A(eps_r) and its cached factorisation
+        self._derivs = None
         self._op_nl = None     # work operator for A + Anl and the Newton Jacobian
         self.nl_strategy = 'reuse'   # 'reuse': linear factors precondition the nonlinear solves;
         #                              'refactor': factorise A + Anl every time, as the reference does
@@ -69,10 +71,7 @@ class Simulation:
             raise FdfdInputError("dl must be a single positive number, was supplied {}".format(dl))
         if not real_scalar(L0) or not float(L0) > 0:
             raise FdfdInputError("L0 must be a positive number, was supplied {},".format(str(L0)))
-        if not isinstance(eps_r, np.ndarray) or eps_r.ndim != 2:
-            raise FdfdInputError("eps_r must be a 2-D numpy array")
-        if np.any(np.real(eps_r) < 0):
-            raise FdfdInputError("eps_r must not be negative")
+        Simulation._check_eps(eps_r)
         try:
             n_npml = len(NPML)
         except TypeError:
@@ -87,15 +86,50 @@ class Simulation:
         if not isinstance(pol, str) or pol not in ('Ez', 'Hz'):
             raise FdfdInputError("pol must be one of 'Ez' or 'Hz'")
 
+    @staticmethod
+    def _check_eps(eps_r):
+        """Shared by the constructor and the eps_r setter."""
+        if not isinstance(eps_r, np.ndarray) or eps_r.ndim != 2:
+            raise FdfdInputError("eps_r must be a 2-D numpy array")
+        if np.any(np.real(eps_r) < 0):
+            raise FdfdInputError("eps_r must not be negative")
+        if min(eps_r.shape) < 4:
+            # the reference accepts degenerate grids (e.g. Ny = 1); the structured solver's elimination tree
+            # needs 4 cells per axis, and this is the place to say so (not the first solve_fields)
+            raise FdfdInputError("the B200 solver needs at least 4 cells per axis, got a {} grid".format(eps_r.shape))
+
+    _DEVICE_STATE = ('_op', '_op_nl', '_derivs')
+
     def __deepcopy__(self, memo):
-        """Device handles are not copied: the twin rebuilds its operator from the same inputs."""
-        twin = Simulation(self.omega, np.array(self.eps_r), self.dl, list(self.NPML), self.pol, self.L0)
-        twin.src = np.array(self.src)
-        twin.modes = list(self.modes)
-        twin.nonlinearity = list(self.nonlinearity)
-        twin.nl_strategy = self.nl_strategy
+        """Everything the reference's ``deepcopy(simulation)`` preserves (fields, sources, modes, nonlinearity,
+        normalisation) is copied; device handles are not: the twin owns no operator until its ``eps_r`` is
+        assigned or its first solve builds one from the copied permittivity (no redundant assembly when the
+        caller replaces eps_r right away, as ``mode.compute_normalization`` does)."""
+        twin = Simulation.__new__(Simulation)
         memo[id(self)] = twin
+        for key, val in self.__dict__.items():
+            if key in self._DEVICE_STATE:
+                continue
+            twin.__dict__[key] = deepcopy(val, memo)
+        twin._op = twin._op_nl = twin._derivs = None
         return twin
+
+    def _ensure_operator(self):
+        if self._op is None:
+            self._op = MaxwellOperator(self.omega, self.__eps_r, self.dl, self.NPML, self.pol, self.L0)
+            self._op_nl = None
+            self._derivs = _LazyDerivs(self._op)
+        return self._op
+
+    @property
+    def A(self):
+        """The system operator (simulation.py:38 keeps the scipy matrix here; this is the device-resident one)."""
+        return self._ensure_operator()
+
+    @property
+    def derivs(self):
+        self._ensure_operator()
+        return self._derivs
 
     # ------------------------------------------------------------------ operator
     @property
@@ -107,7 +141,11 @@ class Simulation:
         """Reassigning eps_r re-assembles A on the device and drops the cached factorisation
         (simulation.py:80-89)."""
         new_eps = np.asarray(new_eps)
+        self._check_eps(new_eps)
+        if (int(self.NPML[0]) >= new_eps.shape[0] or int(self.NPML[1]) >= new_eps.shape[1]):
+            raise FdfdInputError("NPML {} does not fit in a {} grid".format(list(self.NPML), new_eps.shape))
         self.__eps_r = new_eps
+        (self.Nx, self.Ny) = new_eps.shape
         t = time()
         if self._op is not None and (self._op.nx, self._op.ny) == new_eps.shape:
             self._op.assemble(new_eps)
@@ -117,8 +155,7 @@ class Simulation:
             self._op = MaxwellOperator(self.omega, new_eps, self.dl, self.NPML, self.pol, self.L0)
             self._op_nl = None
         self.timings['assemble'] = time() - t
-        self.A = self._op
-        self.derivs = _LazyDerivs(self._op)
+        self._derivs = _LazyDerivs(self._op)
         self.fields = _blank_fields()
         self.fields_nl = _blank_fields()
 
@@ -167,7 +204,7 @@ class Simulation:
         return self._op_nl
 
     def _linear_factors(self):
-        d = self._op.direct()
+        d = self._ensure_operator().direct()
         if not d.factored:
             t = time()
             d.factor()
@@ -193,7 +230,7 @@ class Simulation:
         if s not in DIRECT_SOLVERS + KRYLOV_SOLVERS:
             raise ValueError('Invalid solver choice: {}, options are pardiso or scipy'.format(str(solver)))
         src = np.asarray(self.src)
-        op = self._op if not include_nl else self._nl_operator(self.eps_nl)
+        op = self._ensure_operator() if not include_nl else self._nl_operator(self.eps_nl)
         if not include_nl and s in DIRECT_SOLVERS and src.any():
             # the hot path: one library call, b = i w src formed on the device
             d = self._linear_factors()

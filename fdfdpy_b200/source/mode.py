@@ -13,7 +13,18 @@ class ModeOperator:
     shifted solves and the Rayleigh-Ritz iteration happen on the device."""
 
     def __init__(self, eps_line, omega, dl, pol, L0, averaged):
-        self.eps_line = np.real(np.asarray(eps_line)).reshape(-1)
+        line = np.asarray(eps_line).reshape(-1)
+        # The CUDA mode kernel solves the REAL symmetric eigenproblem (for Hz it symmetrises with sqrt(eps)).
+        # The reference hands a complex matrix to ARPACK, so lossy or metallic cross-sections work there; here
+        # they would silently lose their imaginary part / give NaN, so they are rejected.
+        if np.iscomplexobj(line) and np.any(np.abs(np.imag(line)) > 1e-12 * np.max(np.abs(line))):
+            raise ValueError("modal source: the permittivity on the source line must be real (lossless); "
+                             "got complex values")
+        line = np.real(line)
+        if line.size < 3 or not np.all(line > 0) or not np.all(np.isfinite(line)):
+            raise ValueError("modal source: the permittivity on the source line must be positive and finite "
+                             "on at least 3 cells")
+        self.eps_line = line
         self.omega, self.dl, self.pol, self.L0, self.averaged = omega, dl, pol, L0, bool(averaged)
         n = self.eps_line.size
         self.shape = (n, n)
@@ -23,7 +34,10 @@ class ModeOperator:
         neff = np.sqrt(sigma) / (self.omega * np.sqrt(MU_0 * self.L0 * EPSILON_0 * self.L0))
         vals, vecs = mode_solve(self.eps_line, self.omega, self.dl, self.pol, self.L0, neff, order=k,
                                 averaged=self.averaged)
-        for v in vecs:          # deterministic sign: the largest-magnitude component is positive
+        # ARPACK's eigenvector sign is arbitrary (it depends on its random start vector), so a source built from
+        # it -- and every field it drives -- is defined up to a global factor -1 in the reference.  Here the sign
+        # is fixed: the largest-magnitude component is positive.
+        for v in vecs:
             if v[np.argmax(np.abs(v))] < 0:
                 v *= -1
         return vals.astype(np.complex128), vecs.T.astype(np.complex128)

@@ -105,7 +105,13 @@ void fdfd_direct_destroy(fdfd_direct* s);
 int fdfd_direct_factor(fdfd_direct* s, fdfd_op* op);
 int fdfd_direct_stats(fdfd_direct* s, double* factor_bytes, double* factor_flops);
 /* x = A^-1 b for nrhs right-hand sides [nrhs][nx*ny], followed by up to max_refine steps of
- * iterative refinement with the fp64 stencil residual; relres = max_j ||b_j - A x_j|| / ||b_j||. */
+ * iterative refinement with the fp64 stencil residual; relres = max_j ||b_j - A x_j|| / ||b_j||.
+ * Residual contract (the reference's pivoted LU is accurate by construction, linalg.py:139-146; the
+ * block factorisation here is not): with max_refine >= 1, a residual still above max(tol, 1e-10)
+ * after the refinement steps sends the system to BiCGSTAB preconditioned by the same factors, and
+ * the call FAILS (-1) if the limit is missed even then -- it never returns a silently wrong field.
+ * refine_steps = refinement steps (+ 1000 + Krylov iterations when that fallback ran).
+ * max_refine == 0: raw substitution, residual reported, no guard; < 0: no residual evaluation.   */
 int fdfd_direct_solve_host(fdfd_direct* s, fdfd_op* op, const double* b_c128, double* x_c128, int nrhs,
                            int max_refine, double tol, double* relres, int* refine_steps);
 int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_x, int nrhs,

@@ -179,12 +179,13 @@ def test_krylov_small(core):
     b[20, 18] = 1j * OMEGA
     A = orc.construct_A(OMEGA, eps, 0.05, npml, "Ez", 1e-6)
     ref = orc.sparse_solve(A, b).reshape(nx, ny)
-    x, info = op.krylov(b, method="bicgstab", tol=1e-11, maxiter=20000, check_every=20)
-    assert info["relres"] < 1e-9, info
-    assert relerr(x, ref) < 1e-6
-    x, info = op.krylov(b, method="cocg", tol=1e-11, maxiter=20000, check_every=20)
-    assert info["relres"] < 1e-8, info
-    assert relerr(x, ref) < 1e-6
+    # north_star's bar for fp64 fields: relative L2 error <= 1e-8 against the reference's solve
+    x, info = op.krylov(b, method="bicgstab", tol=1e-12, maxiter=20000, check_every=20)
+    assert info["relres"] < 1e-10, info
+    assert relerr(x, ref) < 1e-8
+    x, info = op.krylov(b, method="cocg", tol=1e-12, maxiter=20000, check_every=20)
+    assert info["relres"] < 1e-10, info
+    assert relerr(x, ref) < 1e-8
     # preconditioned by the cached factorisation of a PERTURBED operator: few iterations
     op2 = core.MaxwellOperator(OMEGA, eps, 0.05, npml, "Ez", 1e-6)
     op2.direct().factor()
@@ -196,6 +197,67 @@ def test_krylov_small(core):
     ref2 = orc.sparse_solve(A2, b).reshape(nx, ny)
     assert info["iters"] <= 10, info
     assert relerr(x, ref2) < 1e-9
+
+
+def test_krylov_preconditioned_512(core):
+    """The Krylov path at a size where unpreconditioned iteration is hopeless: 512 x 512 Ez, the cached factors of
+    a NEARBY operator (permittivity changed inside a design region) precondition BiCGSTAB on the matrix-free
+    stencil; parity with the oracle's sparse solve of the CHANGED operator at the fp64 bar (1e-8)."""
+    rng = np.random.default_rng(17)
+    n = 512
+    eps = np.ones((n, n))
+    eps[:, 236:276] = 12.25                                     # waveguide
+    eps[180:330, 150:360] = 1 + 11 * (rng.random((150, 210)) > 0.5)
+    npml = [15, 15]
+    op = core.MaxwellOperator(OMEGA, eps, 0.02, npml, "Ez", 1e-6)
+    op.direct().factor()
+    eps2 = eps.copy()
+    eps2[230:280, 200:300] += 0.05 * rng.random((50, 100))      # the design step
+    op.assemble(eps2)
+    b = np.zeros((n, n), dtype=complex)
+    b[60, 256] = 1j * OMEGA
+    x, info = op.krylov(b, method="bicgstab", tol=1e-12, maxiter=60, check_every=1, precondition=True, fused=True)
+    assert info["relres"] < 1e-10 and info["iters"] <= 40, info
+    ref = orc.sparse_solve(orc.construct_A(OMEGA, eps2, 0.02, npml, "Ez", 1e-6), b).reshape(n, n)
+    assert relerr(x, ref) < 1e-8
+
+
+def test_residual_guard(core):
+    """The residual contract of the direct solve: stale factors (operator changed after the factorisation, flag
+    forced) make plain refinement stall; the call must either recover through BiCGSTAB on the factors or fail
+    loudly -- never return a field whose residual is above 1e-10."""
+    from fdfdpy_b200._lib import FdfdError
+    rng = np.random.default_rng(23)
+    nx, ny = 96, 80
+    eps = 1 + 5 * rng.random((nx, ny))
+    npml = [8, 8]
+    op = core.MaxwellOperator(OMEGA, eps, 0.04, npml, "Ez", 1e-6)
+    d = op.direct()
+    d.factor()
+    b = rng.standard_normal((2, nx, ny)) + 1j * rng.standard_normal((2, nx, ny))
+    # (1) mild change: one refinement step is not enough, the Krylov fallback recovers
+    eps1 = eps * (1 + 2e-3 * rng.random((nx, ny)))
+    op.assemble(eps1)
+    d.factored = True                                           # pretend the factors are current
+    x = d.solve(b, max_refine=1, tol=1e-12).reshape(2, nx, ny)
+    assert d.last_refine_steps >= 1000, d.last_refine_steps     # the fallback ran
+    assert d.last_relres <= 1e-10
+    A1 = orc.construct_A(OMEGA, eps1, 0.04, npml, "Ez", 1e-6)
+    for j in range(2):
+        assert relerr(x[j], orc.sparse_solve(A1, b[j]).reshape(nx, ny)) < 1e-8
+    # (2) unrelated operator: nothing converges, the call fails instead of returning garbage
+    op.assemble(1 + 11 * rng.random((nx, ny)))
+    d.factored = True
+    with pytest.raises(FdfdError, match="residual"):
+        d.solve(b[0], max_refine=2, tol=1e-12)
+    # (3) raw substitution (max_refine = 0) stays unguarded: it reports, it does not judge
+    d.solve(b[0], max_refine=0)
+    assert d.last_relres > 1e-10
+    # (4) non-finite right-hand side is rejected
+    bad = b[0].copy()
+    bad[3, 3] = np.nan
+    with pytest.raises(FdfdError, match="finite"):
+        d.solve(bad)
 
 
 def test_mode_solve_golden(core, golden):
@@ -237,9 +299,9 @@ def test_single_slab_operator_matches_whole_grid(core, pol):
     b[20, 18] = 1j * OMEGA
     sol = orc.sparse_solve(orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6), b).reshape(nx, ny)
     for method in ("bicgstab", "cocg"):
-        xs, info = slab.krylov(b, method=method, tol=1e-11, maxiter=20000, check_every=20)
-        assert info["relres"] < 1e-8, (method, info)
-        assert relerr(xs, sol) < 1e-6
+        xs, info = slab.krylov(b, method=method, tol=1e-12, maxiter=20000, check_every=20)
+        assert info["relres"] < 1e-10, (method, info)
+        assert relerr(xs, sol) < 1e-8
 
 
 def test_complex64_stencil_and_krylov(core):

@@ -73,7 +73,7 @@ def test_krylov_solver_names(Simulation, golden):
     for name in ("scipy", "pardiso"):
         assert relerr(sim.solve_fields(solver=name)[2], g["Ez_fz"]) < 1e-8
     ez = sim.solve_fields(solver="bicgstab")[2]
-    assert relerr(ez, g["Ez_fz"]) < 1e-6
+    assert relerr(ez, g["Ez_fz"]) < 1e-8
     with pytest.raises(ValueError):
         sim.solve_fields(solver="nope")
 

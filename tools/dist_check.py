@@ -110,7 +110,7 @@ def main():
         b[nx // 2, ny // 2] = 1j * omega
         sol = orc.sparse_solve(A, b).reshape(nx, ny)[sl]
         for method in ("bicgstab", "cocg"):
-            xs, info = slab.krylov(b[sl], method=method, tol=1e-11, maxiter=20000, check_every=20)
+            xs, info = slab.krylov(b[sl], method=method, tol=1e-12, maxiter=20000, check_every=20)
             nrm = torch.tensor([np.linalg.norm(xs - sol) ** 2, np.linalg.norm(sol) ** 2], dtype=torch.float64)
             dist.all_reduce(nrm)
             out["slab_" + method] = dict(info, rel_l2_vs_oracle=float(np.sqrt(nrm[0] / nrm[1])))
