@@ -9,11 +9,15 @@ iterative refinement with the fp64 stencil residual, derived H fields.
 
 * ``value``  : Mcell/s with eps_r and the source already resident in HBM (C ABI, device pointers).
 * ``e2e``    : the same solve through the public API (``Simulation.eps_r = ...; solve_fields()``)
-               with HOST numpy arrays in and out, copies inside the timed region.
+               with HOST numpy arrays in and out, copies inside the timed region, over all ``--steps``.
 * N > 1      : independent solves (one omega per GPU, "frequency sweep sharded one solve per GPU",
-               no data-path collective) -> weak scaling; time = max over ranks.
+               no data-path collective) -> weak scaling; time = max over ranks.  The SAME line then
+               also carries the two one-grid-on-N-GPUs paths, measured right after the replicas:
+               ``sharded`` (4096^2 direct solve, elimination tree split over the ranks, NCCL inside
+               the library) and ``slab`` (8192^2 matrix-free stencil on slabs with halo exchange).
 * ``--impl reference``: the reference's CPU path (oracle port of its scipy/SuperLU branch) on a
-               bounded sub-grid sample of the same workload, on the host cores.
+               FIXED 1024^2 corner of the same workload (2 repetitions, independent of --steps),
+               preceded by a 256/512 size sweep so the extrapolation to 4096^2 is on the record.
 """
 import argparse
 import ctypes as C
@@ -33,6 +37,8 @@ OMEGA0 = 2 * np.pi * 200e12
 DL = 0.02            # cells of 20 nm at lambda0 = 1.5 um: 75 cells per vacuum wavelength
 NPML = [15, 15]
 L0 = 1e-6
+CPU_REF_GRID = 1024  # the reference arm's fixed sample (largest that finishes in about a minute per solve)
+CPU_REF_REPS = 2
 
 
 def synthetic_eps(n, seed=0):
@@ -117,6 +123,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+def captured_traffic():
+    """DRAM bytes of the dominant GEMM launch from the committed `ncu --set full` capture; the file is written by
+    tools/ncu_traffic.py (tools/run_profiles.sh), never typed in by hand."""
+    path = os.path.join(ROOT, "profiles", "zgemm_capture.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference's own algorithm (oracle port of linalg.py:139, scipy SuperLU)
 # --------------------------------------------------------------------------------------------
@@ -134,24 +151,42 @@ def cpu_solve_sample(n_sample, full_n, reps=1):
 
 
 def run_reference(args):
+    """The reference arm: a FIXED sample and repetition count, whatever --steps / --warmup say (a sparse LU's
+    Mcell/s falls with the grid size, so the sample must not shrink when the driver asks for more steps)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    n_s = args.cpu_sample or (256 if total > 6 else (384 if total > 2 else 512))
-    for _ in range(args.warmup):
-        cpu_solve_sample(n_s, args.size)
-    times = [cpu_solve_sample(n_s, args.size) for _ in range(args.steps)]
+    n_s = args.cpu_sample or CPU_REF_GRID
+    sweep = []
+    for n in [v for v in (256, 512) if v < n_s]:            # doubles as the warm-up (imports, scipy, page cache)
+        dt = cpu_solve_sample(n, args.size)
+        sweep.append({"grid": [n, n], "s_per_solve": dt, "Mcell_per_s": n * n / dt / 1e6})
+    times = []
+    for rep in range(CPU_REF_REPS):
+        times.append(cpu_solve_sample(n_s, args.size))
+        if times[-1] > 150.0:                                # a slow host: one repetition has to do
+            break
     dt = float(np.mean(times))
+    sweep.append({"grid": [n_s, n_s], "s_per_solve": dt, "Mcell_per_s": n_s * n_s / dt / 1e6})
     val = n_s * n_s / dt / 1e6
+    # power-law extrapolation of the solve time to the full workload from the last two sweep points
+    extrap = None
+    if len(sweep) >= 2:
+        (a, b) = sweep[-2], sweep[-1]
+        p = np.log(b["s_per_solve"] / a["s_per_solve"]) / np.log(b["grid"][0] ** 2 / a["grid"][0] ** 2)
+        t_full = b["s_per_solve"] * (args.size ** 2 / b["grid"][0] ** 2) ** p
+        extrap = {"exponent_time_vs_cells": float(p), "s_per_solve_at_full_size": float(t_full),
+                  "Mcell_per_s_at_full_size": args.size ** 2 / t_full / 1e6,
+                  "note": "extrapolated, not measured: the {0}x{0} solve does not fit the time budget on a CPU".format(args.size)}
     cores = os.cpu_count()
-    sample = ("{0}x{0} corner of the {1}x{1} workload, same eps/omega/PML, scipy SuperLU direct solve + derived "
-              "fields (the reference's solver='scipy' branch; MKL Pardiso/pyMKL is not installable here)").format(
-                  n_s, args.size)
+    sample = ("{0}x{0} corner of the {1}x{1} workload, same eps/omega/PML, {2} solve(s) of {3:.1f} s: scipy SuperLU direct "
+              "solve + derived fields (the reference's solver='scipy' branch, linalg.py:139; MKL Pardiso/pyMKL is not "
+              "installable here); SuperLU's factorisation is single-threaded").format(n_s, args.size, len(times), dt)
     line = {"impl": "reference", "metric": "fdfd_solve_throughput", "value": val, "unit": "Mcell/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.size, sample=n_s),
+            "cpu_reps": len(times), "size_sweep": sweep, "extrapolation": extrap,
             "cpu_baseline": {"value": val, "unit": "Mcell/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -166,12 +201,25 @@ def workload_config(n, sample=None):
            "l2": "inputs larger than L2 (fronts and factors are tens of GB per step)"}
     if sample:
         cfg["cpu_sample_grid"] = [sample, sample]
+        cfg["cpu_sample_note"] = ("the CPU arm solves a corner of the workload, not the workload: a size-matched ratio "
+                                  "needs the extrapolation printed in `extrapolation`")
     return cfg
 
 
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def stencil_rate(lib, _lib, op, d_in, d_out, ncell, reps=20):
+    for _ in range(3):
+        _lib.check(lib.fdfd_op_apply_dev(op.h, d_in, d_out, 1, 1))
+    _lib.check(lib.fdfd_timer_start(op.h))
+    for _ in range(reps):
+        _lib.check(lib.fdfd_op_apply_dev(op.h, d_in, d_out, 1, 1))
+    sms = C.c_double(0)
+    _lib.check(lib.fdfd_timer_stop(op.h, C.byref(sms)))
+    return 48.0 * ncell * reps / (sms.value * 1e-3) / 1e9
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,18 +308,14 @@ def run_ours(args):
         _lib.check(lib.fdfd_timer_stop(op.h, C.byref(tms)))
         breakdown[name + "_ms"] = tms.value
 
-    # ---------------- stencil kernel on its own (HBM roofline of the matrix-free path) ----------------
-    reps = 20
-    for _ in range(3):
-        _lib.check(lib.fdfd_op_apply_dev(op.h, d_b, d_x, 1, 1))
-    _lib.check(lib.fdfd_timer_start(op.h))
-    for _ in range(reps):
-        _lib.check(lib.fdfd_op_apply_dev(op.h, d_b, d_x, 1, 1))
-    sms = C.c_double(0)
-    _lib.check(lib.fdfd_timer_stop(op.h, C.byref(sms)))
-    stencil_gbs = 48.0 * ncell * reps / (sms.value * 1e-3) / 1e9
-    dmma = C.c_double(0)
-    _lib.check(lib.fdfd_dmma_peak(C.byref(dmma)))
+    # ---------------- the matrix-free stencils on their own (HBM roofline of path (a)), Ez and Hz ----------------
+    stencil_gbs = stencil_rate(lib, _lib, op, d_b, d_x, ncell)
+    op_hz = core.MaxwellOperator(omega, eps, DL, NPML, "Hz", L0)
+    stencil_hz_gbs = stencil_rate(lib, _lib, op_hz, d_b, d_x, ncell)
+    del op_hz
+    # FP64 tensor-pipe probe: register-resident DMMA loop, with the SM clock it ran at measured INSIDE the kernel
+    probe = np.zeros(4)
+    _lib.check(lib.fdfd_dmma_probe_clocked(8, 8, _lib.ptr(probe)))
 
     for p in (d_eps, d_b, d_x, d_f):
         lib.fdfd_free(p)
@@ -281,10 +325,10 @@ def run_ours(args):
     if args.no_e2e:
         print(json.dumps({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "gpu_launches": int(launches),
                           "zgemm_big_ms": gt[0], "zgemm_big_tflops": gt[1] / (gt[0] * 1e-3) / 1e12 if gt[0] else 0,
-                          "stencil_gbs": stencil_gbs}), flush=True)
+                          "stencil_gbs": stencil_gbs, "stencil_hz_gbs": stencil_hz_gbs}), flush=True)
         return
     sim = Simulation(omega, eps, DL, NPML, "Ez", L0)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
 
     def step_api():
         sim.eps_r = eps                 # H2D of eps, re-assembly, drops the factorisation
@@ -302,7 +346,15 @@ def run_ours(args):
     barrier()
     e2e_relres = sim.last_solve["relres"]
     e2e_timings = {k + "_ms": v * 1e3 for k, v in sim.timings.items()}
-    del sim
+    del sim, ez
+
+    # ---------------- one grid on N GPUs (N > 1): sharded direct solve and slab stencil ----------------
+    multi = {}
+    if world > 1 and not args.no_multi:
+        try:
+            multi = run_one_grid_multi_gpu(args, dist, rank, world, local, lib, _lib, core, breakdown)
+        except Exception as e:            # a failure here must not take the replica numbers down with it
+            multi = {"sharded": {"error": repr(e)[:300]}}
 
     # ---------------- reduce over ranks ----------------
     dev_ms_max, e2e_max = dev_ms, e2e_s
@@ -322,11 +374,12 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     big_ms, big_fl, big_n = gt[0], gt[1], gt[2]
     achieved = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
-    # FP64 tensor-pipe ceiling: 64 DFMA/clk/SM (one m8n8k4 DMMA per SM sub-partition every 4 clocks) x 148 SMs at
-    # the SM clock sampled under load; the register-resident DMMA probe is reported next to it (it is
-    # power-limited when run alone: every SM issuing DMMA back to back pulls the clock below what the solver sees)
+    # FP64 tensor-pipe ceiling: 128 flop/clk/SM (one m8n8k4 DMMA per SM sub-partition every 16 clocks) x 148 SMs at
+    # the SM clock sampled under load.  MEASURED_PEAKS.json has no FP64 entry, so the denominator is this pipe rate;
+    # the register-resident probe next to it shows how much of it an ideal instruction stream reaches on this board.
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     fp64_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
+    cap = captured_traffic()
     line = {
         "metric": "fdfd_solve_throughput", "value": value, "unit": "Mcell/s",
         "solves_per_s": world / (ms_per_step * 1e-3),
@@ -334,7 +387,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n),
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "Mcell/s", "ms_per_step": e2e_max * 1e3,
+        "e2e": {"value": e2e_val, "unit": "Mcell/s", "ms_per_step": e2e_max * 1e3, "steps": e2e_steps,
                 "h2d_bytes_per_step": int(eps.nbytes + src.nbytes), "d2h_bytes_per_step": int(3 * nbytes),
                 "host_memory": "inputs: the caller's pageable float64 numpy arrays (eps_r setter, src), widened to "
                                "complex on the device; outputs: three complex128 fields in page-locked arrays "
@@ -345,31 +398,31 @@ def run_ours(args):
         "wall_ms_per_step": wall / args.steps * 1e3,
         "breakdown": breakdown,
         "roofline": {
-            "kernel": "zgemm_dmma_kernel<4,2,3> (rank-T sweep update, complex128 on DMMA m8n8k4)",
+            "kernel": "zgemm_dmma_persistent_kernel (+ the tiled zgemm_dmma_kernel on the many-small-front levels): "
+                      "complex128 GEMM on DMMA m8n8k4, every launch of the step timed with CUDA events",
             "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved / fp64_peak if fp64_peak else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-            # (profiles/r01_full_capture_zgemm_persistent_and_planes_stencil.txt): the level-19 Schur update
-            # S(8192x8192, lower) -= G(8192x4094) F_RE^T, 1.108e12 flop, 2.15e9 algorithmic bytes; DRAM runs at 8 %
-            # of its peak there (tensor-bound kernel, 91.5 % tensor-pipe active), so the 10x re-read is not the limiter
-            "traffic": 2.197e10,
-            "traffic_note": "bytes of one captured launch (1.108e12 flop, 2.15e9 algorithmic bytes), not of the "
-                            "per-step average launch; see profiles/",
+            "traffic": cap.get("dram_bytes") if cap else None,
+            "traffic_capture": cap,
             "peak_source": "FP64 tensor pipe: 148 SMs x 128 flop/clk x the SM clock sampled under load "
                            "(MEASURED_PEAKS.json has no FP64 entry; vendor-nominal is 40 TFLOP/s)",
-            "dmma_probe_tflops": dmma.value,
+            "dmma_probe": {"tflops": probe[0], "sm_mhz_in_kernel": probe[1],
+                           "pipe_rate_at_that_clock": 148 * 128 * probe[1] * 1e6 / 1e12 if probe[1] else None,
+                           "what": "register-resident mma.sync.m8n8k4.f64 loop, 8 warps/SM x 8 accumulator chains; "
+                                   "clock = clock64 / globaltimer measured inside the same kernel"},
             "launches_timed": int(big_n), "kernel_ms_per_step": big_ms / args.steps,
             "share_of_step": big_ms / dev_ms if dev_ms else None,
             "algorithmic_flops_per_step": big_fl / args.steps,
         },
-        "roofline_small_gemm": {"kernel": "zgemm_dmma_kernel<2,1,2>", "ms_per_step": gt[3] / args.steps,
-                                "tflops": gt[4] / (gt[3] * 1e-3) / 1e12 if gt[3] > 0 else 0.0,
-                                "launches": int(gt[5])},
         "roofline_stencil": {"kernel": "stencil_fused_ez_kernel", "bound": "hbm", "achieved": stencil_gbs,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stencil_gbs / peaks["hbm_gbs"],
                              "peak_source": peak_src, "algorithmic_bytes_per_cell": 48},
+        "roofline_stencil_hz": {"kernel": "stencil_fused_hz_kernel", "bound": "hbm", "achieved": stencil_hz_gbs,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stencil_hz_gbs / peaks["hbm_gbs"],
+                                "peak_source": peak_src, "algorithmic_bytes_per_cell": 48},
         "factor": {"bytes": stats["factor_bytes"], "flops": stats["factor_flops"]},
     }
+    line.update(multi)
     # bounded CPU baseline (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu_baseline:
         n_s = 512
@@ -377,10 +430,133 @@ def run_ours(args):
         line["cpu_baseline"] = {
             "value": n_s * n_s / dt / 1e6, "unit": "Mcell/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "{0}x{0} corner of the workload, one solve ({1:.1f} s): scipy SuperLU, the reference's "
-                      "solver='scipy' branch (linalg.py:139); SuperLU factorisation is single-threaded".format(n_s, dt)}
+                      "solver='scipy' branch (linalg.py:139); SuperLU factorisation is single-threaded; the reference "
+                      "arm (--impl reference) times the 1024^2 corner and prints the size sweep".format(n_s, dt)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_one_grid_multi_gpu(args, dist, rank, world, local, lib, _lib, core, breakdown):
+    """ONE grid on all N GPUs, NCCL inside the library (fdfdpy_b200.distributed).
+
+    sharded: the headline 4096^2 Ez solve with the elimination tree split over the ranks (DirectSolver(op, comm));
+             efficiency_vs_n1 = t_factor(1 GPU, this run's breakdown) / (N * t_factor(N GPUs)).
+             A 200 x 160 solve of the same code path is checked against the CPU oracle first (rank 0), so the
+             line carries its own parity evidence for the NCCL path.
+    slab:    the matrix-free stencils (Ez and Hz, 48 B/cell) on an 8192^2 grid split into row slabs with halo
+             exchange, aggregate GB/s = 48 B x cells / max-over-ranks time."""
+    import torch
+    from fdfdpy_b200.distributed import Communicator, SlabOperator
+    gloo = dist.new_group(backend="gloo")
+    comm = Communicator.from_torch(group=gloo)
+    out = {}
+
+    def maxr(v):
+        tt = torch.tensor([float(v)], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=gloo)
+        return float(tt[0])
+
+    # ---- parity of the sharded solve against the oracle (small grid, both polarisations)
+    parity = {}
+    rng = np.random.default_rng(1)
+    nxp, nyp = 200, 160
+    eps_p = 1 + 5 * (rng.random((nxp, nyp)) > 0.5)
+    b_p = rng.standard_normal((nxp, nyp)) + 1j * rng.standard_normal((nxp, nyp))
+    for pol in ("Ez", "Hz"):
+        opp = core.MaxwellOperator(OMEGA0, eps_p, 0.04, [10, 8], pol, 1e-6)
+        dp = core.DirectSolver(opp, comm=comm)
+        xp = dp.solve(b_p).reshape(nxp, nyp)
+        if rank == 0:
+            from oracle import fdfd_oracle as orc
+            ref = orc.sparse_solve(orc.construct_A(OMEGA0, eps_p, 0.04, [10, 8], pol, 1e-6), b_p).reshape(nxp, nyp)
+            parity[pol] = {"rel_l2_vs_oracle": float(np.linalg.norm(xp - ref) / np.linalg.norm(ref)),
+                           "relres": dp.last_relres}
+        del dp, opp
+
+    # ---- the headline grid on N GPUs
+    n = args.size
+    eps = synthetic_eps(n)
+    src = synthetic_src(n)
+    op = core.MaxwellOperator(OMEGA0, eps, DL, NPML, "Ez", L0)
+    d = core.DirectSolver(op, comm=comm)
+    f_ms, s_ms = [], []
+    for rep in range(3):
+        dist.barrier(group=gloo)
+        ms_f, ms_s = C.c_double(0), C.c_double(0)
+        _lib.check(lib.fdfd_timer_start(op.h))
+        d.factor()
+        _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms_f)))
+        t0 = time.perf_counter()
+        d.solve_fields(src, 1j * OMEGA0)
+        ms_s.value = (time.perf_counter() - t0) * 1e3
+        f_ms.append(maxr(ms_f.value))
+        s_ms.append(maxr(ms_s.value))
+    st = d.stats()
+    fb, tb = C.c_double(0), C.c_double(0)
+    lib.fdfd_mem_info(C.byref(fb), C.byref(tb))
+    t1 = breakdown.get("factor_ms")
+    out["sharded"] = {
+        "what": "ONE {0}x{0} Ez grid on {1} GPUs: elimination tree split over the ranks, top fronts distributed by "
+                "block rows, NCCL point-to-point inside the library".format(n, world),
+        "factor_ms": min(f_ms[1:]), "factor_ms_all": f_ms, "solve_fields_host_ms": min(s_ms[1:]),
+        "relres": d.last_relres, "factor_ms_1gpu_same_run": t1,
+        "efficiency_vs_n1": (t1 / (world * min(f_ms[1:]))) if t1 else None,
+        "speedup_vs_n1": (t1 / min(f_ms[1:])) if t1 else None,
+        "factor_bytes_rank0": st["factor_bytes"], "hbm_used_gb_max": maxr((tb.value - fb.value) / 1e9),
+        "parity_200x160": parity, "timing": "CUDA events on the library stream, max over ranks, best of 2 after 1 warm-up"}
+    del d, op
+
+    # ---- slabs: matrix-free stencil with halo exchange
+    ns = 8192
+    eps_s = synthetic_eps(ns)
+    peaks, _ = measured_peaks()
+    slab_out = {"grid": [ns, ns]}
+    for pol in ("Ez", "Hz"):
+        slab = SlabOperator(OMEGA0, eps_s, DL, NPML, pol, L0, comm=comm)
+        nloc = (slab.nxl + 2) * ns
+        d_x, d_y = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.fdfd_malloc(C.byref(d_x), 16.0 * nloc))
+        _lib.check(lib.fdfd_malloc(C.byref(d_y), 16.0 * nloc))
+        xe = np.ones((slab.nxl + 2, ns), dtype=np.complex128)
+        _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(xe), 16.0 * nloc))
+        _lib.check(lib.fdfd_memcpy_h2d(d_y, _lib.ptr(xe), 16.0 * nloc))
+        iters = 100
+        for _ in range(5):
+            _lib.check(lib.fdfd_op_apply_dev(slab.h, d_x, d_y, 1, 1))
+        dist.barrier(group=gloo)
+        ms = C.c_double(0)
+        _lib.check(lib.fdfd_timer_start(slab.h))
+        for _ in range(iters):
+            _lib.check(lib.fdfd_op_apply_dev(slab.h, d_x, d_y, 1, 1))
+        _lib.check(lib.fdfd_timer_stop(slab.h, C.byref(ms)))
+        per = maxr(ms.value) / iters
+        agg = 48.0 * ns * ns / (per * 1e-3) / 1e9
+        slab_out[pol] = {"ms_per_apply": per, "agg_GBps": agg, "per_gpu_frac_of_hbm": agg / world / peaks["hbm_gbs"]}
+        if pol == "Ez":
+            # a fixed number of distributed BiCGSTAB iterations (2 stencils + 3 all-reduced reductions each)
+            it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
+            be = np.zeros((slab.nxl + 2, ns), dtype=np.complex128)
+            if slab.x0 <= ns // 2 < slab.x1:
+                be[1 + ns // 2 - slab.x0, ns // 2] = 1j * OMEGA0
+            _lib.check(lib.fdfd_memcpy_h2d(d_y, _lib.ptr(be), 16.0 * nloc))
+            _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(np.zeros_like(be)), 16.0 * nloc))
+            for warm in (1, 0):
+                dist.barrier(group=gloo)
+                ms = C.c_double(0)
+                _lib.check(lib.fdfd_timer_start(slab.h))
+                _lib.check(lib.fdfd_krylov_solve_dev(slab.h, None, d_y, d_x, 0, 1e-30, 100, 1, 100, None, 0,
+                                                     C.byref(it), C.byref(rr), C.byref(conv)))
+                _lib.check(lib.fdfd_timer_stop(slab.h, C.byref(ms)))
+            slab_out["bicgstab_ms_per_iter"] = maxr(ms.value) / max(it.value, 1)
+        lib.fdfd_free(d_x)
+        lib.fdfd_free(d_y)
+        del slab
+    slab_out["what"] = ("ONE 8192x8192 grid as {0} row slabs: fused matrix-free stencil (48 B/cell) incl. NCCL halo "
+                        "exchange overlapped with the interior rows; device time, max over ranks").format(world)
+    out["slab"] = slab_out
+    del comm
+    return out
 
 
 def run_sweep(args):
@@ -415,8 +591,9 @@ def run_sweep(args):
     _lib.check(lib.fdfd_memcpy_h2d(d_b, _lib.ptr(b_host), nbytes * nrhs))
     relres, steps_ref = C.c_double(0), C.c_int(0)
     ops = {}
+    parts = {"factor_ms": 0.0, "solve_ms": 0.0}
 
-    def step(k):
+    def step(k, timed=False):
         omega = my_freqs[k % len(my_freqs)]
         if omega not in ops:                        # operator handles are per omega (PML depends on it); plan is shared
             if len(ops) >= 2:
@@ -424,10 +601,18 @@ def run_sweep(args):
             op = core.MaxwellOperator(omega, eps, DL, NPML, "Hz", L0)
             ops[omega] = (op, core.DirectSolver(op))
         op, direct = ops[omega]
+        tms = C.c_double(0)
         _lib.check(lib.fdfd_op_assemble_dev(op.h, d_eps, None, 1))
+        _lib.check(lib.fdfd_timer_start(op.h))
         _lib.check(lib.fdfd_direct_factor(direct.h, op.h))
+        _lib.check(lib.fdfd_timer_stop(op.h, C.byref(tms)))
+        if timed:
+            parts["factor_ms"] += tms.value
+        _lib.check(lib.fdfd_timer_start(op.h))
         _lib.check(lib.fdfd_direct_solve_dev(direct.h, op.h, d_b, d_x, nrhs, 3, 1e-12, C.byref(relres), C.byref(steps_ref)))
-        _lib.check(lib.fdfd_op_sync(op.h))
+        _lib.check(lib.fdfd_timer_stop(op.h, C.byref(tms)))
+        if timed:
+            parts["solve_ms"] += tms.value
         return relres.value
 
     for k in range(args.warmup):
@@ -437,7 +622,7 @@ def run_sweep(args):
     t = time.perf_counter()
     worst = 0.0
     for k in range(args.steps):
-        worst = max(worst, step(k % 2))
+        worst = max(worst, step(k % 2, timed=True))
     dt = time.perf_counter() - t
     if dist is not None:
         import torch
@@ -446,11 +631,17 @@ def run_sweep(args):
         dt, worst = float(tt[0]), float(tt[1])
     if rank == 0:
         per = dt / args.steps
+        fstats = ops[next(iter(ops))][1].stats()
         print(json.dumps({
             "metric": "fdfd_sweep_throughput", "value": world * nrhs * ncell / per / 1e6, "unit": "Mcell/s",
             "rhs_solves_per_s": world * nrhs / per, "factorisations_per_s": world / per, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "dtype": "f64", "data": "synthetic", "relres_max": worst,
+            "refine_steps_last": steps_ref.value,
+            "factor_ms_per_omega": parts["factor_ms"] / args.steps,
+            "solve_refine_ms_per_omega": parts["solve_ms"] / args.steps,
+            "factor_bytes": fstats["factor_bytes"],
+            "substitution_floor_ms": 2 * fstats["factor_bytes"] / (measured_peaks()[0]["hbm_gbs"] * 1e9) * 1e3,
             "config": {"workload": "Hz {0}x{0} broadband sweep, 1 factorisation + {1} RHS per omega, omegas sharded over "
                                    "GPUs (BASELINE config 4)".format(n, nrhs), "grid": [n, n], "nrhs": nrhs,
                        "timing": "host wall clock around device-synchronised steps (operator re-created per omega)"}}),
@@ -469,8 +660,9 @@ def main():
     ap.add_argument("--tile", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the public-API arm")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the one-grid-on-N-GPUs arms")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="reference arm: side of the sub-grid sample (default: chosen from steps + warmup)")
+                    help="reference arm: side of the sub-grid sample (default {})".format(CPU_REF_GRID))
     ap.add_argument("--workload", default="solve", choices=["solve", "sweep"],
                     help="solve: the headline 4096^2 Ez solve (default); sweep: BASELINE config 4")
     args = ap.parse_args()

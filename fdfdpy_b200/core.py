@@ -86,7 +86,7 @@ class MaxwellOperator:
             if x.size != self.nx * self.ny:
                 raise ValueError("complex64 apply takes one vector")
             y = np.empty_like(x)
-            check(self.lib.fdfd_op_apply_host_c64(self.h, ptr(x), ptr(y), int(fused and self.pol == "Ez")))
+            check(self.lib.fdfd_op_apply_host_c64(self.h, ptr(x), ptr(y), int(bool(fused))))
             return y
         x = as_c128(x)
         nvec = x.size // (self.nx * self.ny)
@@ -147,7 +147,7 @@ class MaxwellOperator:
             x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, dtype=np.complex64).copy()
             it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
             check(self.lib.fdfd_krylov_solve_host_c64(self.h, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
-                                                      float(tol), int(maxiter), int(fused and self.pol == "Ez"),
+                                                      float(tol), int(maxiter), int(bool(fused)),
                                                       int(check_every), C.byref(it), C.byref(rr), C.byref(conv)))
             return x.reshape(b.shape), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
         b = as_c128(b)
@@ -160,8 +160,6 @@ class MaxwellOperator:
                 d.factor()
             pre = d.h
         c12a = None if c12 is None else as_c128(c12)
-        if self.has_nl and fused and self.pol != "Ez":
-            fused = False
         check(self.lib.fdfd_krylov_solve_host(self.h, pre, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
                                               float(tol), int(maxiter), int(fused), int(check_every), ptr(c12a),
                                               int(bool(real_inner)), C.byref(it), C.byref(rr), C.byref(conv)))

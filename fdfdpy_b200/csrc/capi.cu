@@ -50,6 +50,35 @@ __global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters)
     for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
     if (s == 123.456) out[0] = s;
 }
+/* the same probe with the SM clock it ran at measured INSIDE the kernel (clock64 cycles / globaltimer ns of one
+ * resident warp), so the result can be held against the pipe rate at the clock the board actually sustained:
+ * out[0] = TFLOP/s, out[1] = SM MHz during the probe, out[2] = ms, out[3] = real flops */
+template <int NACC>
+__global__ void __launch_bounds__(1024) dmma_probe_clocked_kernel(double* out, unsigned long long* clk, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    unsigned long long t0 = 0, c0 = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        c0 = clock64();
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+    if (threadIdx.x == 0) {
+        unsigned long long c1 = clock64(), t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        clk[2 * blockIdx.x] = c1 - c0 + (s == 123.456 ? 1 : 0);
+        clk[2 * blockIdx.x + 1] = t1 - t0;
+    }
+    if (s == 123.456) out[0] = s;
+}
 extern "C" {
 
 int fdfd_dmma_peak(double* tflops) {
@@ -103,6 +132,46 @@ int fdfd_dmma_probe(int warps, int nacc, double* tflops) {
     int na = nacc >= 16 ? 16 : nacc;
     *tflops = 148.0 * warps * iters * na * 512.0 / (ms * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
+int fdfd_dmma_probe_clocked(int warps, int nacc, double* out4) {
+    if (warps < 1 || warps > 32) FDFD_FAIL("warps per SM: 1..32");
+    double* d = nullptr;
+    unsigned long long* clk = nullptr;
+    FDFD_CHECK(cudaMalloc(&d, sizeof(double)));
+    FDFD_CHECK(cudaMalloc(&clk, sizeof(unsigned long long) * 2 * 148));
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    const int na = nacc >= 16 ? 16 : nacc >= 8 ? 8 : nacc >= 4 ? 4 : nacc >= 2 ? 2 : 1;
+    const int iters = 400000 / na;                      // ~50 ms: long enough for the clock to settle
+    auto launch = [&](int it) {
+        if (na == 1) dmma_probe_clocked_kernel<1><<<148, warps * 32>>>(d, clk, it);
+        else if (na == 2) dmma_probe_clocked_kernel<2><<<148, warps * 32>>>(d, clk, it);
+        else if (na == 4) dmma_probe_clocked_kernel<4><<<148, warps * 32>>>(d, clk, it);
+        else if (na == 8) dmma_probe_clocked_kernel<8><<<148, warps * 32>>>(d, clk, it);
+        else dmma_probe_clocked_kernel<16><<<148, warps * 32>>>(d, clk, it);
+    };
+    launch(1000);
+    FDFD_CHECK(cudaDeviceSynchronize());
+    FDFD_CHECK(cudaEventRecord(e0));
+    launch(iters);
+    FDFD_CHECK(cudaEventRecord(e1));
+    FDFD_CHECK(cudaEventSynchronize(e1));
+    FDFD_CHECK(cudaGetLastError());
+    float ms = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    unsigned long long h[2 * 148];
+    FDFD_CHECK(cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost));
+    double mhz = 0;
+    for (int i = 0; i < 148; ++i) mhz += h[2 * i + 1] ? (double)h[2 * i] / (double)h[2 * i + 1] * 1e3 : 0.0;
+    const double fl = 148.0 * warps * (double)iters * na * 512.0;
+    out4[0] = fl / (ms * 1e-3) / 1e12;
+    out4[1] = mhz / 148.0;
+    out4[2] = ms;
+    out4[3] = fl;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(clk);
     return 0;
 }
 

@@ -231,6 +231,101 @@ stencil_fused_ez_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fused matrix-free Hz stencil:  A = Dxf ex^-1 Dxb + Dyf ey^-1 Dyb + w^2 mu  (linalg.py:67-98).
+// The face weights 1 / (eps0' * edge-averaged eps) are rebuilt in registers from eps_r itself: the x-faces
+// from the rows the thread marches (one reciprocal per row face, shared by the two cells it couples), the
+// y-faces from the adjacent lanes by shuffle (each lane inverts its own lower face and borrows the upper one
+// from lane + 1).  Same traffic as the Ez kernel: x 16 + eps 16 + y 16 = 48 B/cell against the 112 B/cell of the
+// stored planes.  Tables: ax[ix] = (isxf[ix] isxb[ix], isxf[ix] isxb[ix+1]) / (eps0' dx^2), same along y.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx fast_recip_c(cplx z) {
+    // conj(z) / |z|^2 with a Newton-refined hardware reciprocal (|eps| is O(1): no overflow concerns)
+    const double d = z.x * z.x + z.y * z.y;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return make_double2(z.x * r, -z.y * r);
+}
+template <bool AVG>
+__device__ __forceinline__ cplx face_weight(cplx e_lo, cplx e) {
+    // reciprocal of the permittivity on the LOWER face of a cell holding e, e_lo = the cell below (linalg.py:68-73)
+    return fast_recip_c(AVG ? make_double2(0.5 * (e_lo.x + e.x), 0.5 * (e_lo.y + e.y)) : e);
+}
+
+template <int ROWS, class V, bool AVG>
+__global__ void __launch_bounds__(128)
+stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_nl,
+                        const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
+                        const cplx* __restrict__ aym_t, const cplx* __restrict__ ayp_t,
+                        const V* __restrict__ x, V* __restrict__ y, int nx, int ny, double w2m0, double w2e0,
+                        int row0, int row1) {
+    const int ix0 = row0 + blockIdx.y * ROWS;
+    const int rows = min(ROWS, row1 - ix0);
+    const int iy_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = iy_raw < ny;
+    const int iy = active ? iy_raw : ny - 1;
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)nx * ny;
+    const size_t voff = (size_t)blockIdx.z * n;
+    const V* xv = x + voff;
+    const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || iy_raw >= ny - 1;
+    const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
+    const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
+    // rows ix0 - 1 .. ix0 + ROWS of x and eps (the ragged last CTA re-reads its last row: results discarded)
+    cplx xc[ROWS + 2], e[ROWS + 2];
+    xc[0] = vload(xv + (size_t)ixm * ny + iy);
+    e[0] = vload(eps_r + (size_t)ixm * ny + iy);
+#pragma unroll
+    for (int r = 0; r <= ROWS; ++r) {
+        int ix = ix0 + r;
+        if (r >= rows) ix = ix0 + rows;                // first row past the ones computed here
+        if (ix >= nx) ix -= nx;
+        xc[r + 1] = vload(xv + (size_t)ix * ny + iy);
+        e[r + 1] = vload(eps_r + (size_t)ix * ny + iy);
+    }
+    cplx rx[ROWS + 1];
+#pragma unroll
+    for (int r = 0; r <= ROWS; ++r) rx[r] = face_weight<AVG>(e[r], e[r + 1]);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (r < rows) {                                // block-uniform
+            const int ix = ix0 + r;
+            const cplx axm = ldg_c(axm_t + ix), axp = ldg_c(axp_t + ix);
+            const cplx ec = e[r + 1], xcc = xc[r + 1];
+            cplx xd = shfl_up_c(xcc), xu = shfl_down_c(xcc);
+            cplx ed = shfl_up_c(ec);
+            if (load_dn) {
+                xd = vload(xv + (size_t)ix * ny + iym);
+                ed = vload(eps_r + (size_t)ix * ny + iym);
+            }
+            const cplx ry_lo = face_weight<AVG>(ed, ec);
+            cplx ry_hi = shfl_down_c(ry_lo);
+            if (load_up) {
+                xu = vload(xv + (size_t)ix * ny + iyp);
+                ry_hi = face_weight<AVG>(ec, vload(eps_r + (size_t)ix * ny + iyp));
+            }
+            const cplx cxm = cmul(axm, rx[r]), cxp = cmul(axp, rx[r + 1]);
+            const cplx cym = cmul(aym, ry_lo), cyp = cmul(ayp, ry_hi);
+            cplx c0 = make_double2(w2m0 - (cxm.x + cxp.x) - (cym.x + cyp.x), -(cxm.y + cxp.y) - (cym.y + cyp.y));
+            if (eps_nl) {
+                const cplx en = vload(eps_nl + (size_t)ix * ny + iy);
+                c0.x += en.x * w2e0;
+                c0.y += en.y * w2e0;
+            }
+            cplx acc = cmul(c0, xcc);
+            cfma(acc, cxm, xc[r]);
+            cfma(acc, cxp, xc[r + 2]);
+            cfma(acc, cym, xd);
+            cfma(acc, cyp, xu);
+            if (active) vstore(y + voff + (size_t)ix * ny + iy, acc);
+        }
+    }
+}
+
 // complex64 variant with TWO adjacent y columns per thread: every access is a 16-byte float4 (the same bytes
 // in flight per thread as the complex128 kernel), the pair's inner y-neighbours are the thread's own values,
 // the outer ones come from the adjacent lanes.  Arithmetic is fp32 here (float coefficient tables): at
@@ -425,8 +520,10 @@ static int op_create_impl(FdfdOp** out, int nx, int ny, double omega, double dl,
     // coupling-coefficient tables of the matrix-free Ez stencil
     FDFD_CHECK(cudaMalloc(&op->ax, sizeof(cplx) * 2 * nx));
     FDFD_CHECK(cudaMalloc(&op->ay, sizeof(cplx) * 2 * ny));
-    { pml_products_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->ax, op->ax + nx, op->isxf, op->isxb, nx, 1.0 / (p.m0 * p.dx * p.dx)); ++g_fdfd_launches; }
-    { pml_products_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->ay, op->ay + ny, op->isyf, op->isyb, ny, 1.0 / (p.m0 * p.dy * p.dy)); ++g_fdfd_launches; }
+    // (Ez: divided by mu0'; Hz: by eps0', the permittivity itself is applied per face inside the kernel)
+    const double med = pol == 0 ? p.m0 : p.e0;
+    { pml_products_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->ax, op->ax + nx, op->isxf, op->isxb, nx, 1.0 / (med * p.dx * p.dx)); ++g_fdfd_launches; }
+    { pml_products_kernel<<<ceil_div(ny, 128), 128, 0, op->stream>>>(op->ay, op->ay + ny, op->isyf, op->isyb, ny, 1.0 / (med * p.dy * p.dy)); ++g_fdfd_launches; }
     FDFD_CHECK(cudaMalloc(&op->ax32, sizeof(cplx32) * 2 * nx));
     FDFD_CHECK(cudaMalloc(&op->ay32, sizeof(cplx32) * 2 * ny));
     { narrow_table_kernel<<<ceil_div(2 * nx, 128), 128, 0, op->stream>>>(op->ax, op->ax32, 2 * nx); ++g_fdfd_launches; }
@@ -598,12 +695,28 @@ int op_residual_t(const FdfdOp* op, const V* d_b, const V* d_x, V* d_r, int nvec
 }
 template <class V>
 int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
-    if (op->pol != 0) return op_apply_planes_t<V>(op, d_x, d_y, nvec);
     const V *er, *enl;
     if (eps_of(op, &er, &enl)) return -1;
     RowPlan plan;
     if (slab_begin(op, d_x, nvec, &plan)) return -1;
     AsmParams p = make_params(op);
+    if (op->pol != 0) {
+        const int rows = g_fused_rows == 8 ? 8 : 4;
+        void (*kern)(const V*, const V*, const cplx*, const cplx*, const cplx*, const cplx*, const V*, V*, int, int, double,
+                     double, int, int);
+        if (op->averaging) kern = rows == 8 ? stencil_fused_hz_kernel<8, V, true> : stencil_fused_hz_kernel<4, V, true>;
+        else kern = rows == 8 ? stencil_fused_hz_kernel<8, V, false> : stencil_fused_hz_kernel<4, V, false>;
+        for (int i = 0; i < plan.nranges; ++i) {
+            if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+            dim3 grid(ceil_div(op->ny, 128), ceil_div(plan.r1[i] - plan.r0[i], rows), nvec);
+            kern<<<grid, 128, 0, op->stream>>>(er, enl, op->ax, op->ax + op->nx, op->ay, op->ay + op->ny, d_x, d_y, op->nx,
+                                               op->ny, p.omega * p.omega * p.m0, p.omega * p.omega * p.e0, plan.r0[i],
+                                               plan.r1[i]);
+            ++g_fdfd_launches;
+        }
+        FDFD_CHECK(cudaGetLastError());
+        return 0;
+    }
     if constexpr (std::is_same<V, cplx32>::value) {
         if ((op->ny & 1) == 0 && g_fused_rows32 != 2) {              // two columns per thread, float4 accesses
             const int rows32 = g_fused_rows32 == 8 ? 8 : 4;

@@ -53,12 +53,12 @@ class Communicator:
         return uid.tobytes()
 
     @classmethod
-    def from_torch(cls):
-        """Rank / world / id exchange through the default torch.distributed process group."""
+    def from_torch(cls, group=None):
+        """Rank / world / id exchange through a torch.distributed process group (default: the global one)."""
         import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
         box = [cls.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
+        dist.broadcast_object_list(box, src=0, group=group)
         return cls(rank, world, box[0])
 
     def __del__(self):
@@ -131,7 +131,7 @@ class SlabOperator:
         xe = self.to_ext(np.zeros_like(be[1:-1]) if x0 is None else x0)
         it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
         check(self.lib.fdfd_krylov_solve_host(self.h, None, _lib.ptr(be), _lib.ptr(xe), {"bicgstab": 0, "cocg": 1}[method],
-                                              float(tol), int(maxiter), int(fused and self.pol == "Ez"), int(check_every),
+                                              float(tol), int(maxiter), int(bool(fused)), int(check_every),
                                               None, 0, C.byref(it), C.byref(rr), C.byref(conv)))
         return xe[1:-1].copy(), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
 

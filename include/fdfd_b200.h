@@ -43,6 +43,9 @@ int fdfd_phase_timing(int enable);
 int fdfd_phase_timing_read(double* out13);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur,small */
 int fdfd_phase_timing_read_levels(double* out, int max_levels);   /* out[level * 13 + phase] */
 int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflops);
+/* the same loop run for ~50 ms with the SM clock measured inside the kernel:
+ * out4 = { TFLOP/s, SM MHz during the probe, ms, real flops } */
+int fdfd_dmma_probe_clocked(int warps_per_sm, int independent_accumulators, double* out4);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
 int fdfd_host_unregister(void* host);

@@ -92,8 +92,33 @@ def test_operator_parity_golden(core, golden):
             u = np.random.default_rng(3).standard_normal(eps.shape) + 1j * np.random.default_rng(4).standard_normal(eps.shape)
             ref_y = Aref.dot(u.reshape(-1)).reshape(eps.shape)
             assert relerr(op.dot(u), ref_y) < 1e-14
-            if pol == "Ez":
-                assert relerr(op.dot(u, fused=True), ref_y) < 1e-13
+            assert relerr(op.dot(u, fused=True), ref_y) < 1e-13       # matrix-free kernels, both polarisations
+            if pol == "Hz":                                           # Hz without edge averaging (linalg.py:74-76)
+                op.assemble(eps, averaging=False)
+                Ana = orc.construct_A(omega, eps, dl, npml, pol, L0, averaging=False)
+                ref_na = Ana.dot(u.reshape(-1)).reshape(eps.shape)
+                assert relerr(op.dot(u), ref_na) < 1e-14
+                assert relerr(op.dot(u, fused=True), ref_na) < 1e-13
+
+
+def test_fused_hz_stencil_layouts(core):
+    """The matrix-free Hz kernel (48 B/cell: face weights rebuilt from eps_r by shuffles) on ragged shapes: widths
+    that are not multiples of the warp / CTA, row counts that are not multiples of the rows a thread marches, lossy
+    (complex) permittivity, several vectors per call, and the Kerr diagonal."""
+    rng = np.random.default_rng(31)
+    for (nx, ny), npml in [((33, 31), [4, 5]), ((70, 129), [6, 9]), ((19, 260), [0, 7]), ((128, 128), [10, 10])]:
+        eps = (1 + 5 * rng.random((nx, ny))) * (1 + 0.03j * rng.random((nx, ny)))
+        eps_nl = 0.1 * rng.random((nx, ny))
+        U = rng.standard_normal((2, nx, ny)) + 1j * rng.standard_normal((2, nx, ny))
+        for nl in (None, eps_nl):
+            op = core.MaxwellOperator(OMEGA, eps, 0.03, npml, "Hz", 1e-6, eps_nl=nl)
+            planes = orc.stencil_planes(OMEGA, eps, 0.03, npml, "Hz", 1e-6, eps_nl=nl)
+            ref = np.stack([orc.apply_planes(planes, u) for u in U])
+            assert relerr(op.dot(U), ref) < 1e-14, (nx, ny)
+            assert relerr(op.dot(U, fused=True), ref) < 1e-13, (nx, ny)
+            for rows in (8, 4):
+                _ = op.lib.fdfd_stencil_set_variant(rows, 0)
+                assert relerr(op.dot(U, fused=True), ref) < 1e-13, (nx, ny, rows)
 
 
 def test_apply_multivector_and_nl(core):
@@ -293,8 +318,7 @@ def test_single_slab_operator_matches_whole_grid(core, pol):
     ref = orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6).dot(x.ravel()).reshape(nx, ny)
     assert relerr(slab.dot(x), ref) < 1e-13
     assert relerr(op.dot(x), ref) < 1e-13
-    if pol == "Ez":
-        assert relerr(slab.dot(x, fused=True), ref) < 1e-13
+    assert relerr(slab.dot(x, fused=True), ref) < 1e-13
     b = np.zeros((nx, ny), dtype=complex)
     b[20, 18] = 1j * OMEGA
     sol = orc.sparse_solve(orc.construct_A(OMEGA, eps, 0.05, npml, pol, 1e-6), b).reshape(nx, ny)

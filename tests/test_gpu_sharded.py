@@ -49,8 +49,7 @@ def test_slab_stencil_and_krylov_vs_oracle(world, pol):
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     for o in [out["rank0"]] + out["others"]:
         assert o["slab_apply_rel_err"] < 1e-13
-        if pol == "Ez":
-            assert o["slab_apply_fused_rel_err"] < 1e-13
+        assert o["slab_apply_fused_rel_err"] < 1e-13
         for method in ("slab_bicgstab", "slab_cocg"):
             assert o[method]["relres"] < 1e-10, (method, o[method])
             assert o[method]["rel_l2_vs_oracle"] < 1e-8, (method, o[method])

@@ -103,7 +103,7 @@ def main():
         ref = A.dot(xv.ravel()).reshape(nx, ny)[sl]
         y = slab.dot(xv[sl])
         out["slab_apply_rel_err"] = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
-        if args.pol == "Ez":
+        if True:
             yf = slab.dot(xv[sl], fused=True)
             out["slab_apply_fused_rel_err"] = float(np.linalg.norm(yf - ref) / np.linalg.norm(ref))
         b = np.zeros((nx, ny), dtype=complex)
