@@ -2,6 +2,10 @@
 // looked up with dlsym so the library neither links against nor requires NCCL unless a communicator is made.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include "comm.cuh"
 
 namespace {
@@ -34,6 +38,138 @@ bool sym(F& fn, const char* name) {
     return fn != nullptr;
 }
 }  // namespace
+
+// ------------------------------------------------------------------------------------------
+// in-process transport
+// ------------------------------------------------------------------------------------------
+struct LocalMsg { const void* ptr; size_t count; };
+struct LocalOp { int kind; const void* sbuf; void* rbuf; size_t count; int peer; cudaStream_t st; };   // kind 0 send, 1 recv
+struct LocalHub {
+    int world, refs;
+    bool aborted;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::deque<LocalMsg>> box;      // box[src * world + dst]: posted, not yet consumed
+    std::vector<unsigned long long> posted, consumed;   // per (src, dst) counters
+};
+#define LOCAL_TIMEOUT_S 300
+
+static int local_run(FdfdComm* c, std::vector<LocalOp>& ops) {
+    LocalHub* h = c->hub;
+    // 1. the data of every send must be complete before a peer may copy it
+    for (auto& o : ops)
+        if (o.kind == 0) FDFD_CHECK(cudaStreamSynchronize(o.st));
+    std::vector<std::pair<int, unsigned long long>> mine;       // (slot, ticket) of my posts
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        for (auto& o : ops)
+            if (o.kind == 0) {
+                const int slot = c->rank * h->world + o.peer;
+                h->box[slot].push_back({o.sbuf, o.count});
+                mine.push_back({slot, ++h->posted[slot]});
+            }
+    }
+    h->cv.notify_all();
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(LOCAL_TIMEOUT_S);
+    // 2. receives, in the order they were listed (messages between one pair of ranks match in posting order)
+    for (auto& o : ops) {
+        if (o.kind != 1) continue;
+        const int slot = o.peer * h->world + c->rank;
+        LocalMsg m;
+        {
+            std::unique_lock<std::mutex> lk(h->mu);
+            if (!h->cv.wait_until(lk, deadline, [&] { return h->aborted || !h->box[slot].empty(); }))
+                FDFD_FAIL("in-process communicator: rank %d timed out waiting for rank %d", c->rank, o.peer);
+            if (h->aborted) FDFD_FAIL("in-process communicator aborted (another rank failed)");
+            m = h->box[slot].front();
+            h->box[slot].pop_front();
+        }
+        if (m.count != o.count) {
+            comm_abort(c);
+            FDFD_FAIL("in-process communicator: rank %d expected %zu doubles from rank %d, got %zu", c->rank, o.count,
+                      o.peer, m.count);
+        }
+        FDFD_CHECK(cudaMemcpyAsync(o.rbuf, m.ptr, sizeof(double) * o.count, cudaMemcpyDefault, o.st));
+        FDFD_CHECK(cudaStreamSynchronize(o.st));
+        {
+            std::lock_guard<std::mutex> lk(h->mu);
+            ++h->consumed[slot];
+        }
+        h->cv.notify_all();
+    }
+    // 3. my send buffers are free again once every post has been consumed
+    for (auto& t : mine) {
+        std::unique_lock<std::mutex> lk(h->mu);
+        if (!h->cv.wait_until(lk, deadline, [&] { return h->aborted || h->consumed[t.first] >= t.second; }))
+            FDFD_FAIL("in-process communicator: rank %d timed out waiting for a send to complete", c->rank);
+        if (h->aborted) FDFD_FAIL("in-process communicator aborted (another rank failed)");
+    }
+    return 0;
+}
+static int local_post(FdfdComm* c, const LocalOp& op) {
+    if (op.peer < 0 || op.peer >= c->world || op.peer == c->rank) FDFD_FAIL("in-process communicator: bad peer %d", op.peer);
+    auto* q = static_cast<std::vector<LocalOp>*>(c->pending);
+    q->push_back(op);
+    if (c->group_depth > 0) return 0;
+    std::vector<LocalOp> ops;
+    ops.swap(*q);
+    return local_run(c, ops);
+}
+template <class T, class F>
+static int local_allreduce(FdfdComm* c, T* buf, size_t count, cudaStream_t st, F combine) {
+    // everybody sends to everybody; summed on the host in rank order (test transport: clarity over speed)
+    const int w = c->world;
+    if (w == 1) return 0;
+    const size_t bytes = sizeof(T) * count, dbl = (bytes + 7) / 8;
+    char* tmp = nullptr;
+    FDFD_CHECK(cudaMalloc(&tmp, dbl * 8 * w));
+    FDFD_CHECK(cudaMemcpyAsync(tmp + dbl * 8 * c->rank, buf, bytes, cudaMemcpyDeviceToDevice, st));
+    std::vector<LocalOp> ops;
+    for (int p = 0; p < w; ++p)
+        if (p != c->rank) {
+            ops.push_back({0, tmp + dbl * 8 * c->rank, nullptr, dbl, p, st});
+            ops.push_back({1, nullptr, tmp + dbl * 8 * p, dbl, p, st});
+        }
+    int rc = local_run(c, ops);
+    if (!rc) {
+        std::vector<T> host((dbl * 8 / sizeof(T)) * w), acc(count);
+        if (cudaMemcpy(host.data(), tmp, dbl * 8 * w, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+        const size_t stride = dbl * 8 / sizeof(T);
+        for (size_t i = 0; i < count; ++i) {
+            T v = host[i];
+            for (int p = 1; p < w; ++p) v = combine(v, host[p * stride + i]);
+            acc[i] = v;
+        }
+        if (!rc && cudaMemcpy(buf, acc.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+    }
+    cudaFree(tmp);
+    if (rc && !g_fdfd_err[0]) snprintf(g_fdfd_err, sizeof(g_fdfd_err), "in-process all-reduce failed");
+    return rc;
+}
+
+int comm_create_local(FdfdComm** out, int world) {
+    if (world < 1 || world > 64) FDFD_FAIL("in-process communicator: world size 1..64");
+    LocalHub* h = new LocalHub();
+    h->world = world; h->refs = world; h->aborted = false;
+    h->box.resize((size_t)world * world);
+    h->posted.assign((size_t)world * world, 0);
+    h->consumed.assign((size_t)world * world, 0);
+    for (int r = 0; r < world; ++r) {
+        FdfdComm* c = new FdfdComm();
+        c->nccl = nullptr; c->rank = r; c->world = world; c->hub = h; c->group_depth = 0;
+        c->pending = new std::vector<LocalOp>();
+        out[r] = c;
+    }
+    return 0;
+}
+void comm_abort(FdfdComm* c) {
+    if (!c || !c->hub) return;
+    {
+        std::lock_guard<std::mutex> lk(c->hub->mu);
+        c->hub->aborted = true;
+    }
+    c->hub->cv.notify_all();
+}
 
 int comm_load(const char* path) {
     if (g_nccl.handle) return 0;
@@ -71,26 +207,59 @@ int comm_create(FdfdComm** out, const void* id128, int rank, int world) {
     NCCL_CHECK(g_nccl.CommInitRank(&comm, world, id, rank));
     FdfdComm* c = new FdfdComm();
     c->nccl = comm; c->rank = rank; c->world = world;
+    c->hub = nullptr; c->group_depth = 0; c->pending = nullptr;
     *out = c;
     return 0;
 }
 
 void comm_destroy(FdfdComm* c) {
     if (!c) return;
-    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl);
+    if (c->hub) {
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(c->hub->mu);
+            last = --c->hub->refs == 0;
+        }
+        if (last) delete c->hub;
+        delete static_cast<std::vector<LocalOp>*>(c->pending);
+    } else if (c->nccl && g_nccl.CommDestroy) {
+        g_nccl.CommDestroy((ncclComm_t)c->nccl);
+    }
     delete c;
 }
 
+int comm_group_begin(FdfdComm* c) {
+    if (c->group_depth++ == 0 && !c->hub) NCCL_CHECK(g_nccl.GroupStart());
+    return 0;
+}
+int comm_group_end(FdfdComm* c) {
+    if (c->group_depth <= 0) FDFD_FAIL("comm_group_end without comm_group_begin");
+    if (--c->group_depth > 0) return 0;
+    if (c->hub) {
+        std::vector<LocalOp> ops;
+        ops.swap(*static_cast<std::vector<LocalOp>*>(c->pending));
+        return local_run(c, ops);
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+    return 0;
+}
+
 int comm_send(FdfdComm* c, const void* buf, size_t count, int peer, cudaStream_t st) {
+    if (c->hub) return local_post(c, {0, buf, nullptr, count, peer, st});
     NCCL_CHECK(g_nccl.Send(buf, count, ncclDouble, peer, (ncclComm_t)c->nccl, st));
     return 0;
 }
 int comm_recv(FdfdComm* c, void* buf, size_t count, int peer, cudaStream_t st) {
+    if (c->hub) return local_post(c, {1, nullptr, buf, count, peer, st});
     NCCL_CHECK(g_nccl.Recv(buf, count, ncclDouble, peer, (ncclComm_t)c->nccl, st));
     return 0;
 }
 int comm_sendrecv(FdfdComm* c, const void* sbuf, int send_peer, void* rbuf, int recv_peer, size_t count,
                   cudaStream_t st) {
+    if (c->hub) {
+        if (comm_group_begin(c) || comm_send(c, sbuf, count, send_peer, st) || comm_recv(c, rbuf, count, recv_peer, st)) return -1;
+        return comm_group_end(c);
+    }
     NCCL_CHECK(g_nccl.GroupStart());
     ncclResult_t r1 = g_nccl.Send(sbuf, count, ncclDouble, send_peer, (ncclComm_t)c->nccl, st);
     ncclResult_t r2 = g_nccl.Recv(rbuf, count, ncclDouble, recv_peer, (ncclComm_t)c->nccl, st);
@@ -104,6 +273,12 @@ int comm_halo_exchange(FdfdComm* c, const void* first, const void* last, void* h
     // one NCCL group = one fused kernel for all four transfers.  Per peer the posting order pairs the
     // messages: with two ranks (lower == upper) the peer's first row meets the halo_hi receive, its last row
     // the halo_lo receive.
+    if (c->hub) {
+        if (comm_group_begin(c) || comm_send(c, first, count, lower, st) || comm_send(c, last, count, upper, st) ||
+            comm_recv(c, halo_hi, count, upper, st) || comm_recv(c, halo_lo, count, lower, st))
+            return -1;
+        return comm_group_end(c);
+    }
     NCCL_CHECK(g_nccl.GroupStart());
     ncclResult_t r1 = g_nccl.Send(first, count, ncclDouble, lower, (ncclComm_t)c->nccl, st);
     ncclResult_t r2 = g_nccl.Send(last, count, ncclDouble, upper, (ncclComm_t)c->nccl, st);
@@ -114,10 +289,12 @@ int comm_halo_exchange(FdfdComm* c, const void* first, const void* last, void* h
     return 0;
 }
 int comm_allreduce_sum(FdfdComm* c, void* buf, size_t count, cudaStream_t st) {
+    if (c->hub) return local_allreduce<double>(c, static_cast<double*>(buf), count, st, [](double a, double b) { return a + b; });
     NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)c->nccl, st));
     return 0;
 }
 int comm_allreduce_max_i32(FdfdComm* c, int* buf, size_t count, cudaStream_t st) {
+    if (c->hub) return local_allreduce<int>(c, buf, count, st, [](int a, int b) { return a > b ? a : b; });
     NCCL_CHECK(g_nccl.AllReduce(buf, buf, count, ncclInt32, ncclMax, (ncclComm_t)c->nccl, st));
     return 0;
 }

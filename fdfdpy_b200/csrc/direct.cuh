@@ -35,6 +35,35 @@ struct NdLevel {
     int inplace;  // chain level factorised in place on the previous level's Schur blocks (no assembly pass)
 };
 
+// A front of a level shared by several ranks, stored and factorised DISTRIBUTED by block rows (ndplan.DistFront).
+struct NdDistFrontDesc {      // host view handed over the C ABI
+    int level0, nsteps;       // plan levels [level0, level0 + nsteps) are this front's elimination steps
+    int gbase, gsize;         // ranks gbase .. gbase + gsize - 1 share it
+    int n, nblk;              // compact front size, number of row blocks
+    const int* bstart;        // [nblk + 1] first slot of every block (blocks 0 .. nsteps-1 are the pivot blocks)
+    const int* bowner;        // [nblk]     group rank that owns the block's rows
+    int mc1, mc2;             // ring sizes of the two children
+    const int* inv1;          // [n] front slot -> position in child 1's ring (-1: none)
+    const int* inv2;
+};
+
+struct NdDistFront {
+    int level0, nsteps, gbase, gsize, grank, cidx, n, nblk, kfull, m, kmax_step;
+    std::vector<int> bstart, bowner, lrow0;   // lrow0[j]: first local row of block j (-1: not mine)
+    std::vector<int> nloc_of;                 // local row count of every group rank
+    int nloc;
+    int mc[2];
+    int *d_inv[2];                            // [n] each
+    int* d_cmap_mine;                         // [mc[cidx]] my child's ring position -> front slot
+    std::vector<int*> d_rows_of;              // per group rank: the front slots of its local rows
+    int* d_lslot;                             // = d_rows_of[grank]
+    long long* d_ring_off;                    // [m] element offset of ring row a inside F (incl. the column origin), -1: not mine
+    std::vector<int> r0;                      // per step: first local row below the pivot block
+    std::vector<cplx*> Einv, G;               // per step: Einv [k][k] (replicated), G [(nloc - r0)][k]
+    cplx* F;                                  // my rows of the front, [nloc][n], lower part valid
+    cplx *vec, *yE, *oring, *gat;             // solve workspace: front vector [n][8], yE [kfull][8], other child's ring, gather buffer
+};
+
 struct NdSolver {
     int nx, ny;
     int tile;                         // (kept for ABI compatibility; the block inversion uses 64-wide base tiles)
@@ -57,10 +86,15 @@ struct NdSolver {
     FdfdComm* comm;
     cplx* xchg;
     size_t xchg_cap;
+    // distributed fronts of the shared levels, in elimination order (front j + 1 is the parent of front j)
+    std::vector<NdDistFront*> dist;
+    cplx *dist_send, *dist_recv, *dist_panel;
+    size_t dist_send_cap, dist_recv_cap, dist_panel_cap;
 };
 
 int nd_create(NdSolver** out, int nx, int ny, int tile);
 int nd_add_level(NdSolver* s, const NdLevelDesc* d);
+int nd_add_dist_front(NdSolver* s, const NdDistFrontDesc* d);   // after fdfd_direct_set_comm and all levels
 void nd_destroy(NdSolver* s);
 int nd_factor(NdSolver* s, const FdfdOp* op);
 // d_b, d_x: [nrhs][nx*ny] device vectors

@@ -239,23 +239,33 @@ stencil_fused_ez_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
 // from lane + 1).  Same traffic as the Ez kernel: x 16 + eps 16 + y 16 = 48 B/cell against the 112 B/cell of the
 // stored planes.  Tables: ax[ix] = (isxf[ix] isxb[ix], isxf[ix] isxb[ix+1]) / (eps0' dx^2), same along y.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ cplx fast_recip_c(cplx z) {
-    // conj(z) / |z|^2 with a Newton-refined hardware reciprocal (|eps| is O(1): no overflow concerns)
-    const double d = z.x * z.x + z.y * z.y;
+// Face weights: W = cplx for a lossy (complex) permittivity, W = double when every eps_r entry is real -- the common
+// lossless case, detected once per assembly -- which halves the arithmetic of the reciprocals and fluxes.
+__device__ __forceinline__ double fast_rcp64(double d) {
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));      // ~20 good bits; two Newton steps reach fp64
     r = r * (2.0 - d * r);
     r = r * (2.0 - d * r);
     r = r * (2.0 - d * r);
-    return make_double2(z.x * r, -z.y * r);
+    return r;
 }
-template <bool AVG>
-__device__ __forceinline__ cplx face_weight(cplx e_lo, cplx e) {
+template <bool AVG> __device__ __forceinline__ void face_weight(cplx e_lo, cplx e, cplx& w) {
     // reciprocal of the permittivity on the LOWER face of a cell holding e, e_lo = the cell below (linalg.py:68-73)
-    return fast_recip_c(AVG ? make_double2(0.5 * (e_lo.x + e.x), 0.5 * (e_lo.y + e.y)) : e);
+    const cplx z = AVG ? make_double2(0.5 * (e_lo.x + e.x), 0.5 * (e_lo.y + e.y)) : e;
+    const double r = fast_rcp64(z.x * z.x + z.y * z.y);
+    w = make_double2(z.x * r, -z.y * r);
 }
+template <bool AVG> __device__ __forceinline__ void face_weight(cplx e_lo, cplx e, double& w) {
+    w = fast_rcp64(AVG ? 0.5 * (e_lo.x + e.x) : e.x);
+}
+__device__ __forceinline__ cplx wmul(cplx w, cplx d) { return cmul(w, d); }
+__device__ __forceinline__ cplx wmul(double w, cplx d) { return make_double2(w * d.x, w * d.y); }
 
-template <int ROWS, class V, bool AVG>
+// The operator in flux form:  (A x)_c = sum over the four faces of  a_face * w_face * (x_neighbour - x_c)  + w^2 mu x_c,
+// where a_face are the 1-D PML products and w_face = 1 / eps on the face.  The flux  w_face (x_c - x_below)  of a
+// face is computed ONCE and used by both cells it couples: along x by the thread that marches the rows, along y by
+// handing the lower-face flux of lane + 1 to lane (one shuffle) instead of shuffling weight and neighbour apart.
+template <int ROWS, class V, bool AVG, class W>
 __global__ void __launch_bounds__(128)
 stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_nl,
                         const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
@@ -268,62 +278,74 @@ stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
     const bool active = iy_raw < ny;
     const int iy = active ? iy_raw : ny - 1;
     const int lane = threadIdx.x & 31;
-    const size_t n = (size_t)nx * ny;
-    const size_t voff = (size_t)blockIdx.z * n;
+    const size_t voff = (size_t)blockIdx.z * nx * ny;
     const V* xv = x + voff;
     const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
     const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || iy_raw >= ny - 1;
     const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
     const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
-    // rows ix0 - 1 .. ix0 + ROWS of x and eps (the ragged last CTA re-reads its last row: results discarded)
+    // rows ix0 - 1 .. ix0 + ROWS of x and eps (a ragged last CTA re-reads the row after its last one: discarded)
     cplx xc[ROWS + 2], e[ROWS + 2];
-    xc[0] = vload(xv + (size_t)ixm * ny + iy);
-    e[0] = vload(eps_r + (size_t)ixm * ny + iy);
+    {
+        const size_t o = (size_t)ixm * ny + iy;
+        xc[0] = vload(xv + o);
+        e[0] = vload(eps_r + o);
+    }
 #pragma unroll
     for (int r = 0; r <= ROWS; ++r) {
-        int ix = ix0 + r;
-        if (r >= rows) ix = ix0 + rows;                // first row past the ones computed here
+        int ix = ix0 + (r < rows ? r : rows);
         if (ix >= nx) ix -= nx;
-        xc[r + 1] = vload(xv + (size_t)ix * ny + iy);
-        e[r + 1] = vload(eps_r + (size_t)ix * ny + iy);
+        const size_t o = (size_t)ix * ny + iy;
+        xc[r + 1] = vload(xv + o);
+        e[r + 1] = vload(eps_r + o);
     }
-    cplx rx[ROWS + 1];
+    // x-fluxes on the ROWS + 1 row faces this thread touches: fx[r] = w (x_r - x_{r-1}), face below row ix0 + r
+    cplx fx[ROWS + 1];
 #pragma unroll
-    for (int r = 0; r <= ROWS; ++r) rx[r] = face_weight<AVG>(e[r], e[r + 1]);
+    for (int r = 0; r <= ROWS; ++r) {
+        W w;
+        face_weight<AVG>(e[r], e[r + 1], w);
+        fx[r] = wmul(w, csub(xc[r + 1], xc[r]));
+    }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (r < rows) {                                // block-uniform
             const int ix = ix0 + r;
+            const size_t rowo = (size_t)ix * ny;
             const cplx axm = ldg_c(axm_t + ix), axp = ldg_c(axp_t + ix);
             const cplx ec = e[r + 1], xcc = xc[r + 1];
-            cplx xd = shfl_up_c(xcc), xu = shfl_down_c(xcc);
-            cplx ed = shfl_up_c(ec);
+            cplx xd = shfl_up_c(xcc), ed = shfl_up_c(ec);
             if (load_dn) {
-                xd = vload(xv + (size_t)ix * ny + iym);
-                ed = vload(eps_r + (size_t)ix * ny + iym);
+                xd = vload(xv + rowo + iym);
+                ed = vload(eps_r + rowo + iym);
             }
-            const cplx ry_lo = face_weight<AVG>(ed, ec);
-            cplx ry_hi = shfl_down_c(ry_lo);
+            W wlo;
+            face_weight<AVG>(ed, ec, wlo);
+            const cplx fy_lo = wmul(wlo, csub(xcc, xd));          // flux through my lower y-face
+            cplx fy_hi = shfl_down_c(fy_lo);                      // = lower-face flux of the cell above
             if (load_up) {
-                xu = vload(xv + (size_t)ix * ny + iyp);
-                ry_hi = face_weight<AVG>(ec, vload(eps_r + (size_t)ix * ny + iyp));
+                W whi;
+                face_weight<AVG>(ec, vload(eps_r + rowo + iyp), whi);
+                fy_hi = wmul(whi, csub(vload(xv + rowo + iyp), xcc));
             }
-            const cplx cxm = cmul(axm, rx[r]), cxp = cmul(axp, rx[r + 1]);
-            const cplx cym = cmul(aym, ry_lo), cyp = cmul(ayp, ry_hi);
-            cplx c0 = make_double2(w2m0 - (cxm.x + cxp.x) - (cym.x + cyp.x), -(cxm.y + cxp.y) - (cym.y + cyp.y));
-            if (eps_nl) {
-                const cplx en = vload(eps_nl + (size_t)ix * ny + iy);
-                c0.x += en.x * w2e0;
-                c0.y += en.y * w2e0;
-            }
-            cplx acc = cmul(c0, xcc);
-            cfma(acc, cxm, xc[r]);
-            cfma(acc, cxp, xc[r + 2]);
-            cfma(acc, cym, xd);
-            cfma(acc, cyp, xu);
-            if (active) vstore(y + voff + (size_t)ix * ny + iy, acc);
+            // A x = axp fx[r+1] - axm fx[r] + ayp fy_hi - aym fy_lo + w^2 mu x   (+ w^2 eps0 eps_nl x)
+            cplx acc = make_double2(w2m0 * xcc.x, w2m0 * xcc.y);
+            if (eps_nl) cfma(acc, cscale(vload(eps_nl + rowo + iy), w2e0), xcc);
+            cfma(acc, axp, fx[r + 1]);
+            cfma(acc, cneg(axm), fx[r]);
+            cfma(acc, ayp, fy_hi);
+            cfma(acc, cneg(aym), fy_lo);
+            if (active) vstore(y + voff + rowo + iy, acc);
         }
     }
+}
+
+// flag[0] = 1 if some entry of eps (n values) has a non-zero imaginary part
+__global__ void eps_imag_kernel(const cplx* __restrict__ eps, size_t n, int* __restrict__ flag) {
+    int any = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        any |= eps[i].y != 0.0;
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // complex64 variant with TWO adjacent y columns per thread: every access is a 16-byte float4 (the same bytes
@@ -497,6 +519,8 @@ static int op_create_impl(FdfdOp** out, int nx, int ny, double omega, double dl,
     FDFD_CHECK(cudaMalloc(&op->eps_r, sizeof(cplx) * n));
     FDFD_CHECK(cudaMalloc(&op->eps_nl, sizeof(cplx) * n));
     FDFD_CHECK(cudaMalloc(&op->planes, sizeof(cplx) * n * 5));
+    FDFD_CHECK(cudaMalloc(&op->d_eps_flag, sizeof(int)));
+    op->eps_real = -1;
     AsmParams p = make_params(op);
     if (!halo) {
         { pml_axis_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, npml_x, p.dx, omega, L0); ++g_fdfd_launches; }
@@ -562,7 +586,7 @@ int op_halo_exchange(const FdfdOp* op, void* xv, size_t elem, cudaStream_t st) {
 void op_destroy(FdfdOp* op) {
     if (!op) return;
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
-    cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes);
+    cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes); cudaFree(op->d_eps_flag);
     if (op->io_buf) cudaFree(op->io_buf);
     cudaFree(op->ax); cudaFree(op->ay); cudaFree(op->ax32); cudaFree(op->ay32);
     if (op->eps32) cudaFree(op->eps32);
@@ -608,9 +632,28 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     if (d_eps_nl && d_eps_nl != op->eps_nl)
         FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, d_eps_nl, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
     AsmParams p = make_params(op);
+    if (op->pol != 0) {                  // lossless permittivity gets the real-weight Hz stencil
+        FDFD_CHECK(cudaMemsetAsync(op->d_eps_flag, 0, sizeof(int), op->stream));
+        { eps_imag_kernel<<<592, 256, 0, op->stream>>>(op->eps_r, n, op->d_eps_flag); ++g_fdfd_launches; }
+        op->eps_real = -1;
+    }
     { assemble_planes_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(
         op->planes, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, p); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Is every eps_r entry real?  Evaluated on the device after an assembly, read back lazily (one 4-byte copy) by the
+// first fused Hz application that needs to choose between the real- and the complex-weight kernel.
+static int op_eps_is_real(const FdfdOp* cop, int* out) {
+    FdfdOp* op = const_cast<FdfdOp*>(cop);
+    if (op->eps_real < 0) {
+        int h = 1;
+        FDFD_CHECK(cudaMemcpyAsync(&h, op->d_eps_flag, sizeof(int), cudaMemcpyDeviceToHost, op->stream));
+        FDFD_CHECK(cudaStreamSynchronize(op->stream));
+        op->eps_real = h ? 0 : 1;
+    }
+    *out = op->eps_real;
     return 0;
 }
 
@@ -702,10 +745,17 @@ int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
     AsmParams p = make_params(op);
     if (op->pol != 0) {
         const int rows = g_fused_rows == 8 ? 8 : 4;
+        int real_eps = 0;
+        if (op_eps_is_real(op, &real_eps)) return -1;
         void (*kern)(const V*, const V*, const cplx*, const cplx*, const cplx*, const cplx*, const V*, V*, int, int, double,
                      double, int, int);
-        if (op->averaging) kern = rows == 8 ? stencil_fused_hz_kernel<8, V, true> : stencil_fused_hz_kernel<4, V, true>;
-        else kern = rows == 8 ? stencil_fused_hz_kernel<8, V, false> : stencil_fused_hz_kernel<4, V, false>;
+        if (real_eps) {
+            if (op->averaging) kern = rows == 8 ? stencil_fused_hz_kernel<8, V, true, double> : stencil_fused_hz_kernel<4, V, true, double>;
+            else kern = rows == 8 ? stencil_fused_hz_kernel<8, V, false, double> : stencil_fused_hz_kernel<4, V, false, double>;
+        } else {
+            if (op->averaging) kern = rows == 8 ? stencil_fused_hz_kernel<8, V, true, cplx> : stencil_fused_hz_kernel<4, V, true, cplx>;
+            else kern = rows == 8 ? stencil_fused_hz_kernel<8, V, false, cplx> : stencil_fused_hz_kernel<4, V, false, cplx>;
+        }
         for (int i = 0; i < plan.nranges; ++i) {
             if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
             dim3 grid(ceil_div(op->ny, 128), ceil_div(plan.r1[i] - plan.r0[i], rows), nvec);

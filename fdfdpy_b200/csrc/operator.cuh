@@ -27,6 +27,8 @@ struct FdfdOp {
     cplx *planes;
     // lazily allocated staging for the *_host entry points (4*nx*ny complex: b, x, f1, f2)
     cplx *io_buf;
+    int* d_eps_flag;    // device flag: some eps_r entry has an imaginary part (Hz fused stencil: complex face weights)
+    int eps_real;       // host copy: 1 all real, 0 not, -1 not read back yet
     cplx32* eps32;      // complex64 copy of eps_r (| eps_nl) for the complex64 stencil, built on first use
     int eps32_valid;
     // slab of a grid split over several GPUs (halo = 1): nx counts the slab's rows PLUS one halo row on each

