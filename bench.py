@@ -287,6 +287,8 @@ def run_ours(args):
     launches = lib.fdfd_launch_count(1)
     gt = np.zeros(6)
     _lib.check(lib.fdfd_gemm_timing_read(_lib.ptr(gt)))
+    exec_fl = C.c_double(0)
+    _lib.check(lib.fdfd_gemm_timing_exec_flops(C.byref(exec_fl)))
     _lib.check(lib.fdfd_gemm_timing(0))
     stats = direct.stats()
     dev_ms = ms.value
@@ -372,8 +374,12 @@ def run_ours(args):
     value = world * ncell / (ms_per_step * 1e-3) / 1e6
     e2e_val = world * ncell / e2e_max / 1e6
     peaks, peak_src = measured_peaks()
-    big_ms, big_fl, big_n = gt[0], gt[1], gt[2]
-    achieved = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
+    big_ms, big_fl, big_n = gt[0] + gt[3], gt[1] + gt[4], gt[2] + gt[5]
+    # The GEMMs compute a complex multiply-add with THREE real tensor products (3M / Karatsuba, zgemm.cuh): the
+    # algorithm's flop count is 6 per complex MAC, and that is what is held against the pipe; the textbook count
+    # (8 per complex MAC, what cuBLAS ZGEMM executes) is reported next to it as the 4M-equivalent rate.
+    achieved = exec_fl.value / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
+    achieved_4m = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
     # FP64 tensor-pipe ceiling: 128 flop/clk/SM (one m8n8k4 DMMA per SM sub-partition every 16 clocks) x 148 SMs at
     # the SM clock sampled under load.  MEASURED_PEAKS.json has no FP64 entry, so the denominator is this pipe rate;
     # the register-resident probe next to it shows how much of it an ideal instruction stream reaches on this board.
@@ -412,7 +418,11 @@ def run_ours(args):
                                    "clock = clock64 / globaltimer measured inside the same kernel"},
             "launches_timed": int(big_n), "kernel_ms_per_step": big_ms / args.steps,
             "share_of_step": big_ms / dev_ms if dev_ms else None,
-            "algorithmic_flops_per_step": big_fl / args.steps,
+            "algorithmic_flops_per_step": exec_fl.value / args.steps,
+            "flops_per_complex_mac": 6,
+            "achieved_4m_equivalent": achieved_4m,
+            "achieved_4m_equivalent_note": "8 flops per complex multiply-add, the count cuBLAS ZGEMM executes "
+                                           "(tools/zgemm_vs_cublas.py: cuBLAS ZGEMM 8192^3 = 36.9 TFLOP/s on this board)",
         },
         "roofline_stencil": {"kernel": "stencil_fused_ez_kernel", "bound": "hbm", "achieved": stencil_gbs,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stencil_gbs / peaks["hbm_gbs"],

@@ -28,6 +28,12 @@ class LevelDesc(C.Structure):
                 ("slot_up", _ip), ("send_to", C.c_int), ("recv_from", C.c_int)]
 
 
+class DistFrontDesc(C.Structure):
+    _fields_ = [("level0", C.c_int), ("nsteps", C.c_int), ("gbase", C.c_int), ("gsize", C.c_int), ("n", C.c_int),
+                ("nblk", C.c_int), ("bstart", _ip), ("bowner", _ip), ("mc1", C.c_int), ("mc2", C.c_int),
+                ("inv1", _ip), ("inv2", _ip)]
+
+
 # name -> (restype, argtypes); mirrors include/fdfd_b200.h one to one
 SIGNATURES = {
     "fdfd_version": (C.c_int, []),
@@ -45,6 +51,7 @@ SIGNATURES = {
     "fdfd_timer_stop": (C.c_int, [_vp, _dp]),
     "fdfd_gemm_timing": (C.c_int, [C.c_int]),
     "fdfd_gemm_timing_read": (C.c_int, [_vp]),
+    "fdfd_gemm_timing_exec_flops": (C.c_int, [_dp]),
     "fdfd_dmma_peak": (C.c_int, [_dp]),
     "fdfd_phase_timing": (C.c_int, [C.c_int]),
     "fdfd_phase_timing_read": (C.c_int, [_vp]),
@@ -82,6 +89,9 @@ SIGNATURES = {
     "fdfd_comm_destroy": (None, [_vp]),
     "fdfd_comm_allreduce_sum_dev": (C.c_int, [_vp, _vp, _vp, C.c_double]),
     "fdfd_direct_set_comm": (C.c_int, [_vp, _vp]),
+    "fdfd_direct_add_dist_front": (C.c_int, [_vp, C.POINTER(DistFrontDesc)]),
+    "fdfd_comm_create_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "fdfd_comm_abort": (None, [_vp]),
     "fdfd_slab_op_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                       C.c_int, C.c_int, C.c_int, C.c_double]),
     "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,

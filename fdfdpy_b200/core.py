@@ -179,8 +179,14 @@ class DirectSolver:
         self.levels = get_plan(op.nx, op.ny)
         self.comm = comm
         if comm is not None and comm.world > 1:
+            import os
             from .ndplan import shard_plan
-            self.levels = shard_plan(self.levels, comm.world, comm.rank)
+            # FDFD_DIST_FRONTS=0: shared fronts live on the lowest rank of their group (the older scheme);
+            # FDFD_DIST_RB: rows per ring block of a distributed front
+            rb = os.environ.get("FDFD_DIST_RB")
+            self.levels = shard_plan(self.levels, comm.world, comm.rank,
+                                     distribute=os.environ.get("FDFD_DIST_FRONTS", "1") != "0",
+                                     rb=int(rb) if rb else None)
             check(self.lib.fdfd_direct_set_comm(self.h, comm.h))
         keep = []
         for lv in self.levels:
@@ -196,6 +202,15 @@ class DirectSolver:
                 keep.append(arr)
                 setattr(d, nme, arr.ctypes.data_as(C.POINTER(C.c_int)))
             check(self.lib.fdfd_direct_add_level(self.h, C.byref(d)))
+        for df in getattr(self.levels, "dist", ()):
+            d = _lib.DistFrontDesc()
+            d.level0, d.nsteps, d.gbase, d.gsize, d.n, d.nblk = df.level0, df.nsteps, df.gbase, df.gsize, df.n, len(df.bowner)
+            d.mc1, d.mc2 = df.mc
+            for nme, arr in (("bstart", df.bstart), ("bowner", df.bowner), ("inv1", df.inv[0]), ("inv2", df.inv[1])):
+                arr = as_i32(arr)
+                keep.append(arr)
+                setattr(d, nme, arr.ctypes.data_as(C.POINTER(C.c_int)))
+            check(self.lib.fdfd_direct_add_dist_front(self.h, C.byref(d)))
         del keep
         self.factored = False       # cached factors belong to the operator's CURRENT planes
         self.has_factors = False    # some factorisation is cached (possibly of an earlier operator state)

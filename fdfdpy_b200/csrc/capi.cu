@@ -177,7 +177,7 @@ int fdfd_dmma_probe_clocked(int warps, int nacc, double* out4) {
 
 int fdfd_gemm_timing(int enable) {
     for (cudaEvent_t e : g_zgemm_timing.ev) cudaEventDestroy(e);
-    g_zgemm_timing.ev.clear(); g_zgemm_timing.flops.clear(); g_zgemm_timing.big.clear();
+    g_zgemm_timing.ev.clear(); g_zgemm_timing.flops.clear(); g_zgemm_timing.big.clear(); g_zgemm_timing.tflops_exec.clear();
     g_zgemm_timing.on = enable != 0;
     return 0;
 }
@@ -192,6 +192,13 @@ int fdfd_gemm_timing_read(double* out) {
         int o = g_zgemm_timing.big[i] ? 0 : 3;
         out[o] += ms; out[o + 1] += g_zgemm_timing.flops[i]; out[o + 2] += 1;
     }
+    return 0;
+}
+/* real flops the tensor pipe executed in the launches timed so far (6 per complex multiply-add with the 3M form) */
+int fdfd_gemm_timing_exec_flops(double* out) {
+    double t = 0;
+    for (double v : g_zgemm_timing.tflops_exec) t += v;
+    *out = t;
     return 0;
 }
 int fdfd_phase_timing(int enable) {
@@ -429,6 +436,14 @@ int fdfd_slab_op_create(fdfd_op** out, fdfd_comm* comm, int gnx, int ny, int x0,
     if (!(omega > 0) || !(dl > 0) || !(L0 > 0)) FDFD_FAIL("omega, dl and L0 must be positive");
     if (npml_x < 0 || npml_y < 0) FDFD_FAIL("NPML entries must be >= 0");
     return op_create_slab(out, comm, gnx, ny, x0, nxl, omega, dl, npml_x, npml_y, pol, L0);
+}
+int fdfd_comm_create_local(fdfd_comm** out, int world) { return comm_create_local(out, world); }
+void fdfd_comm_abort(fdfd_comm* c) { comm_abort(c); }
+int fdfd_direct_add_dist_front(fdfd_direct* s, const fdfd_dist_front_desc* d) {
+    NdDistFrontDesc x;
+    x.level0 = d->level0; x.nsteps = d->nsteps; x.gbase = d->gbase; x.gsize = d->gsize; x.n = d->n; x.nblk = d->nblk;
+    x.bstart = d->bstart; x.bowner = d->bowner; x.mc1 = d->mc1; x.mc2 = d->mc2; x.inv1 = d->inv1; x.inv2 = d->inv2;
+    return nd_add_dist_front(s, &x);
 }
 int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c) {
     s->comm = c;

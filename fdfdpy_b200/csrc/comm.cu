@@ -52,7 +52,11 @@ struct LocalHub {
     std::vector<std::deque<LocalMsg>> box;      // box[src * world + dst]: posted, not yet consumed
     std::vector<unsigned long long> posted, consumed;   // per (src, dst) counters
 };
-#define LOCAL_TIMEOUT_S 300
+static int local_timeout_s() {
+    const char* e = getenv("FDFD_LOCAL_TIMEOUT_S");
+    int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 120;
+}
 
 static int local_run(FdfdComm* c, std::vector<LocalOp>& ops) {
     LocalHub* h = c->hub;
@@ -70,7 +74,7 @@ static int local_run(FdfdComm* c, std::vector<LocalOp>& ops) {
             }
     }
     h->cv.notify_all();
-    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(LOCAL_TIMEOUT_S);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(local_timeout_s());
     // 2. receives, in the order they were listed (messages between one pair of ranks match in posting order)
     for (auto& o : ops) {
         if (o.kind != 1) continue;

@@ -771,6 +771,8 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->ws_bsplit_cap = 0;
     s->xchg = nullptr;
     s->xchg_cap = 0;
+    s->dist_send = s->dist_recv = s->dist_panel = nullptr;
+    s->dist_send_cap = s->dist_recv_cap = s->dist_panel_cap = 0;
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
     *out = s;
     return 0;
@@ -842,8 +844,10 @@ static void free_level_factors(NdLevel& L) {
     L.Einv = L.G = nullptr;
 }
 
+static void dist_destroy(NdSolver* s);
 void nd_destroy(NdSolver* s) {
     if (!s) return;
+    dist_destroy(s);
     for (auto& L : s->levels) {
         free_level_factors(L);
         int* ptrs[] = {L.cls, L.k_cls, L.ch1, L.ch2, L.c1map, L.c2map, L.inv1, L.inv2,
@@ -960,6 +964,8 @@ static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, l
     return 0;
 }
 
+#include "distfront.cuh"
+
 // one arena for all transient factorisation buffers: two ping-pong front batches plus the workspace
 // stack of the block inversion, sized for the largest level; allocated once and kept
 static int ensure_factor_workspace(NdSolver* s) {
@@ -976,6 +982,7 @@ static int ensure_factor_workspace(NdSolver* s) {
         maxW = std::max(maxW, (size_t)L.nb * inv_ws_need(L.kmax));
         if (L.send_to >= 0 || L.recv_from >= 0) maxX = std::max(maxX, (size_t)L.child_mmax * L.child_mmax);
     }
+    for (const NdDistFront* f : s->dist) maxW = std::max(maxW, inv_ws_need(f->kmax_step));
     if (maxX > s->xchg_cap) {
         if (s->xchg) cudaFree(s->xchg);
         s->xchg = nullptr;
@@ -1014,6 +1021,15 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     for (size_t li = 0; li < s->levels.size(); ++li) {
         NdLevel& L = s->levels[li];
         g_phase_timing.level = (int)li;
+        int dj = 0;
+        if (NdDistFront* df = dist_at_level(s, (int)li, &dj)) {
+            // a front shared by several ranks: levels li .. li + nsteps - 1 are its elimination steps
+            if (dj == 0 && (!Fprev || prev_m != df->mc[df->cidx])) FDFD_FAIL("distributed front: local child size mismatch");
+            const cplx* cbase = dj == 0 ? Fprev + (size_t)prev_k * prev_n + prev_k : nullptr;
+            if (dist_factor(s, df, dj > 0 ? s->dist[dj - 1] : nullptr, cbase, prev_n, st)) return -1;
+            li += df->nsteps - 1;
+            continue;
+        }
         const long long nb = L.nb;
         const int nmax = L.nmax, kmax = L.kmax, mmax = L.mmax;
         // A chain level that continues the elimination of the same fronts works IN PLACE on the previous Schur
@@ -1211,6 +1227,13 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         NdLevel& L = s->levels[li];
         g_phase_timing.level = (int)li;
         PhaseScope phf(PH_SOLVE_FWD, st);
+        int dj = 0;
+        if (NdDistFront* df = dist_at_level(s, (int)li, &dj)) {
+            const cplx* my_ring = dj == 0 ? ring_prev : s->dist[dj - 1]->vec + (size_t)s->dist[dj - 1]->kfull * NR;
+            if (dist_forward<NR>(s, df, my_ring, st)) return -1;
+            li += df->nsteps - 1;
+            continue;
+        }
         const long long nb = L.nb;
         // sharded tree: the second child's ring right-hand side arrives in slot 1 of the child batch
         const size_t ring_cnt = 2 * (size_t)L.child_mmax * NR;
@@ -1241,6 +1264,17 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         NdLevel& L = s->levels[li];
         g_phase_timing.level = (int)li;
         PhaseScope phb(PH_SOLVE_BWD, st);
+        {
+            bool handled = false;
+            for (size_t dj = 0; dj < s->dist.size() && !handled; ++dj) {
+                NdDistFront* df = s->dist[dj];
+                if ((size_t)(df->level0 + df->nsteps - 1) != li) continue;
+                if (dist_backward<NR>(s, df, dj + 1 < s->dist.size() ? s->dist[dj + 1] : nullptr, st)) return -1;
+                li = (size_t)df->level0;          // the loop's decrement moves on to the level below the front
+                handled = true;
+            }
+            if (handled) continue;
+        }
         const long long nb = L.nb;
         const NdLevel* Pp = li + 1 < nlev ? &s->levels[li + 1] : nullptr;
         const bool remote_child = Pp && Pp->recv_from >= 0, from_parent = Pp && Pp->send_to >= 0;
@@ -1252,6 +1286,12 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
             long long tot = (long long)P.nb * 2 * P.child_mmax;
             { child_scatter_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(u, u_par, P.cls, P.ch1, P.ch2, P.c1map, P.c2map,
                                                                          P.nmax, P.child_mmax, L.kmax, L.nmax, P.nb); ++g_fdfd_launches; }
+        }
+        if (!s->dist.empty() && (size_t)s->dist[0]->level0 == li + 1 && nb > 0) {
+            // my local front is a child of the first distributed front: its ring solution comes out of that front's vector
+            const NdDistFront* df = s->dist[0];
+            { dist_child_ring_kernel<NR><<<ceil_div(df->mc[df->cidx], 128), 128, 0, st>>>(u, df->vec, df->d_cmap_mine,
+                                                                                       df->mc[df->cidx], L.kmax); ++g_fdfd_launches; }
         }
         // sharded tree: the remote child's ring solution (slot 1) goes back to the rank that owns it
         if (remote_child && comm_send(s->comm, u + vec_cnt, 2 * vec_cnt, Pp->recv_from, st)) return -1;

@@ -8,9 +8,12 @@
 // outside diagonal tiles).
 //
 // All matrices are row-major interleaved complex (re, im) with leading dimensions and 64-bit
-// batch strides.  A complex product is four real DMMA products; the tiles are split into real
-// and imaginary planes when they are staged in shared memory so every fragment load is a plain
-// conflict-free LDS.64 (leading dimensions are = 4 mod 16 doubles).
+// batch strides.  A complex product is THREE real DMMA products (Karatsuba / "3M"):
+//        T1 = Ar Br,  T2 = Ai Bi,  T3 = (Ar + Ai)(Br + Bi);   Re C = T1 - T2,  Im C = T3 - T1 - T2,
+// i.e. 6 real flops per complex multiply-add on the tensor pipe instead of the 8 of the textbook form (M3 = false
+// keeps that "4M" form: the pipe is the limiter of this kernel, so 3M is a straight 4/3 on the mainloop).  3M is
+// normwise backward stable like 4M; what it gives up is componentwise accuracy of a small imaginary part next to
+// a large real one, which the fp64 residual refinement of the solver does not depend on.
 //
 // Warp tile 16 (M) x 32 (N) complex; CTA = WM x WN warps.
 #pragma once
@@ -46,7 +49,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // are LDS.128.  Leading dimensions LDA = 4 mod 8 and LDB = 2 mod 8 complex make every 8-lane phase of
 // those loads hit eight different 16-byte bank groups.
 // (mma.sync m16n8k16 f64 was tried: ptxas lowers it to eight DMMA.8x8x4 on sm_100a and it ran ~6 % slower.)
-template <int WM, int WN, int STAGES, bool TB>
+template <int WM, int WN, int STAGES, bool TB, bool M3>
 __global__ void __launch_bounds__(WM * WN * 32)
 zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     constexpr int BM = 16 * WM, BN = 32 * WN, BK = 16, NT = WM * WN * 32;
@@ -70,11 +73,13 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
     const int wm = warp / WN, wn = warp % WN;
     const int gq = lane >> 2, tq = lane & 3;
 
-    double cr[2][4][2], ci[2][4][2];
+    // 4M: cr, ci (t3 unused);  3M: cr = T1, ci = T2, t3 = T3
+    double cr[2][4][2], ci[2][4][2], t3[2][4][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j)
+            cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0;
 
     auto load_tile = [&](int stage, int kt) {
         const int k0 = kt * BK;
@@ -131,18 +136,46 @@ zgemm_dmma_kernel(GemmBatch g, int tiles_m, int tiles_n) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
                 bq[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+            if (M3) {
+                double as_[2], bs_[4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < 2; ++mt) as_[mt] = a[mt].x + a[mt].y;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
-                }
+                for (int nt = 0; nt < 4; ++nt) bs_[nt] = bq[nt].x + bq[nt].y;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].y);
+                        dmma884(t3[mt][nt][0], t3[mt][nt][1], as_[mt], bs_[nt]);
+                    }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
+                    }
+            }
         }
     }
     cp_async_wait<0>();
+    if (M3) {               // (T1, T2, T3) -> (Re, Im)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double p1 = cr[mt][nt][e], p2 = ci[mt][nt][e];
+                    cr[mt][nt][e] = p1 - p2;
+                    ci[mt][nt][e] = t3[mt][nt][e] - p1 - p2;
+                }
+    }
 
     // epilogue: each thread owns, per (mt, nt), two adjacent complex entries of one row
 #pragma unroll
@@ -194,7 +227,7 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned tile, unsigned tiles_p
     return t;
 }
 
-template <int STAGES, bool TB>
+template <int STAGES, bool TB, bool M3>
 __global__ void __launch_bounds__(256, 1)
 zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles) {
     constexpr int WN = 2, BM = 64, BN = 64, BK = 16;
@@ -271,7 +304,7 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         issue_load();
         cp_async_commit();
     }
-    double cr[2][4][2], ci[2][4][2];
+    double cr[2][4][2], ci[2][4][2], t3[2][4][2];       // 3M: cr = T1, ci = T2, t3 = T3
     cplx cpre[2][4][2];
     int stage = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -281,7 +314,8 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+            for (int j = 0; j < 4; ++j)
+                cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0;
       for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -315,20 +349,39 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
                 bq[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+            if (M3) {
+                double as_[2], bs_[4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < 2; ++mt) as_[mt] = a[mt].x + a[mt].y;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
-                }
+                for (int nt = 0; nt < 4; ++nt) bs_[nt] = bq[nt].x + bq[nt].y;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
-                    dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
-                }
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].y);
+                    }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], as_[mt], bs_[nt]);
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
+                    }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
+                    }
+            }
             if (kk == 0) {
                 // refill the stage consumed in the previous iteration; issued here, under the first
                 // k-step's DMMAs, so the tensor pipe is not idle while the copies are set up
@@ -348,7 +401,9 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         if (col + e < g.N) {
-                            cplx v = make_double2(cr[mt][nt][e], ci[mt][nt][e]);
+                            cplx v = M3 ? make_double2(cr[mt][nt][e] - ci[mt][nt][e],
+                                                       t3[mt][nt][e] - cr[mt][nt][e] - ci[mt][nt][e])
+                                        : make_double2(cr[mt][nt][e], ci[mt][nt][e]);
                             if (g.mode == 1) v = make_double2(cpre[mt][nt][e].x - v.x, cpre[mt][nt][e].y - v.y);
                             else if (g.mode == 2) v = make_double2(-v.x, -v.y);
                             p[e] = v;
@@ -371,19 +426,21 @@ constexpr size_t zgemm_smem_bytes() {
 struct ZgemmTiming {
     bool on = false;
     std::vector<cudaEvent_t> ev;      // start/stop pairs
-    std::vector<double> flops;        // real flops of each launch (8 per complex MAC)
+    std::vector<double> flops;        // algorithmic real flops of each launch (8 per complex MAC)
+    std::vector<double> tflops_exec;  // real flops the tensor pipe executed (6 per complex MAC with 3M)
     std::vector<int> big;             // 1: 64x64-tile kernel, 0: 32x32-tile kernel
 };
 extern ZgemmTiming g_zgemm_timing;
-extern int g_zgemm_variant;   // 0: persistent kernel for large problems, 1: always the tiled kernel
+extern int g_zgemm_variant;   // bit 0: always the tiled kernel (default: persistent kernel for large problems);
+                              // bit 1: textbook 4M complex products (default: 3M)
 
-template <bool TB>
+template <bool TB, bool M3>
 static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
     if (g.M <= 32 && g.N <= 32) {
         int tm = (g.M + 31) / 32, tn = (g.N + 31) / 32;
         long long blocks = (long long)tm * tn * g.batch;
         constexpr size_t sm = zgemm_smem_bytes<2, 1, 2, TB>();
-        zgemm_dmma_kernel<2, 1, 2, TB><<<(unsigned)blocks, 64, sm, stream>>>(g, tm, tn);
+        zgemm_dmma_kernel<2, 1, 2, TB, M3><<<(unsigned)blocks, 64, sm, stream>>>(g, tm, tn);
         ++g_fdfd_launches;
         return 0;
     }
@@ -394,24 +451,24 @@ static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
         snprintf(g_fdfd_err, sizeof(g_fdfd_err), "zgemm grid too large");
         return -1;
     }
-    if (g_zgemm_variant == 0 && blocks >= 148) {
+    if ((g_zgemm_variant & 1) == 0 && blocks >= 148) {
         constexpr int ST = 4;
         constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB>();
         static bool attr_p = false;
         if (!attr_p) {
-            cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sm);
             attr_p = true;
         }
-        zgemm_dmma_persistent_kernel<ST, TB><<<148, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+        zgemm_dmma_persistent_kernel<ST, TB, M3><<<148, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
     } else {
         constexpr size_t sm = zgemm_smem_bytes<4, 2, 3, TB>();
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(zgemm_dmma_kernel<4, 2, 3, TB, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             attr_set = true;
         }
-        zgemm_dmma_kernel<4, 2, 3, TB><<<(unsigned)((long long)tm * tn * g.batch), 256, sm, stream>>>(g, tm, tn);
+        zgemm_dmma_kernel<4, 2, 3, TB, M3><<<(unsigned)((long long)tm * tn * g.batch), 256, sm, stream>>>(g, tm, tn);
     }
     ++g_fdfd_launches;
     return 0;
@@ -429,7 +486,9 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    int rc = g.transb ? zgemm_launch<true>(g, stream) : zgemm_launch<false>(g, stream);
+    const bool m3 = (g_zgemm_variant & 2) == 0;
+    int rc = g.transb ? (m3 ? zgemm_launch<true, true>(g, stream) : zgemm_launch<true, false>(g, stream))
+                      : (m3 ? zgemm_launch<false, true>(g, stream) : zgemm_launch<false, false>(g, stream));
     if (rc) return rc;
     if (g_zgemm_timing.on) {
         cudaEventRecord(e1, stream);
@@ -438,6 +497,7 @@ static inline int zgemm_batched(const GemmBatch& g, cudaStream_t stream) {
         // flops actually computed: a lower-masked launch does (about) half of M*N*K
         double mn = g.lower ? 0.5 * (double)g.M * ((double)g.N + 64.0) : (double)g.M * (double)g.N;
         g_zgemm_timing.flops.push_back(8.0 * mn * g.K * g.batch);
+        g_zgemm_timing.tflops_exec.push_back((m3 ? 6.0 : 8.0) * mn * g.K * g.batch);
         g_zgemm_timing.big.push_back((g.M <= 32 && g.N <= 32) ? 0 : 1);
     }
     cudaError_t e = cudaGetLastError();

@@ -61,6 +61,24 @@ class Communicator:
         dist.broadcast_object_list(box, src=0, group=group)
         return cls(rank, world, box[0])
 
+    @classmethod
+    def local_group(cls, world):
+        """``world`` in-process communicators (one per host thread; see ``run_ranks``): the multi-rank code paths
+        on a single GPU, transfers are device copies behind a rendezvous instead of NCCL."""
+        lib = _lib.load()
+        _lib.require_gpu()
+        arr = (C.c_void_p * world)()
+        check(lib.fdfd_comm_create_local(arr, int(world)))
+        out = []
+        for r in range(world):
+            c = cls.__new__(cls)
+            c.lib, c.rank, c.world, c.h = lib, r, int(world), C.c_void_p(arr[r])
+            out.append(c)
+        return out
+
+    def abort(self):
+        self.lib.fdfd_comm_abort(self.h)
+
     def __del__(self):
         try:
             if getattr(self, "h", None) and self.h.value:
@@ -68,6 +86,34 @@ class Communicator:
                 self.h = C.c_void_p()
         except Exception:
             pass
+
+
+def run_ranks(world, fn):
+    """Run ``fn(comm)`` for ``world`` in-process ranks, one thread each (ctypes releases the GIL inside the
+    library, so the ranks really overlap); returns the list of results, re-raises the first failure."""
+    import threading
+    comms = Communicator.local_group(world)
+    results, errors = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            results[r] = fn(comms[r])
+        except BaseException as e:          # noqa: B902 - the other ranks must be released whatever went wrong
+            errors[r] = e
+            comms[r].abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None and "aborted" not in str(e):
+            raise e
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
 
 
 def slab_rows(gnx, world, rank):

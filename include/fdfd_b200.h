@@ -38,6 +38,7 @@ int fdfd_timer_start(fdfd_op* op);
 int fdfd_timer_stop(fdfd_op* op, double* ms);
 int fdfd_gemm_timing(int enable);
 int fdfd_gemm_timing_read(double* out6);
+int fdfd_gemm_timing_exec_flops(double* flops);   /* flops the tensor pipe executed (3M: 6 per complex MAC) */
 int fdfd_dmma_peak(double* tflops);
 int fdfd_phase_timing(int enable);
 int fdfd_phase_timing_read(double* out13);   /* ms: assemble,pivot,panel,rowgemm,copy,update,expand,solve_fwd,solve_bwd,stencil,ggemm,schur,small */
@@ -142,6 +143,27 @@ int fdfd_comm_allreduce_sum_dev(fdfd_comm* c, fdfd_op* op, void* d_buf, double c
  * exchange one Schur block / ring vector per level point to point, the solution is summed over
  * ranks (every cell is written by exactly one).  Operator, b and x are replicated on every rank. */
 int fdfd_direct_set_comm(fdfd_direct* s, fdfd_comm* c);
+/* A front of a level shared by `gsize` ranks, distributed over them by block rows (ndplan.DistFront): plan levels
+ * level0 .. level0 + nsteps - 1 are its elimination steps (those levels are added empty, nb = 0, on every rank).
+ * Slots are compact: [pivot piece 0 | ... | pivot piece nsteps-1 | ring]; block j covers slots bstart[j]..bstart[j+1]
+ * and its rows live on group rank bowner[j]; inv1/inv2[p] = position of slot p in the first/second child's ring or -1.
+ * Call after fdfd_direct_set_comm and after every fdfd_direct_add_level, in elimination order.  Every rank of the
+ * group takes part in the front's factorisation (owner inverts the pivot block and broadcasts it, every rank forms its
+ * rows of G and updates its block rows of the Schur complement after an all-gather of the F_RE panel) and substitution. */
+typedef struct {
+    int level0, nsteps, gbase, gsize, n, nblk;
+    const int* bstart;     /* [nblk + 1] */
+    const int* bowner;     /* [nblk] group rank */
+    int mc1, mc2;          /* ring sizes of the two children */
+    const int* inv1;       /* [n] */
+    const int* inv2;       /* [n] */
+} fdfd_dist_front_desc;
+int fdfd_direct_add_dist_front(fdfd_direct* s, const fdfd_dist_front_desc* d);
+/* In-process communicators: `world` ranks inside ONE process (one host thread each; same call surface, transfers are
+ * device copies behind a rendezvous).  out[world].  This is how the multi-rank code paths run on a single-GPU box;
+ * fdfd_comm_abort wakes every rank blocked in the hub with an error (call it when a rank's thread fails). */
+int fdfd_comm_create_local(fdfd_comm** out, int world);
+void fdfd_comm_abort(fdfd_comm* c);
 /* slab operator: rows [x0, x0 + nxl) of a gnx x ny grid (rows = the slow index of the reference's
  * C-ordered fields; a split along the other axis is the same call on the transposed problem).
  * Every array of a slab operator -- eps_r for fdfd_op_assemble_*, x / y / b of fdfd_op_apply_* and
@@ -196,7 +218,8 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, 
 
 /* rows each thread of the fused Ez stencil marches (2, 4, 8; defaults 4 for complex128, 8 for complex64) */
 int fdfd_stencil_set_variant(int rows_per_thread, int complex64);
-/* kernel selection for A/B measurements: 0 = persistent kernel for large problems (default), 1 = tiled only */
+/* kernel selection for A/B measurements (bit mask): bit 0 = tiled kernel only (default: persistent kernel for large
+ * problems); bit 1 = textbook 4M complex products (default: 3M Karatsuba products, 6 tensor flops per complex MAC) */
 int fdfd_zgemm_set_variant(int v);
 /* 1 (default): levels of tiny fronts (k <= 32) run as one fused kernel each; 0: generic path everywhere */
 int fdfd_direct_set_small_fronts(int enable);

@@ -47,6 +47,34 @@ def test_zgemm_hook():
                 assert relerr(C, ref) < 1e-14, (M, N, K, batch, mode, transb)
 
 
+def test_zgemm_4m_variant_matches():
+    """The textbook 4M complex product stays available (fdfd_zgemm_set_variant bit 1) and agrees with the default 3M
+    form to rounding; both against numpy."""
+    from fdfdpy_b200 import _lib
+    lib = _lib.load()
+    _lib.require_gpu()
+    rng = np.random.default_rng(2)
+    for (M, N, K, batch) in [(150, 170, 90, 2), (1100, 900, 260, 1), (30, 28, 11, 9)]:
+        A = rng.standard_normal((batch, M, K)) + 1j * rng.standard_normal((batch, M, K))
+        B = rng.standard_normal((batch, N, K)) + 1j * rng.standard_normal((batch, N, K))
+        ref = A @ np.transpose(B, (0, 2, 1))
+        outs = []
+        for variant in (0, 2, 1, 3):
+            _lib.check(lib.fdfd_zgemm_set_variant(variant))
+            C = np.zeros((batch, M, N), dtype=complex)
+            _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, batch, 0, 1, 0))
+            assert relerr(C, ref) < 1e-14, (M, N, K, variant)
+            outs.append(C)
+        _lib.check(lib.fdfd_zgemm_set_variant(0))
+        assert relerr(outs[0], outs[1]) < 1e-14
+    # a purely real product keeps a clean imaginary part under 3M too (T3 - T1 - T2 cancels to rounding of |Re|)
+    A = rng.standard_normal((1, 200, 300)) + 0j
+    B = rng.standard_normal((1, 180, 300)) + 0j
+    C = np.zeros((1, 200, 180), dtype=complex)
+    _lib.check(lib.fdfd_zgemm_batched_host(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), 200, 180, 300, 1, 0, 1, 0))
+    assert np.abs(C.imag).max() <= 1e-13 * np.abs(C.real).max()
+
+
 def test_zgemm_lower_schur_update():
     """S -= G F^T on the lower tiles only: the lower triangle is exact, entries of tiles strictly
     above the diagonal tiles are untouched (persistent kernel for the big case, tiled for the small)."""
