@@ -1024,7 +1024,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         int dj = 0;
         if (NdDistFront* df = dist_at_level(s, (int)li, &dj)) {
             // a front shared by several ranks: levels li .. li + nsteps - 1 are its elimination steps
-            if (dj == 0 && (!Fprev || prev_m != df->mc[df->cidx])) FDFD_FAIL("distributed front: local child size mismatch");
+            // (the local child's batch is padded to its level's largest shape class: ring entries keep their positions)
+            if (dj == 0 && (!Fprev || prev_m < df->mc[df->cidx])) FDFD_FAIL("distributed front: local child size mismatch");
             const cplx* cbase = dj == 0 ? Fprev + (size_t)prev_k * prev_n + prev_k : nullptr;
             if (dist_factor(s, df, dj > 0 ? s->dist[dj - 1] : nullptr, cbase, prev_n, st)) return -1;
             li += df->nsteps - 1;

@@ -283,19 +283,22 @@ int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond, const V* d_b, V* d_x,
     FdfdComm* comm = op->comm;
     d_b += pad; d_x += pad;
     cudaStream_t st = op->stream;
-    const int nvec = precond ? 8 : 6;
+    const int nvec = (precond ? 8 : 6) + 1;          // + the last checked iterate (breakdown restarts)
+    int restarts = 0;
     Scratch ws, wsc;
     FDFD_CHECK(cudaMalloc(&ws.base, sizeof(V) * vs * nvec));
     FDFD_CHECK(cudaMalloc(&wsc.base, sizeof(cplx) * (2 * RED_BLOCKS + S_COUNT)));
     if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(V) * vs * nvec, st));
     V *r = static_cast<V*>(ws.base) + pad, *r0 = r + vs, *p = r0 + vs, *v = p + vs, *s = v + vs, *t = s + vs;
     V *ph = precond ? t + vs : p, *sh = precond ? ph + vs : s;
+    V* xbak = (precond ? sh : t) + vs;
     cplx* partial = static_cast<cplx*>(wsc.base);
     cplx* sc = partial + 2 * RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
     cplx h;
     if (check_every < 1) check_every = 1;
     // r = b - A x
+    FDFD_CHECK(cudaMemcpyAsync(xbak, d_x, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
     if (residual_A<V>(op, d_b, d_x, r, c12)) return -1;
     FDFD_CHECK(cudaMemcpyAsync(r0, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
     FDFD_CHECK(cudaMemsetAsync(p, 0, sizeof(V) * n, st));
@@ -333,10 +336,25 @@ int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond, const V* d_b, V* d_x,
         if (it % check_every == 0 || it == maxiter) {
             if (host_scalar(st, sc + S_RR, &h)) return -1;       // ||r||^2 came with the fused update
             res->relres = sqrt(h.x) / bnorm;
-            if (!(res->relres == res->relres)) break;           // NaN: breakdown
+            if (!(res->relres == res->relres) || res->relres > 1e150) {
+                // breakdown (rho or omega ~ 0 poisoned the recurrences): go back to the last checked iterate and
+                // restart the recurrences from its true residual; a few restarts are allowed
+                if (restarts++ >= 5) break;
+                FDFD_CHECK(cudaMemcpyAsync(d_x, xbak, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+                if (residual_A<V>(op, d_b, d_x, r, c12)) return -1;
+                FDFD_CHECK(cudaMemcpyAsync(r0, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+                FDFD_CHECK(cudaMemsetAsync(p, 0, sizeof(V) * n, st));
+                FDFD_CHECK(cudaMemsetAsync(v, 0, sizeof(V) * n, st));
+                FDFD_CHECK(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+                if (dots<V>(st, r0, r, 1, r, r, 1, n, partial, sc, POST_BICG_RHO, 0, 0, RI, comm)) return -1;
+                continue;
+            }
             if (res->relres <= tol) { res->converged = 1; break; }
+            FDFD_CHECK(cudaMemcpyAsync(xbak, d_x, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
         }
     }
+    if (!(res->relres == res->relres) || res->relres > 1e150)
+        FDFD_CHECK(cudaMemcpyAsync(d_x, xbak, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));   // never hand back NaNs
     // report the TRUE residual of the returned iterate
     if (residual_A<V>(op, d_b, d_x, r, c12)) return -1;
     if (dots<V>(st, r, r, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, RI, comm)) return -1;
@@ -356,10 +374,11 @@ int krylov_cocg_t(const FdfdOp* op, const V* d_b, V* d_x, double tol, int maxite
     const int nxo = op->nx - 2 * op->halo;
     cudaStream_t st = op->stream;
     Scratch ws, wsc;
-    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(V) * vs * 4));
+    int restarts = 0;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(V) * vs * 5));
     FDFD_CHECK(cudaMalloc(&wsc.base, sizeof(cplx) * (2 * RED_BLOCKS + S_COUNT)));
-    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(V) * vs * 4, st));
-    V *r = static_cast<V*>(ws.base) + pad, *p = r + vs, *q = p + vs, *bs = q + vs;
+    if (pad) FDFD_CHECK(cudaMemsetAsync(ws.base, 0, sizeof(V) * vs * 5, st));
+    V *r = static_cast<V*>(ws.base) + pad, *p = r + vs, *q = p + vs, *bs = q + vs, *xbak = bs + vs;
     cplx* partial = static_cast<cplx*>(wsc.base);
     cplx* sc = partial + 2 * RED_BLOCKS;
     const int nblk = ceil_div(n, 256);
@@ -371,6 +390,7 @@ int krylov_cocg_t(const FdfdOp* op, const V* d_b, V* d_x, double tol, int maxite
     if (residual_A<V>(op, d_b, d_x, r, nullptr)) return -1;
     { sym_scale_kernel<V><<<nblk, 256, 0, st>>>(r, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
     FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+    FDFD_CHECK(cudaMemcpyAsync(xbak, d_x, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
     if (dots<V>(st, bs, bs, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 0, comm)) return -1;
     if (host_scalar(st, sc + S_RR, &h)) return -1;
     const double bnorm = sqrt(h.x);
@@ -393,10 +413,23 @@ int krylov_cocg_t(const FdfdOp* op, const V* d_b, V* d_x, double tol, int maxite
         if (it % check_every == 0 || it == maxiter) {
             if (host_scalar(st, sc + S_RR, &h)) return -1;
             res->relres = sqrt(h.x) / bnorm;
-            if (!(res->relres == res->relres)) break;
+            if (!(res->relres == res->relres) || res->relres > 1e150) {
+                // COCG breakdown (p^T A p ~ 0 is possible for a complex symmetric indefinite operator): restart from
+                // the last checked iterate with p = r
+                if (restarts++ >= 5) break;
+                FDFD_CHECK(cudaMemcpyAsync(d_x, xbak, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+                if (residual_A<V>(op, d_b, d_x, r, nullptr)) return -1;
+                { sym_scale_kernel<V><<<nblk, 256, 0, st>>>(r, sxf, syf, nxo, op->ny); ++g_fdfd_launches; }
+                FDFD_CHECK(cudaMemcpyAsync(p, r, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
+                if (dots<V>(st, r, r, 0, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RHO, -1, 0, comm)) return -1;
+                continue;
+            }
             if (res->relres <= tol) { res->converged = 1; break; }
+            FDFD_CHECK(cudaMemcpyAsync(xbak, d_x, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
         }
     }
+    if (!(res->relres == res->relres) || res->relres > 1e150)
+        FDFD_CHECK(cudaMemcpyAsync(d_x, xbak, sizeof(V) * n, cudaMemcpyDeviceToDevice, st));
     // true residual in the ORIGINAL (unscaled) system
     if (residual_A<V>(op, d_b, d_x, r, nullptr)) return -1;
     if (dots<V>(st, r, r, 1, d_b, d_b, 1, n, partial, sc, POST_STORE, S_RR, S_TT, 0, comm)) return -1;

@@ -265,8 +265,10 @@ __device__ __forceinline__ cplx wmul(double w, cplx d) { return make_double2(w *
 // where a_face are the 1-D PML products and w_face = 1 / eps on the face.  The flux  w_face (x_c - x_below)  of a
 // face is computed ONCE and used by both cells it couples: along x by the thread that marches the rows, along y by
 // handing the lower-face flux of lane + 1 to lane (one shuffle) instead of shuffling weight and neighbour apart.
+// (32-bit element offsets: the matrix-free kernels are used for grids below 2^31 cells; the address arithmetic of the
+// dozen loads per cell is what this kernel issues most after the fp64 work, so it is kept to one IMAD.WIDE per load.)
 template <int ROWS, class V, bool AVG, class W>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_nl,
                         const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
                         const cplx* __restrict__ aym_t, const cplx* __restrict__ ayp_t,
@@ -276,28 +278,28 @@ stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
     const int rows = min(ROWS, row1 - ix0);
     const int iy_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = iy_raw < ny;
-    const int iy = active ? iy_raw : ny - 1;
+    const unsigned uny = (unsigned)ny;
+    const unsigned iy = active ? (unsigned)iy_raw : uny - 1u;
     const int lane = threadIdx.x & 31;
     const size_t voff = (size_t)blockIdx.z * nx * ny;
     const V* xv = x + voff;
-    const int iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    const unsigned iym = iy == 0 ? uny - 1u : iy - 1u, iyp = iy + 1u == uny ? 0u : iy + 1u;
     const bool load_dn = lane == 0 || iy == 0, load_up = lane == 31 || iy_raw >= ny - 1;
-    const int ixm = ix0 == 0 ? nx - 1 : ix0 - 1;
     const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
-    // rows ix0 - 1 .. ix0 + ROWS of x and eps (a ragged last CTA re-reads the row after its last one: discarded)
-    cplx xc[ROWS + 2], e[ROWS + 2];
-    {
-        const size_t o = (size_t)ixm * ny + iy;
-        xc[0] = vload(xv + o);
-        e[0] = vload(eps_r + o);
-    }
+    // element offsets of column iy in rows ix0 - 1 .. ix0 + ROWS (a ragged last CTA re-reads the row after its last one)
+    unsigned rb[ROWS + 2];
+    rb[0] = (unsigned)(ix0 == 0 ? nx - 1 : ix0 - 1) * uny;
 #pragma unroll
     for (int r = 0; r <= ROWS; ++r) {
         int ix = ix0 + (r < rows ? r : rows);
         if (ix >= nx) ix -= nx;
-        const size_t o = (size_t)ix * ny + iy;
-        xc[r + 1] = vload(xv + o);
-        e[r + 1] = vload(eps_r + o);
+        rb[r + 1] = (unsigned)ix * uny;
+    }
+    cplx xc[ROWS + 2], e[ROWS + 2];
+#pragma unroll
+    for (int r = 0; r < ROWS + 2; ++r) {
+        xc[r] = vload(xv + (rb[r] + iy));
+        e[r] = vload(eps_r + (rb[r] + iy));
     }
     // x-fluxes on the ROWS + 1 row faces this thread touches: fx[r] = w (x_r - x_{r-1}), face below row ix0 + r
     cplx fx[ROWS + 1];
@@ -310,14 +312,13 @@ stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (r < rows) {                                // block-uniform
-            const int ix = ix0 + r;
-            const size_t rowo = (size_t)ix * ny;
-            const cplx axm = ldg_c(axm_t + ix), axp = ldg_c(axp_t + ix);
+            const unsigned rowo = rb[r + 1];
+            const cplx axm = ldg_c(axm_t + ix0 + r), axp = ldg_c(axp_t + ix0 + r);
             const cplx ec = e[r + 1], xcc = xc[r + 1];
             cplx xd = shfl_up_c(xcc), ed = shfl_up_c(ec);
             if (load_dn) {
-                xd = vload(xv + rowo + iym);
-                ed = vload(eps_r + rowo + iym);
+                xd = vload(xv + (rowo + iym));
+                ed = vload(eps_r + (rowo + iym));
             }
             W wlo;
             face_weight<AVG>(ed, ec, wlo);
@@ -325,17 +326,17 @@ stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
             cplx fy_hi = shfl_down_c(fy_lo);                      // = lower-face flux of the cell above
             if (load_up) {
                 W whi;
-                face_weight<AVG>(ec, vload(eps_r + rowo + iyp), whi);
-                fy_hi = wmul(whi, csub(vload(xv + rowo + iyp), xcc));
+                face_weight<AVG>(ec, vload(eps_r + (rowo + iyp)), whi);
+                fy_hi = wmul(whi, csub(vload(xv + (rowo + iyp)), xcc));
             }
             // A x = axp fx[r+1] - axm fx[r] + ayp fy_hi - aym fy_lo + w^2 mu x   (+ w^2 eps0 eps_nl x)
             cplx acc = make_double2(w2m0 * xcc.x, w2m0 * xcc.y);
-            if (eps_nl) cfma(acc, cscale(vload(eps_nl + rowo + iy), w2e0), xcc);
+            if (eps_nl) cfma(acc, cscale(vload(eps_nl + (rowo + iy)), w2e0), xcc);
             cfma(acc, axp, fx[r + 1]);
             cfma(acc, cneg(axm), fx[r]);
             cfma(acc, ayp, fy_hi);
             cfma(acc, cneg(aym), fy_lo);
-            if (active) vstore(y + voff + rowo + iy, acc);
+            if (active) vstore(y + voff + (rowo + iy), acc);
         }
     }
 }
@@ -743,6 +744,7 @@ int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
     RowPlan plan;
     if (slab_begin(op, d_x, nvec, &plan)) return -1;
     AsmParams p = make_params(op);
+    if (op->pol != 0 && op->n() >= (1ull << 31)) return op_apply_planes_t<V>(op, d_x, d_y, nvec);   // 32-bit offsets
     if (op->pol != 0) {
         const int rows = g_fused_rows == 8 ? 8 : 4;
         int real_eps = 0;

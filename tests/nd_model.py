@@ -41,11 +41,14 @@ def _lower_to_full(L):
 
 def factor(levels, planes, nx, ny, dscale, tile=32, comm=None):
     """``comm`` (send(array, dst) / recv(shape, src) / allreduce(array)) runs a plan produced by
-    ndplan.shard_plan: the exchanges sit exactly where nd_factor / nd_solve_chunk put them."""
+    ndplan.shard_plan: the exchanges sit exactly where nd_factor / nd_solve_chunk put them.
+    A plan with distributed fronts (``levels.dist``) continues in ``dist_factor`` after the local levels."""
     c0, cxm, cxp, cym, cyp = [p.reshape(-1) for p in planes]
     store = []
     S_prev = None
-    for lv in levels:
+    dist = list(getattr(levels, "dist", ()))
+    nlocal = dist[0].level0 if dist else len(levels)
+    for lv in levels[:nlocal]:
         if getattr(lv, "send_to", -1) >= 0:
             comm.send(S_prev[0], lv.send_to)
         if getattr(lv, "recv_from", -1) >= 0:
@@ -90,14 +93,122 @@ def factor(levels, planes, nx, ny, dscale, tile=32, comm=None):
         G = FRE @ Einv
         S_prev = np.tril(F[:, k:, k:] - G @ np.transpose(FRE, (0, 2, 1)))   # lower triangle only
         store.append((Einv, G))
+    if dist:
+        store += [None] * (len(levels) - nlocal)
+        store.append(dist_factor(dist, levels, S_prev[0], comm, tile))    # one extra entry: the distributed fronts
     return store
+
+
+# ------------------------------------------------------------------------------------------
+# distributed fronts (ndplan.DistFront), executed the way csrc/distfront.cuh does: block rows dealt to the group,
+# personalised all-to-all assembly, owner inverts the pivot block and broadcasts it, panel all-gather, every rank
+# updates its own block rows; replicated substitution vectors.
+# ------------------------------------------------------------------------------------------
+class _DistState:
+    pass
+
+
+def _group_bcast(comm, df, me, arr, root, shape):
+    if me == root:
+        for p in range(df.gsize):
+            if p != root:
+                comm.send(arr, df.gbase + p)
+        return arr
+    return comm.recv(shape, df.gbase + root)
+
+
+def dist_factor(dist, levels, S_local, comm, tile):
+    """S_local: the Schur block (lower) of this rank's single front on the level below the first distributed front."""
+    rank = comm.dist.get_rank()
+    states = []
+    child_rows, child_S = None, None          # my rows (ring indices) of the child's Schur block, and the rows themselves
+    for j, df in enumerate(dist):
+        me = rank - df.gbase
+        g, n = df.gsize, df.n
+        cidx = 1 if me >= g // 2 else 0
+        inv = df.inv[cidx]
+        if j == 0:
+            child_rows = np.arange(S_local.shape[0])
+            child_S = _lower_to_full(S_local[None])[0]
+        row_of = {a: i for i, a in enumerate(child_rows)}
+        rows_of = [np.concatenate([np.arange(df.bstart[b], df.bstart[b + 1]) for b in range(len(df.bowner)) if df.bowner[b] == o]
+                                  or [np.zeros(0, dtype=int)]).astype(int) for o in range(g)]
+        mine = rows_of[me]
+
+        def pack(dst_rows):
+            out = np.zeros((len(dst_rows), n), dtype=np.complex128)
+            for lp, p in enumerate(dst_rows):
+                a = inv[p]
+                if a < 0:
+                    continue
+                for q in range(p + 1):
+                    b = inv[q]
+                    if b < 0:
+                        continue
+                    hi, lo = max(a, b), min(a, b)
+                    if hi in row_of:                       # the child entry (hi, lo) lives on the rank that owns row hi
+                        out[lp, q] = child_S[row_of[hi], lo]
+            return out
+
+        F = pack(mine)
+        for t in range(1, g):
+            d, src = (me + t) % g, (me - t) % g
+            sbuf = pack(rows_of[d])
+            rb = comm.sendrecv(sbuf if len(rows_of[d]) else None, df.gbase + d,
+                               F.shape if len(mine) else None, df.gbase + src)
+            if rb is not None:
+                F += rb
+        st = _DistState()
+        st.df, st.me, st.cidx, st.mine = df, me, cidx, mine
+        st.Einv, st.G, st.below = [], [], []
+        for sidx in range(df.nsteps):
+            col0, b1 = int(df.bstart[sidx]), int(df.bstart[sidx + 1])
+            k, owner = b1 - col0, int(df.bowner[sidx])
+            Einv = None
+            if me == owner:
+                loc = np.flatnonzero((mine >= col0) & (mine < b1))
+                E = F[loc][:, col0:b1]
+                Einv = gj_inverse(_lower_to_full(E[None]), tile)[0]
+            Einv = _group_bcast(comm, df, me, Einv, owner, (k, k))
+            below = np.flatnonzero(mine >= b1)
+            FRE = F[below][:, col0:b1]
+            G = FRE @ Einv
+            st.Einv.append(Einv)
+            st.G.append(G)
+            st.below.append(below)
+            if b1 == n:
+                continue
+            # all-gather of the F_RE panel in global row order
+            panel = np.zeros((n - b1, k), dtype=np.complex128)
+            for o in range(g):
+                rows_o = rows_of[o][rows_of[o] >= b1]
+                if o == me:
+                    panel[rows_o - b1] = FRE
+                    for p in range(g):
+                        if p != me and len(rows_o):
+                            comm.send(FRE, df.gbase + p)
+                elif len(rows_o):
+                    panel[rows_o - b1] = comm.recv((len(rows_o), k), df.gbase + o)
+            upd = G @ panel.T                               # my rows x all remaining columns
+            for i, li in enumerate(below):
+                p = mine[li]
+                F[li, b1:p + 1] -= upd[i, :p + 1 - b1]     # lower part only
+        states.append(st)
+        ring = np.flatnonzero(mine >= df.kfull)
+        child_rows = mine[ring] - df.kfull
+        child_S = F[ring][:, df.kfull:]
+        # the parent needs full rows of the symmetric block, but only owns the lower part of each: entry (hi, lo) is
+        # looked up on the rank that owns row hi, which is exactly what pack() does -- so the lower part suffices.
+    return states
 
 
 def solve(levels, store, b, nx, ny, dscale, comm=None):
     b = np.asarray(b, dtype=np.complex128).reshape(-1) * dscale
     ring_prev = None
     ysave = []
-    for lv, fac in zip(levels, store):
+    dist = list(getattr(levels, "dist", ()))
+    nlocal = dist[0].level0 if dist else len(levels)
+    for lv, fac in zip(levels[:nlocal], store):
         if getattr(lv, "send_to", -1) >= 0:
             comm.send(ring_prev[0], lv.send_to)
         if getattr(lv, "recv_from", -1) >= 0:
@@ -127,15 +238,20 @@ def solve(levels, store, b, nx, ny, dscale, comm=None):
         fe = f[:, :k]
         ring_prev = f[:, k:] - np.einsum('bmk,bk->bm', G, fe)
         ysave.append(np.einsum('bkj,bj->bk', Einv, fe))
+    top_ring = None
+    if dist:
+        top_ring = dist_solve(store[-1], ring_prev[0], comm)      # ring solution of my last local front
     # backward
     u_parent = None
     out = np.zeros(nx * ny, dtype=np.complex128)
-    for li in range(len(levels) - 1, -1, -1):
+    for li in range(nlocal - 1, -1, -1):
         lv = levels[li]
         k = lv.kmax
-        par = levels[li + 1] if li < len(levels) - 1 else None
+        par = levels[li + 1] if li < nlocal - 1 else None
         remote_child = par is not None and getattr(par, "recv_from", -1) >= 0
         u = np.zeros((lv.nb + (1 if remote_child else 0), lv.nmax), dtype=np.complex128)
+        if par is None and top_ring is not None:
+            u[0, k:k + len(top_ring)] = top_ring
         if par is not None:
             for pb in range(par.nb):
                 c = par.cls[pb]
@@ -165,3 +281,68 @@ def solve(levels, store, b, nx, ny, dscale, comm=None):
     if comm is not None:
         out = comm.allreduce(out)                  # every cell is written by exactly one rank
     return out.reshape(nx, ny)
+
+
+def dist_solve(states, my_ring, comm):
+    """Forward and backward substitution through the distributed fronts; returns the ring solution of this rank's
+    local child front.  Front vectors are replicated inside a group, as in csrc/distfront.cuh."""
+    vecs = []
+    for st in states:
+        df, me, g, n = st.df, st.me, st.df.gsize, st.df.n
+        partner = df.gbase + (me + g // 2) % g
+        mc_mine, mc_other = df.mc[st.cidx], df.mc[1 - st.cidx]
+        my_ring = np.asarray(my_ring)[:mc_mine]
+        if me < g // 2:
+            comm.send(my_ring, partner)
+            other = comm.recv((mc_other,), partner)
+        else:
+            other = comm.recv((mc_other,), partner)
+            comm.send(my_ring, partner)
+        rings = (my_ring, other) if st.cidx == 0 else (other, my_ring)
+        f = np.zeros(n, dtype=np.complex128)
+        for c in (0, 1):
+            ok = df.inv[c] >= 0
+            f[ok] += rings[c][df.inv[c][ok]]
+        yE = np.zeros(df.kfull, dtype=np.complex128)
+        for sidx in range(df.nsteps):
+            col0, b1 = int(df.bstart[sidx]), int(df.bstart[sidx + 1])
+            fE = _group_bcast(comm, df, me, f[col0:b1].copy(), int(df.bowner[sidx]), (b1 - col0,))
+            f[col0:b1] = fE
+            yE[col0:b1] = st.Einv[sidx] @ fE
+            rows = st.mine[st.below[sidx]]
+            f[rows] -= st.G[sidx] @ fE
+        # replicate the ring: every block from its owner
+        for b in range(df.nsteps, len(df.bowner)):
+            sl = slice(int(df.bstart[b]), int(df.bstart[b + 1]))
+            f[sl] = _group_bcast(comm, df, me, f[sl].copy(), int(df.bowner[b]), (sl.stop - sl.start,))
+        vecs.append((f, yE))
+        my_ring = f[df.kfull:]
+    # backward, root first
+    for j in range(len(states) - 1, -1, -1):
+        st = states[j]
+        df, me, g, n = st.df, st.me, st.df.gsize, st.df.n
+        u, yE = vecs[j]
+        if j + 1 < len(states):
+            par = states[j + 1]
+            cmap = np.zeros(par.df.mc[par.cidx], dtype=int)
+            inv = par.df.inv[par.cidx]
+            cmap[inv[inv >= 0]] = np.flatnonzero(inv >= 0)
+            u[df.kfull:] = vecs[j + 1][0][cmap]
+        for sidx in range(df.nsteps - 1, -1, -1):
+            col0, b1 = int(df.bstart[sidx]), int(df.bstart[sidx + 1])
+            part = st.G[sidx].T @ u[st.mine[st.below[sidx]]] if len(st.below[sidx]) else np.zeros(b1 - col0, dtype=np.complex128)
+            parts = [None] * g
+            parts[me] = part
+            for p in range(g):                          # all-gather, summed in rank order on every rank
+                if p == me:
+                    for q in range(g):
+                        if q != me:
+                            comm.send(part, df.gbase + q)
+                else:
+                    parts[p] = comm.recv((b1 - col0,), df.gbase + p)
+            u[col0:b1] = yE[col0:b1] - sum(parts[1:], parts[0])
+    st = states[0]
+    inv = st.df.inv[st.cidx]
+    cmap = np.zeros(st.df.mc[st.cidx], dtype=int)
+    cmap[inv[inv >= 0]] = np.flatnonzero(inv >= 0)
+    return vecs[0][0][cmap]

@@ -31,13 +31,24 @@ class GlooComm:
         self.dist.recv(t, src)
         return out
 
+    def sendrecv(self, sarr, dst, rshape, src):
+        """Both directions at once (non-blocking send), like a grouped NCCL send/recv pair."""
+        req = None
+        if sarr is not None:
+            t = self.torch.from_numpy(np.ascontiguousarray(sarr).view(np.float64).copy())
+            req = self.dist.isend(t, dst)
+        out = self.recv(rshape, src) if rshape is not None else None
+        if req is not None:
+            req.wait()
+        return out
+
     def allreduce(self, arr):
         t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.float64).copy())
         self.dist.all_reduce(t)
         return t.numpy().view(np.complex128)
 
 
-def _worker_direct(rank, world, port, shape, npml, pol, q, split=None):
+def _worker_direct(rank, world, port, shape, npml, pol, q, split=None, distribute=False, rb=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -54,7 +65,7 @@ def _worker_direct(rank, world, port, shape, npml, pol, q, split=None):
         isxf, _, isyf, _ = orc.pml_inverse_factors(omega, 1e-6, (nx, ny), npml, 0.04)
         d = row_scale(isxf, isyf)
         full = build_plan(nx, ny) if split is None else build_plan(nx, ny, split_min=split[0], split_parts=split[1])
-        levels = shard_plan(full, world, rank)
+        levels = shard_plan(full, world, rank, distribute=distribute, rb=rb)
         comm = GlooComm(dist, torch)
         store = factor(levels, planes, nx, ny, d, tile=8, comm=comm)
         b = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
@@ -88,11 +99,67 @@ def test_sharded_elimination_tree_gloo(world, shape, npml, pol, split):
         assert err < 1e-11, (rank, err)
 
 
+@pytest.mark.parametrize("world,shape,npml,pol,split,rb", [(2, (24, 20), [3, 3], "Ez", None, None),
+                                                           (2, (19, 33), [0, 4], "Hz", (6, 3), 5),
+                                                           (4, (32, 28), [3, 3], "Ez", (6, -4), 6),
+                                                           (4, (37, 30), [3, 3], "Hz", (8, 2), 4)])
+def test_distributed_fronts_gloo(world, shape, npml, pol, split, rb):
+    """The DISTRIBUTED top fronts (ndplan.DistFront: block rows dealt to the ranks of a group, all-to-all assembly,
+    pivot owner broadcasts Einv, panel all-gather, replicated substitution vectors) executed by the numpy model over
+    gloo point-to-point messages, against the oracle's sparse solve."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_direct, args=(r, world, port, shape, npml, pol, q, split, True, rb)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, _ in res:
+        assert isinstance(err, float), (rank, err)
+        assert err < 1e-11, (rank, err)
+
+
+def test_dist_front_plan_is_consistent():
+    """Host logic of the distributed fronts: compact slots, block structure, child maps, the same front seen by
+    every rank of its group."""
+    from fdfdpy_b200.ndplan import build_plan, shard_plan
+    for (nx, ny, sm, sp, rb) in [(96, 80, None, None, None), (203, 157, 30, -16, 24), (4096, 4096, None, None, None)]:
+        levels = build_plan(nx, ny, split_min=sm, split_parts=sp)
+        for world in (2, 4, 8):
+            plans = [shard_plan(levels, world, r, rb=rb) for r in range(world)]
+            assert all(len(p.dist) == int(np.log2(world)) for p in plans)
+            for j in range(int(np.log2(world))):
+                for r in range(world):
+                    df = plans[r].dist[j]
+                    assert df.gsize == 2 ** (j + 1) and df.gbase == (r // df.gsize) * df.gsize
+                    twin = plans[df.gbase].dist[j]                    # every rank of the group describes the same front
+                    for k in ("level0", "nsteps", "n", "m", "kfull"):
+                        assert getattr(df, k) == getattr(twin, k)
+                    assert np.array_equal(df.bstart, twin.bstart) and np.array_equal(df.bowner, twin.bowner)
+                    assert df.bstart[0] == 0 and df.bstart[-1] == df.n and np.all(np.diff(df.bstart) > 0)
+                    assert df.bstart[df.nsteps] == df.kfull
+                    assert set(df.bowner.tolist()) <= set(range(df.gsize))
+                    for c in (0, 1):
+                        inv = df.inv[c]
+                        hit = np.sort(inv[inv >= 0])
+                        assert np.array_equal(hit, np.arange(df.mc[c]))      # every child ring node lands exactly once
+                    assert np.all((df.inv[0] >= 0) | (df.inv[1] >= 0))       # every front slot comes from a child
+                    # nodes reached by BOTH children are exactly the separator being closed plus shared corners
+                    if j > 0:
+                        assert plans[r].dist[j - 1].m == df.mc[1 if (r - df.gbase) >= df.gsize // 2 else 0]
+                    assert all(plans[r][df.level0 + s].nb == 0 for s in range(df.nsteps))
+                # the root front ends with an empty ring
+            assert plans[0].dist[-1].m == 0
+
+
 def test_shard_plan_partitions_the_tree():
     from fdfdpy_b200.ndplan import build_plan, shard_plan
     levels = build_plan(96, 80)
     for world in (1, 2, 4, 8):
-        shards = [shard_plan(levels, world, r) for r in range(world)]
+        shards = [shard_plan(levels, world, r, distribute=False) for r in range(world)]
         for l, lv in enumerate(levels):
             gids = np.concatenate([s[l].gids for s in shards])
             assert sorted(gids.tolist()) == list(range(lv.nb))          # every front owned exactly once
