@@ -16,6 +16,7 @@
 #include <algorithm>
 #include "direct.cuh"
 #include "zgemm.cuh"
+#include "mrhs.cuh"
 
 // ------------------------------------------------------------------------------------------
 // assembly
@@ -1249,12 +1250,27 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         else
             { merge_gather_kernel<NR><<<ceil_div(tot, 128), 128, 0, st>>>(f, ring_prev, L.cls, L.ch1, L.ch2, L.inv1,
                                                                         L.inv2, L.nmax, L.child_mmax, nb); ++g_fdfd_launches; }
-        if (L.kmax <= 16)
+        if (L.kmax <= 16) {
             { forward_mv_thread_kernel<NR><<<ceil_div(tot, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
                                                                              L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
-        else
+        } else if constexpr (NR >= 8) {
+            // many right-hand sides: the factor blocks stream once through the tensor-pipe kernel (mrhs.cuh)
+            MrhsArgs a{};
+            a.batch = nb; a.lda = L.kmax; a.K = L.kmax;
+            a.V = f; a.sV = (long long)L.nmax * NR;
+            a.A = L.Einv; a.sA = (long long)L.kmax * L.kmax; a.M = L.kmax;
+            a.D = nullptr; a.C = s->ws_ye + L.ye_off; a.sC = (long long)L.kmax * NR;
+            if (mrhs_launch<NR, false>(a, &s->ws_bsplit, &s->ws_bsplit_cap, st)) return -1;
+            if (L.mmax > 0) {
+                a.A = L.G; a.sA = (long long)L.mmax * L.kmax; a.M = L.mmax;
+                a.D = f + (size_t)L.kmax * NR; a.sD = (long long)L.nmax * NR;
+                a.C = ring_cur; a.sC = (long long)L.mmax * NR;
+                if (mrhs_launch<NR, false>(a, &s->ws_bsplit, &s->ws_bsplit_cap, st)) return -1;
+            }
+        } else {
             { forward_mv_kernel<NR><<<ceil_div(tot * 32, 256), 256, 0, st>>>(L.Einv, L.G, f, s->ws_ye + L.ye_off, ring_cur,
                                                                            L.kmax, L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        }
         FDFD_CHECK(cudaGetLastError());
         std::swap(ring_prev, ring_cur);
     }
@@ -1303,6 +1319,20 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
         if (L.kmax <= 16 && L.mmax <= 128) {
             { backward_mvt_thread_kernel<NR><<<ceil_div(nb * L.kmax, 128), 128, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
                                                                                        L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+        } else if constexpr (NR >= 8) {
+            // u_E = yE - G^T u_R for all NR right-hand sides at once on the tensor pipe (mrhs.cuh)
+            MrhsArgs a{};
+            a.batch = nb; a.lda = L.kmax; a.M = L.kmax; a.K = L.mmax;
+            a.A = L.G; a.sA = (long long)L.mmax * L.kmax;
+            a.V = u + (size_t)L.kmax * NR; a.sV = (long long)L.nmax * NR;
+            a.D = s->ws_ye + L.ye_off; a.sD = (long long)L.kmax * NR;
+            a.C = u; a.sC = (long long)L.nmax * NR;
+            if (L.mmax > 0) {
+                if (mrhs_launch<NR, true>(a, &s->ws_bsplit, &s->ws_bsplit_cap, st)) return -1;
+            } else {
+                FDFD_CHECK(cudaMemcpy2DAsync(u, sizeof(cplx) * L.nmax * NR, s->ws_ye + L.ye_off, sizeof(cplx) * L.kmax * NR,
+                                             sizeof(cplx) * L.kmax * NR, nb, cudaMemcpyDeviceToDevice, st));
+            }
         } else if (nsplit >= 2) {
             // few fronts, long rings: also split the ring rows over CTAs (two-pass, fixed summation order)
             const size_t need = (size_t)nsplit * nb * L.kmax * NR;
@@ -1314,13 +1344,17 @@ static int nd_solve_chunk(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* 
                 s->ws_bsplit_cap = need;
             }
             const int rows_per = ceil_div(L.mmax, nsplit);
-            dim3 grid(ecta, nsplit);
-            { backward_mvt_split_kernel<NR><<<grid, 256, 0, st>>>(L.G, u, s->ws_bsplit, L.kmax, L.mmax, L.nmax, nb, rows_per); ++g_fdfd_launches; }
-            { backward_mvt_reduce_kernel<NR><<<ceil_div(nb * L.kmax, 128), 128, 0, st>>>(s->ws_bsplit, s->ws_ye + L.ye_off, u,
-                                                                                          L.kmax, L.nmax, nb, nsplit); ++g_fdfd_launches; }
+            if constexpr (NR < 8) {
+                dim3 grid(ecta, nsplit);
+                { backward_mvt_split_kernel<NR><<<grid, 256, 0, st>>>(L.G, u, s->ws_bsplit, L.kmax, L.mmax, L.nmax, nb, rows_per); ++g_fdfd_launches; }
+                { backward_mvt_reduce_kernel<NR><<<ceil_div(nb * L.kmax, 128), 128, 0, st>>>(s->ws_bsplit, s->ws_ye + L.ye_off, u,
+                                                                                              L.kmax, L.nmax, nb, nsplit); ++g_fdfd_launches; }
+            }
         } else {
-            { backward_mvt_kernel<NR><<<ecta, 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
-                                                            L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+            if constexpr (NR < 8) {
+                { backward_mvt_kernel<NR><<<ecta, 256, 0, st>>>(L.G, s->ws_ye + L.ye_off, u, L.kmax,
+                                                                L.mmax, L.nmax, nb); ++g_fdfd_launches; }
+            }
         }
         if (L.kind == 0) {
             long long tot = nb * L.nmax;
@@ -1342,7 +1376,8 @@ int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs
     if (sharded) FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(cplx) * n * nrhs, op->stream));
     for (int j0 = 0; j0 < nrhs;) {
         int rem = nrhs - j0, rc;
-        if (rem >= 8) { rc = 8; if (nd_solve_chunk<8>(s, op, d_b + j0 * n, d_x + j0 * n, 8)) return -1; }
+        if (rem >= 16) { rc = 16; if (nd_solve_chunk<16>(s, op, d_b + j0 * n, d_x + j0 * n, 16)) return -1; }
+        else if (rem >= 8) { rc = 8; if (nd_solve_chunk<8>(s, op, d_b + j0 * n, d_x + j0 * n, 8)) return -1; }
         else if (rem > 2) { rc = rem < 4 ? rem : 4; if (nd_solve_chunk<4>(s, op, d_b + j0 * n, d_x + j0 * n, rc)) return -1; }
         else if (rem == 2) { rc = 2; if (nd_solve_chunk<2>(s, op, d_b + j0 * n, d_x + j0 * n, 2)) return -1; }
         else { rc = 1; if (nd_solve_chunk<1>(s, op, d_b + j0 * n, d_x + j0 * n, 1)) return -1; }

@@ -114,10 +114,10 @@ dist_fwd_step_kernel(const cplx* __restrict__ Einv, const cplx* __restrict__ G, 
 
 // backward: tmp[split][c] = sum over my rows i of this split of G[i][c] u[lslot[r0 + i]]   (lanes along c)
 template <int NR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 dist_bwd_partial_kernel(const cplx* __restrict__ G, const cplx* __restrict__ u, const int* __restrict__ lslot, int r0,
                         int mloc, int k, int rows_per_split, cplx* __restrict__ tmp) {
-    __shared__ cplx part[8][32][NR];
+    __shared__ cplx part[4][32][NR];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     const int i0 = blockIdx.y * rows_per_split, i1 = min(mloc, i0 + rows_per_split);
@@ -125,7 +125,7 @@ dist_bwd_partial_kernel(const cplx* __restrict__ G, const cplx* __restrict__ u, 
 #pragma unroll
     for (int j = 0; j < NR; ++j) acc[j] = make_double2(0.0, 0.0);
     if (c < k) {
-        for (int i = i0 + w; i < i1; i += 8) {
+        for (int i = i0 + w; i < i1; i += 4) {
             const cplx mv = ldg_c(G + (size_t)i * k + c);
             const size_t slot = lslot[r0 + i];
 #pragma unroll
@@ -140,7 +140,7 @@ dist_bwd_partial_kernel(const cplx* __restrict__ G, const cplx* __restrict__ u, 
         for (int j = 0; j < NR; ++j) {
             cplx t = part[0][lane][j];
 #pragma unroll
-            for (int q = 1; q < 8; ++q) t = cadd(t, part[q][lane][j]);
+            for (int q = 1; q < 4; ++q) t = cadd(t, part[q][lane][j]);
             tmp[((size_t)blockIdx.y * k + c) * NR + j] = t;
         }
     }
@@ -178,7 +178,7 @@ __global__ void dist_child_ring_kernel(cplx* __restrict__ uc, const cplx* __rest
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-#define DIST_NR_MAX 8
+#define DIST_NR_MAX 16
 
 static int dist_upload(int** dst, const std::vector<int>& v) { return upload_i32(dst, v.data(), v.size()); }
 
@@ -508,7 +508,7 @@ static int dist_backward(NdSolver* s, NdDistFront* f, const NdDistFront* parent,
             nsplit = ceil_div(mloc, rows_per);
             cplx* tmp = f->gat + (size_t)g * f->kmax_step * NR;
             dim3 grid(ceil_div(k, 32), nsplit);
-            { dist_bwd_partial_kernel<NR><<<grid, 256, 0, st>>>(f->G[sidx], f->vec, f->d_lslot, r0, mloc, k, rows_per, tmp); ++g_fdfd_launches; }
+            { dist_bwd_partial_kernel<NR><<<grid, 128, 0, st>>>(f->G[sidx], f->vec, f->d_lslot, r0, mloc, k, rows_per, tmp); ++g_fdfd_launches; }
             { dist_bwd_reduce_kernel<NR><<<ceil_div(k * NR, 128), 128, 0, st>>>(tmp, mine, k, nsplit); ++g_fdfd_launches; }
             FDFD_CHECK(cudaGetLastError());
         } else {

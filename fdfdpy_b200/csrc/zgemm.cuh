@@ -305,8 +305,23 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         cp_async_commit();
     }
     double cr[2][4][2], ci[2][4][2], t3[2][4][2];       // 3M: cr = T1, ci = T2, t3 = T3
-    cplx cpre[2][4][2];
     int stage = 0;
+    // operand fragments of one k-step (4 k values): a[mt], b[nt] and, for 3M, their re + im sums
+    struct Frag { cplx a[2], b[4]; double as_[2], bs_[4]; };
+    auto load_frag = [&](Frag& f, const cplx* as, const cplx* bs, int kk) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) f.a[mt] = as[(wm * 16 + mt * 8 + gq) * LDA + kk + tq];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            f.b[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+        // the sums (3M) / the negated imaginary part (4M) are formed one k-step AHEAD of the DMMAs that read them
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) f.as_[mt] = M3 ? f.a[mt].x + f.a[mt].y : -f.a[mt].y;
+        if (M3) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) f.bs_[nt] = f.b[nt].x + f.b[nt].y;
+        }
+    };
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, tiles_per_batch, (unsigned)tiles_n, g.lower);
         cplx* __restrict__ C = g.C + (long long)tc.b * g.sC;
@@ -321,68 +336,57 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         __syncthreads();
         const bool last = kt == KT - 1;
         if (last && g.mode == 1) {
+            // the C tile of an update is pulled into L2 / L1 under the last k-tile's DMMAs (no registers held)
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                int row = m_base + wm * 16 + mt * 8 + gq;
+                const int row = m_base + wm * 16 + mt * 8 + gq;
+                if (row < g.M) {
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    int col = n_base + wn * 32 + nt * 8 + 2 * tq;
-                    const cplx* p = C + (size_t)row * g.ldc + col;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        cpre[mt][nt][e] = (row < g.M && col + e < g.N) ? p[e] : make_double2(0.0, 0.0);
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int col = n_base + wn * 32 + nt * 8 + 2 * tq;
+                        if (col < g.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(C + (size_t)row * g.ldc + col));
+                    }
                 }
             }
         }
         const cplx* as = As + stage * A_ELEMS;
         const cplx* bs = Bs + stage * B_ELEMS;
         stage = stage + 1 == STAGES ? 0 : stage + 1;
+        Frag f[2];
+        load_frag(f[0], as, bs, 0);
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            cplx a[2], bq[4];
-            double nai[2];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                a[mt] = as[(wm * 16 + mt * 8 + gq) * LDA + kk + tq];
-                nai[mt] = -a[mt].y;
-            }
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-                bq[nt] = TB ? bs[(wn * 32 + nt * 8 + gq) * LDB + kk + tq] : bs[(kk + tq) * LDB + wn * 32 + nt * 8 + gq];
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            if (ks + 1 < BK / 4) load_frag(f[(ks + 1) & 1], as, bs, 4 * (ks + 1));
+            const Frag& c = f[ks & 1];
             if (M3) {
-                double as_[2], bs_[4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) as_[mt] = a[mt].x + a[mt].y;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) bs_[nt] = bq[nt].x + bq[nt].y;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
-                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].y);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], c.a[mt].x, c.b[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], c.a[mt].y, c.b[nt].y);
                     }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], as_[mt], bs_[nt]);
+                    for (int nt = 0; nt < 4; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], c.as_[mt], c.bs_[nt]);
             } else {
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, bq[nt].x);
-                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].x, bq[nt].y);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], c.a[mt].x, c.b[nt].x);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], c.a[mt].x, c.b[nt].y);
                     }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        dmma884(cr[mt][nt][0], cr[mt][nt][1], nai[mt], bq[nt].y);
-                        dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, bq[nt].x);
+                        dmma884(cr[mt][nt][0], cr[mt][nt][1], c.as_[mt], c.b[nt].y);
+                        dmma884(ci[mt][nt][0], ci[mt][nt][1], c.a[mt].y, c.b[nt].x);
                     }
             }
-            if (kk == 0) {
+            if (ks == 0) {
                 // refill the stage consumed in the previous iteration; issued here, under the first
                 // k-step's DMMAs, so the tensor pipe is not idle while the copies are set up
                 issue_load();
@@ -404,8 +408,10 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
                             cplx v = M3 ? make_double2(cr[mt][nt][e] - ci[mt][nt][e],
                                                        t3[mt][nt][e] - cr[mt][nt][e] - ci[mt][nt][e])
                                         : make_double2(cr[mt][nt][e], ci[mt][nt][e]);
-                            if (g.mode == 1) v = make_double2(cpre[mt][nt][e].x - v.x, cpre[mt][nt][e].y - v.y);
-                            else if (g.mode == 2) v = make_double2(-v.x, -v.y);
+                            if (g.mode == 1) {
+                                const cplx o = p[e];
+                                v = make_double2(o.x - v.x, o.y - v.y);
+                            } else if (g.mode == 2) v = make_double2(-v.x, -v.y);
                             p[e] = v;
                         }
                     }

@@ -198,6 +198,32 @@ def test_direct_multi_rhs_reuses_factorisation(core):
     assert not d.solve(np.zeros((nx, ny))).any()
 
 
+def test_direct_many_rhs_tensor_substitution(core):
+    """>= 8 right-hand sides per pass take the tensor-pipe substitution (mrhs.cuh: skinny GEMMs, factor blocks streamed
+    once for 8 / 16 columns, K-split partial sums at the top of the tree): 37 = 16 + 16 + 4 + 1 columns, checked
+    against the single-column path and the oracle; the second grid is large enough for separators cut into 512-node
+    pieces and for the K-split."""
+    rng = np.random.default_rng(14)
+    for (nx, ny), pol, nrhs, ncheck in [((150, 131), "Hz", 37, 37), ((640, 600), "Ez", 24, 3)]:
+        eps = 1 + 5 * (rng.random((nx, ny)) > 0.6)
+        npml = [10, 12]
+        op = core.MaxwellOperator(OMEGA, eps, 0.03, npml, pol, 1e-6)
+        d = op.direct()
+        B = rng.standard_normal((nrhs, nx, ny)) + 1j * rng.standard_normal((nrhs, nx, ny))
+        X = d.solve(B, max_refine=0).reshape(nrhs, nx, ny)          # raw substitution: no refinement to hide behind
+        for j in (0, nrhs - 1):
+            xj = d.solve(B[j], max_refine=0).reshape(nx, ny)        # the matrix-vector path
+            assert relerr(X[j], xj) < 1e-10, (nx, j)
+        X = d.solve(B).reshape(nrhs, nx, ny)
+        assert d.last_relres < 1e-10
+        A = orc.construct_A(OMEGA, eps, 0.03, npml, pol, 1e-6)
+        import scipy.sparse.linalg as spl
+        lu = spl.splu(A.tocsc())
+        for j in list(range(ncheck)) if ncheck == nrhs else [0, nrhs // 2, nrhs - 1]:
+            ref = lu.solve(B[j].ravel()).reshape(nx, ny)
+            assert relerr(X[j], ref) < 1e-8, (nx, j)
+
+
 def test_config0_dipole_golden(core, golden):
     g = golden("config0_dipole")
     omega, dl, L0, npx, npy = g["meta"]

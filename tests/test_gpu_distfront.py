@@ -99,15 +99,15 @@ def test_owner_per_front_scheme_still_works():
 
 
 def test_distributed_fronts_multi_rhs_chunks():
-    """11 right-hand sides = chunks of 8 + 2 + 1 through the distributed substitution."""
+    """27 right-hand sides = chunks of 16 + 8 + 2 + 1 through the distributed substitution."""
     rng = np.random.default_rng(3)
     nx, ny = 112, 104
     eps = 1 + 5 * rng.random((nx, ny))
-    b = rng.standard_normal((11, nx, ny)) + 1j * rng.standard_normal((11, nx, ny))
+    b = rng.standard_normal((27, nx, ny)) + 1j * rng.standard_normal((27, nx, ny))
     with env(FDFD_SPLIT_MIN=40, FDFD_SPLIT_PARTS=-20, FDFD_DIST_RB=28):
         res = _sharded_solve(4, eps, [8, 8], "Hz", b)
     A = orc.construct_A(OMEGA, eps, 0.04, [8, 8], "Hz", 1e-6)
-    for j in range(11):
+    for j in (0, 7, 15, 16, 23, 24, 25, 26):
         ref = orc.sparse_solve(A, b[j]).reshape(nx, ny)
         assert relerr(res[0][0][j], ref) < 1e-8, j
         assert relerr(res[3][0][j], ref) < 1e-8, j
