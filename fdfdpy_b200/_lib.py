@@ -98,6 +98,7 @@ SIGNATURES = {
                                          _vp, C.c_int, _ip, _dp, _ip]),
     "fdfd_krylov_solve_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                         _vp, C.c_int, _ip, _dp, _ip]),
+    "fdfd_nl_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _ip, _ip]),
     "fdfd_op_apply_host_c64": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "fdfd_op_apply_dev_c64": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "fdfd_krylov_solve_host_c64": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _ip, _dp,

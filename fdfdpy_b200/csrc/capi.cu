@@ -489,6 +489,24 @@ int fdfd_krylov_solve_host(fdfd_op* op, fdfd_direct* precond, const double* b, d
     return 0;
 }
 
+int fdfd_nl_solve_host(fdfd_op* op_nl, fdfd_direct* lin, fdfd_direct* work, const double* K, const double* b, double* E,
+                       int method, int strategy, double conv_threshold, int max_iter, double* conv, int* iters,
+                       int* inner_iters) {
+    if (method != 0 && method != 1) FDFD_FAIL("nonlinear method: 0 = born, 1 = newton");
+    if (max_iter < 1) FDFD_FAIL("max_iter must be >= 1");
+    const size_t n = op_nl->n();
+    DevBuf dk, db, de;
+    if (dk.alloc(n) || db.alloc(n) || de.alloc(n)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(dk.p, K, sizeof(cplx) * n, cudaMemcpyHostToDevice, op_nl->stream));
+    FDFD_CHECK(cudaMemcpyAsync(db.p, b, sizeof(cplx) * n, cudaMemcpyHostToDevice, op_nl->stream));
+    FDFD_CHECK(cudaMemcpyAsync(de.p, E, sizeof(cplx) * n, cudaMemcpyHostToDevice, op_nl->stream));
+    if (nl_solve(op_nl, lin, work, dk.p, db.p, de.p, method, strategy, conv_threshold, max_iter, conv, iters, inner_iters))
+        return -1;
+    FDFD_CHECK(cudaMemcpyAsync(E, de.p, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op_nl->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op_nl->stream));
+    return 0;
+}
+
 /* ---- complex64 storage (fp64 arithmetic): stencil and Krylov loop ---- */
 int fdfd_op_apply_dev_c64(fdfd_op* op, const void* d_x, void* d_y, int fused) {
     return fused ? op_apply_fused_t<cplx32>(op, (const cplx32*)d_x, (cplx32*)d_y, 1)

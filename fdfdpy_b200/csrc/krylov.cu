@@ -537,3 +537,113 @@ int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int
     *steps_out = step + (fallback_iters ? 1000 + fallback_iters : 0);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Device-resident Born / Newton iterations for the Kerr problem (nonlinear_solvers.py:13-110, simulation.py:57-68).
+// Every Kerr term of the reference is  eps_nl = 3 chi region |E|^2 w(eps_r): a sum of them is K(x) |E|^2 with one
+// complex coefficient plane K, and  d eps_nl / dE = K conj(E).  The permittivity update, the Newton right-hand side
+// f(E) = (A + Anl(E)) E - b, the Jacobian's anti-linear diagonal and the convergence norm are kernels; the host sees
+// one scalar per iteration (plus the residual norms the inner Krylov solve checks).
+// ------------------------------------------------------------------------------------------
+// eps_out = scale * K |E|^2 ; c12 (optional) = kfac * conj(K conj(E)) * E = kfac * conj(K) * E * E
+__global__ void kerr_terms_kernel(const cplx* __restrict__ K, const cplx* __restrict__ E, cplx* __restrict__ eps_out,
+                                  double scale, cplx* __restrict__ c12, double kfac, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cplx k = K[i], e = E[i];
+    const double e2 = e.x * e.x + e.y * e.y;
+    eps_out[i] = make_double2(scale * k.x * e2, scale * k.y * e2);
+    if (c12) c12[i] = cscale(cmul(cconj(k), cmul(e, e)), kfac);
+}
+// x = a - b (out may alias a); partial sums of |x|^2-type norms are taken by dots() afterwards
+__global__ void sub_kernel(cplx* __restrict__ out, const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = csub(a[i], b[i]);
+}
+__global__ void neg_kernel(cplx* __restrict__ v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = cneg(v[i]);
+}
+
+// one solve with the work operator (planes = A + diagonal perturbation), optionally with the anti-linear term c12:
+// strategy 0 ("reuse"): BiCGSTAB preconditioned by the LINEAR operator's cached factors, falling back to an exact
+// factorisation of the work operator when that stalls; strategy 1 ("refactor"): always the exact factorisation.
+static int nl_inner_solve(FdfdOp* op_nl, NdSolver* lin, NdSolver* work, const cplx* b, cplx* x, const cplx* c12,
+                          int strategy, int* inner_iters) {
+    KrylovResult kr;
+    kr.iters = 0; kr.relres = 1.0; kr.converged = 0;
+    if (strategy == 0) {
+        if (krylov_bicgstab(op_nl, lin, b, x, 1e-13, 40, 0, 1, c12, 0, &kr)) return -1;
+        *inner_iters += kr.iters;
+        if (kr.relres <= 1e-11) return 0;
+    }
+    if (nd_factor(work, op_nl)) return -1;
+    if (!c12) {
+        double rr;
+        int steps;
+        return refine_solve(work, op_nl, b, x, 1, 3, 1e-12, &rr, &steps);
+    }
+    if (krylov_bicgstab(op_nl, work, b, x, 1e-13, 200, 0, 1, c12, 0, &kr)) return -1;
+    *inner_iters += kr.iters;
+    if (kr.relres > 1e-9) FDFD_FAIL("Newton Jacobian solve did not converge (relres %.2e after %d iterations)", kr.relres, kr.iters);
+    return 0;
+}
+
+int nl_solve(FdfdOp* op_nl, NdSolver* lin, NdSolver* work, const cplx* d_K, const cplx* d_b, cplx* d_E, int method,
+             int strategy, double thr, int max_iter, double* conv, int* iters_out, int* inner_iters_out) {
+    const size_t n = op_nl->n();
+    cudaStream_t st = op_nl->stream;
+    if (op_nl->pol != 0) FDFD_FAIL("the nonlinear solvers are defined for Ez (nonlinear_solvers.py:18)");
+    if (strategy == 0 && (!lin || !lin->factored)) FDFD_FAIL("nonlinear solve ('reuse'): the linear operator is not factorised");
+    Scratch ws;
+    FDFD_CHECK(cudaMalloc(&ws.base, sizeof(cplx) * (4 * n + 2 * RED_BLOCKS + S_COUNT)));
+    cplx *x = static_cast<cplx*>(ws.base), *f = x + n, *c12 = f + n, *dl = c12 + n, *partial = dl + n, *sc = partial + 2 * RED_BLOCKS;
+    const double kfac = op_nl->omega * op_nl->omega * FDFD_EPS0 * op_nl->L0;
+    const int nblk = ceil_div(n, 256);
+    cplx h;
+    int it = 0, inner = 0;
+    for (int i = 0; i < max_iter; ++i) conv[i] = 0.0;
+    for (it = 0; it < max_iter; ++it) {
+        double cv;
+        if (method == 0) {
+            // Born: E <- (A + Anl(E))^-1 b
+            { kerr_terms_kernel<<<nblk, 256, 0, st>>>(d_K, d_E, op_nl->eps_nl, 1.0, nullptr, 0.0, n); ++g_fdfd_launches; }
+            if (op_assemble_dev(op_nl, op_nl->eps_r, op_nl->eps_nl, op_nl->averaging)) return -1;
+            FDFD_CHECK(cudaMemcpyAsync(x, d_E, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));   // initial guess
+            if (nl_inner_solve(op_nl, lin, work, d_b, x, nullptr, strategy, &inner)) return -1;
+            { sub_kernel<<<nblk, 256, 0, st>>>(dl, x, d_E, n); ++g_fdfd_launches; }
+            if (dots<cplx>(st, dl, dl, 1, x, x, 1, n, partial, sc, POST_STORE, S_RR, S_TT, 1, nullptr)) return -1;
+            FDFD_CHECK(cudaMemcpyAsync(d_E, x, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
+        } else {
+            // Newton: f = (A + Anl(E)) E - b ;  J11 = A + diag(k (eps_nl + dnl_de E)) = A(eps_nl -> 2 K |E|^2),
+            // J12 = diag(k conj(K) E^2) acting on conj(dE);  E <- E - dE
+            { kerr_terms_kernel<<<nblk, 256, 0, st>>>(d_K, d_E, op_nl->eps_nl, 1.0, c12, kfac, n); ++g_fdfd_launches; }
+            if (op_assemble_dev(op_nl, op_nl->eps_r, op_nl->eps_nl, op_nl->averaging)) return -1;
+            if (op_residual(op_nl, d_b, d_E, f, 1)) return -1;                  // b - (A + Anl) E
+            { neg_kernel<<<nblk, 256, 0, st>>>(f, n); ++g_fdfd_launches; }
+            if (dots<cplx>(st, f, f, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 1, nullptr)) return -1;
+            if (host_scalar(st, sc + S_RR, &h)) return -1;
+            if (h.x > 0.0) {
+                { kerr_terms_kernel<<<nblk, 256, 0, st>>>(d_K, d_E, op_nl->eps_nl, 2.0, nullptr, 0.0, n); ++g_fdfd_launches; }
+                if (op_assemble_dev(op_nl, op_nl->eps_r, op_nl->eps_nl, op_nl->averaging)) return -1;
+                FDFD_CHECK(cudaMemsetAsync(dl, 0, sizeof(cplx) * n, st));
+                if (nl_inner_solve(op_nl, lin, work, f, dl, c12, strategy, &inner)) return -1;
+            } else {
+                FDFD_CHECK(cudaMemsetAsync(dl, 0, sizeof(cplx) * n, st));
+            }
+            { sub_kernel<<<nblk, 256, 0, st>>>(d_E, d_E, dl, n); ++g_fdfd_launches; }
+            if (dots<cplx>(st, dl, dl, 1, d_E, d_E, 1, n, partial, sc, POST_STORE, S_RR, S_TT, 1, nullptr)) return -1;
+        }
+        FDFD_CHECK(cudaGetLastError());
+        cplx nrm[2];
+        FDFD_CHECK(cudaMemcpyAsync(&nrm[0], sc + S_RR, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        FDFD_CHECK(cudaMemcpyAsync(&nrm[1], sc + S_TT, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        FDFD_CHECK(cudaStreamSynchronize(st));
+        cv = sqrt(nrm[0].x) / sqrt(nrm[1].x);
+        conv[it] = cv;
+        if (cv < thr) { ++it; break; }
+    }
+    *iters_out = it;
+    *inner_iters_out = inner;
+    return 0;
+}

@@ -22,3 +22,6 @@ int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int ma
                 KrylovResult* res);
 int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs, int max_refine, double tol,
                  double* relres_out, int* steps_out);
+// device-resident Born (method 0) / Newton (method 1) iteration of the Kerr problem; see krylov.cu
+int nl_solve(FdfdOp* op_nl, NdSolver* lin, NdSolver* work, const cplx* d_K, const cplx* d_b, cplx* d_E, int method,
+             int strategy, double thr, int max_iter, double* conv, int* iters_out, int* inner_iters_out);

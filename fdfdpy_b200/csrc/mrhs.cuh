@@ -25,10 +25,10 @@ struct MrhsArgs {
     long long batch;
 };
 
-template <int NR, bool TRANS>
-__global__ void __launch_bounds__(256)
+template <int NR, bool TRANS, int BM, int STAGES>
+__global__ void __launch_bounds__(BM * 2)
 mrhs_dmma_kernel(MrhsArgs a) {
-    constexpr int BM = 128, BK = 16, STAGES = 3, NT = NR / 8;
+    constexpr int BK = 16, NT = NR / 8, NTHR = BM * 2;          // one warp per 16 rows
     constexpr int LDA = TRANS ? BM + 2 : BK + 4;                 // conflict-free fragment reads (see zgemm.cuh)
     constexpr int A_ELEMS = TRANS ? BK * LDA : BM * LDA;
     constexpr int LDV = NR + 2, V_ELEMS = BK * LDV;
@@ -51,7 +51,7 @@ mrhs_dmma_kernel(MrhsArgs a) {
         if (!TRANS) {
             // A tile: 128 rows x 16 k, k contiguous in memory
 #pragma unroll
-            for (int i = tid; i < BM * BK; i += 256) {
+            for (int i = tid; i < BM * BK; i += NTHR) {
                 const int r = i >> 4, c = i & 15;
                 const int gm = m_base + r, gk = k0 + c;
                 const bool ok = gm < a.M && gk < k_hi;
@@ -60,14 +60,14 @@ mrhs_dmma_kernel(MrhsArgs a) {
         } else {
             // A^T tile: 16 rows of the stored matrix (the K index) x 128 columns (the M index), M contiguous
 #pragma unroll
-            for (int i = tid; i < BM * BK; i += 256) {
-                const int r = i >> 7, c = i & 127;
+            for (int i = tid; i < BM * BK; i += NTHR) {
+                const int r = i / BM, c = i % BM;
                 const int gk = k0 + r, gm = m_base + c;
                 const bool ok = gm < a.M && gk < k_hi;
                 cp_async16(as + r * LDA + c, ok ? A + (size_t)gk * a.lda + gm : A, ok);
             }
         }
-        for (int i = tid; i < BK * NR; i += 256) {
+        for (int i = tid; i < BK * NR; i += NTHR) {
             const int r = i / NR, c = i % NR;
             const bool ok = k0 + r < k_hi;
             cp_async16(vs + r * LDV + c, ok ? V + (size_t)(k0 + r) * NR + c : V, ok);
@@ -160,16 +160,33 @@ __global__ void mrhs_reduce_kernel(MrhsArgs a) {
     a.C[b * a.sC + o] = t;
 }
 
-template <int NR, bool TRANS>
+template <int NR, bool TRANS, int BM, int STAGES>
 constexpr size_t mrhs_smem_bytes() {
-    return sizeof(cplx) * 3 * ((TRANS ? 16 * (128 + 2) : 128 * (16 + 4)) + 16 * (NR + 2));
+    return sizeof(cplx) * STAGES * ((TRANS ? 16 * (BM + 2) : BM * (16 + 4)) + 16 * (NR + 2));
+}
+
+template <int NR, bool TRANS, int BM, int STAGES>
+static int mrhs_launch_cfg(const MrhsArgs& a, cudaStream_t st) {
+    constexpr size_t sm = mrhs_smem_bytes<NR, TRANS, BM, STAGES>();
+    static bool attr = false;
+    if (!attr) {
+        FDFD_CHECK(cudaFuncSetAttribute(mrhs_dmma_kernel<NR, TRANS, BM, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr = true;
+    }
+    dim3 grid((a.M + BM - 1) / BM, (unsigned)a.batch, a.kslices);
+    mrhs_dmma_kernel<NR, TRANS, BM, STAGES><<<grid, BM * 2, sm, st>>>(a);
+    ++g_fdfd_launches;
+    return 0;
 }
 
 // scratch: device buffer for the K-slice partial sums, grown on demand (owned by the caller)
 template <int NR, bool TRANS>
 static int mrhs_launch(MrhsArgs a, cplx** scratch, size_t* scratch_cap, cudaStream_t st) {
     if (a.M <= 0 || a.batch <= 0) return 0;
-    const int mtiles = (a.M + 127) / 128;
+    // short reductions (the many mid-size fronts: K of a few k-steps) take 64-row tiles and a 2-stage ring, four CTAs
+    // per SM, instead of one 128-row CTA whose pipeline never fills
+    const bool small = a.K <= 128;
+    const int mtiles = (a.M + (small ? 63 : 127)) / (small ? 64 : 128);
     // enough CTAs for the machine: split K when the level has few fronts and a long reduction
     long long ctas = (long long)mtiles * a.batch;
     int ks = 1;
@@ -188,16 +205,8 @@ static int mrhs_launch(MrhsArgs a, cplx** scratch, size_t* scratch_cap, cudaStre
         }
         a.part = *scratch;
     }
-    constexpr size_t sm = mrhs_smem_bytes<NR, TRANS>();
-    static bool attr = false;
-    if (!attr) {
-        FDFD_CHECK(cudaFuncSetAttribute(mrhs_dmma_kernel<NR, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        attr = true;
-    }
     if (a.batch > 65535) FDFD_FAIL("mrhs: batch too large for one launch");
-    dim3 grid(mtiles, (unsigned)a.batch, a.kslices);
-    mrhs_dmma_kernel<NR, TRANS><<<grid, 256, sm, st>>>(a);
-    ++g_fdfd_launches;
+    if (small ? mrhs_launch_cfg<NR, TRANS, 64, 2>(a, st) : mrhs_launch_cfg<NR, TRANS, 128, 3>(a, st)) return -1;
     if (a.kslices > 1) {
         mrhs_reduce_kernel<NR><<<ceil_div(a.batch * a.M * NR, 256), 256, 0, st>>>(a);
         ++g_fdfd_launches;

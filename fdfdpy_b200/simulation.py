@@ -49,6 +49,7 @@ class Simulation:
         self._op = None        # linear operator A(eps_r) and its cached factorisation
         self._derivs = None
         self._op_nl = None     # work operator for A + Anl and the Newton Jacobian
+        self.nl_device = True        # Born / Newton loops run inside the library (False: host-driven loops)
         self.nl_strategy = 'reuse'   # 'reuse': linear factors precondition the nonlinear solves;
         #                              'refactor': factorise A + Anl every time, as the reference does
         self.eps_r = eps_r     # builds the system operator (simulation.py:38)

@@ -191,6 +191,21 @@ int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, vo
                           double tol, int maxiter, int fused, int check_every, const void* d_c12,
                           int real_inner, int* iters, double* relres, int* converged);
 
+/* ---- Born / Newton iteration of the Kerr problem on the device: replaces the loops of nonlinear_solvers.py:13-110
+ * (born_solve, newton_solve, nl_eq_and_jac) together with Simulation.compute_nl (simulation.py:57-68).  Every Kerr
+ * term of the reference is 3 chi region |E|^2 w(eps_r), so their sum is K |E|^2 with one complex plane K (host,
+ * nx*ny).  op_nl: a work operator of the same grid holding the LINEAR eps_r (its eps_nl / planes are overwritten);
+ * lin: the direct solver holding the factors of the linear operator (strategy 0, "reuse": they precondition
+ * BiCGSTAB on every perturbed / Jacobian system; an exact factorisation through `work` is the fallback);
+ * strategy 1 ("refactor"): `work` factorises the perturbed operator every iteration, as the reference does.
+ * method 0 = Born, 1 = Newton (R-linear Jacobian solved in the real inner product instead of the reference's real
+ * 2N x 2N LU, linalg.py:152-186).  E: start field in, converged field out.  conv[max_iter] receives
+ * ||E_new - E_old|| / ||E_new|| per iteration (zero after the last one), *iters the number of iterations done,
+ * *inner_iters the Krylov iterations spent.  Only that one scalar per iteration crosses to the host. */
+int fdfd_nl_solve_host(fdfd_op* op_nl, fdfd_direct* lin, fdfd_direct* work, const double* K_c128, const double* b_c128,
+                       double* E_c128, int method, int strategy, double conv_threshold, int max_iter, double* conv,
+                       int* iters, int* inner_iters);
+
 /* complex64 storage for the matrix-free path (interleaved float re, im = numpy complex64): vectors and eps_r
  * stream as 8-byte values (24 B/cell for the fused Ez stencil), arithmetic, inner products and iteration
  * scalars stay fp64.  Parity bar: relative L2 error <= 1e-4 against the fp64 reference.           */

@@ -158,6 +158,28 @@ def test_born_newton_golden(Simulation, golden, strategy):
     assert_allclose(sim.eps_nl, g["eps_nl_final"], rtol=1e-6, atol=1e-12 * np.abs(g["eps_nl_final"]).max())
 
 
+def test_device_and_host_nonlinear_loops_agree(Simulation, golden):
+    """The device-resident Born / Newton iteration (fdfd_nl_solve_host, the default) against the host-driven loops
+    of nonlinear_solvers.py (one library solve per iteration): same fields, same convergence history."""
+    g = golden("nonlinear")
+    out = {}
+    for device in (True, False):
+        sim = _kerr_sim(Simulation, g)
+        sim.nl_device = device
+        sim.solve_fields()
+        for method in ("born", "newton"):
+            hx, hy, ez, conv = sim.solve_fields_nl(solver_nl=method)
+            out[(device, method)] = (np.array(hx), np.array(hy), np.array(ez), np.array(conv))
+    for method in ("born", "newton"):
+        dev, host = out[(True, method)], out[(False, method)]
+        for a, b in zip(dev[:3], host[:3]):
+            assert relerr(a, b) < 1e-9, method
+        assert np.count_nonzero(dev[3]) == np.count_nonzero(host[3]), method
+        nz = np.count_nonzero(host[3])
+        assert_allclose(dev[3][:nz - 1], host[3][:nz - 1], rtol=1e-3)
+        assert relerr(dev[2], g[method + "_ez"]) < 1e-8
+
+
 def test_born_equals_newton(Simulation):
     """tests/test_nonlinear_solvers.py of the reference on a 2.5x coarser grid."""
     n0, omega, dl, chi3 = 3.4, 2 * np.pi * 200e12, 0.025, 2.8e-18
