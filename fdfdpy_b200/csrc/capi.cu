@@ -18,6 +18,7 @@ struct DevBuf {
 
 ZgemmTiming g_zgemm_timing;
 int g_zgemm_variant = 0;
+int g_zgemm_max_ctas = 148;
 
 // register-resident DMMA loop: the practical FP64 tensor-pipe ceiling at the clocks the board runs at
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {

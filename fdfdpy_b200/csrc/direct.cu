@@ -774,6 +774,13 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     s->xchg_cap = 0;
     s->dist_send = s->dist_recv = s->dist_panel = nullptr;
     s->dist_send_cap = s->dist_recv_cap = s->dist_panel_cap = 0;
+    {
+        int lo = 0, hi = 0;
+        FDFD_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FDFD_CHECK(cudaStreamCreateWithPriority(&s->la_stream, cudaStreamNonBlocking, hi));
+        FDFD_CHECK(cudaEventCreateWithFlags(&s->la_ready, cudaEventDisableTiming));
+        FDFD_CHECK(cudaEventCreateWithFlags(&s->la_done, cudaEventDisableTiming));
+    }
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
     *out = s;
     return 0;
@@ -862,9 +869,13 @@ void nd_destroy(NdSolver* s) {
     if (s->xchg) cudaFree(s->xchg);
     if (s->ws_refine) cudaFree(s->ws_refine);
     if (s->ws_bsplit) cudaFree(s->ws_bsplit);
+    cudaStreamDestroy(s->la_stream);
+    cudaEventDestroy(s->la_ready);
+    cudaEventDestroy(s->la_done);
     delete s;
 }
 
+int g_lookahead_enabled = 1;       // A/B switch (FDFD_LOOKAHEAD=0): pivot-block look-ahead on chain levels
 int g_small_front_enabled = 1;     // A/B switch (fdfd_direct_set_small_fronts): 0 = generic path on every level
 
 static int chunks_for(long long per_front_elems, long long nb) {
@@ -1011,10 +1022,15 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     cudaStream_t st = op->stream;
     s->factored = false;
     if (ensure_factor_workspace(s)) return -1;
+    {
+        const char* e = getenv("FDFD_LOOKAHEAD");
+        g_lookahead_enabled = !(e && e[0] == '0');
+    }
     FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
     // the previous level's Schur blocks: batch base, first ring entry at (prev_k, prev_k), leading dimension
     // prev_n, batch stride prev_stride, ring size prev_m
     cplx* Fprev = nullptr;
+    bool lookahead_done = false;
     int prev_k = 0, prev_n = 0, prev_m = 0, cur = 1;
     long long prev_stride = 0;
     s->factor_bytes = 0;
@@ -1128,7 +1144,11 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         }
         FDFD_CHECK(cudaGetLastError());
         // ---- Einv = F_EE^-1
-        if (kmax <= 64) {
+        if (lookahead_done) {
+            // inverted on the side stream while the previous level's Schur update ran
+            FDFD_CHECK(cudaStreamWaitEvent(st, s->la_done, 0));
+            lookahead_done = false;
+        } else if (kmax <= 64) {
             PhaseScope ph(PH_PIVOT, st);
             launch_tile_inverse(F, fstride, ld, kmax, L.Einv, (long long)kmax * kmax, kmax, s->d_info, 1, nb, st);
         } else {
@@ -1159,7 +1179,53 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             g.B = F + (size_t)kmax * ld; g.sB = fstride; g.ldb = ld;
             g.C = F + (size_t)kmax * ld + kmax; g.sC = fstride; g.ldc = ld;
             g.M = mmax; g.N = mmax; g.K = kmax;
-            {
+            // LOOK-AHEAD: when the next level continues this front in place (a chain step), its pivot block is the
+            // leading k1 x k1 corner of this Schur block.  That corner is updated first, then inverted on a
+            // high-priority side stream (the latency-bound recursive block inversion, ~1.5-3 ms) while the rest of
+            // the update -- the bulk of the level -- runs on all but a few SMs of the main stream.
+            NdLevel* Nx = li + 1 < s->levels.size() ? &s->levels[li + 1] : nullptr;
+            const bool la = g_lookahead_enabled && Nx && Nx->inplace && Nx->nb == nb && Nx->kmax > 64 && Nx->kmax < mmax &&
+                            nb <= 16 && !dist_at_level(s, (int)li + 1, nullptr);
+            if (la) {
+                const int k1 = Nx->kmax;
+                if (!Nx->Einv) FDFD_CHECK(cudaMalloc(&Nx->Einv, sizeof(cplx) * (size_t)nb * k1 * k1));
+                GemmBatch c = g;
+                {   // corner: rows and columns [0, k1)
+                    PhaseScope ph(PH_SCHUR, st);
+                    c.M = k1; c.N = k1;
+                    if (zgemm_batched(c, st)) return -1;
+                }
+                FDFD_CHECK(cudaEventRecord(s->la_ready, st));
+                FDFD_CHECK(cudaStreamWaitEvent(s->la_stream, s->la_ready, 0));
+                {
+                    cplx* Fn = F + (size_t)kmax * ld + kmax;           // the next level's front (a view)
+                    int chunks = chunks_for((long long)k1 * k1, nb);
+                    sym_expand_kernel<<<(unsigned)(nb * chunks), 256, 0, s->la_stream>>>(Fn, Nx->Einv, k1, ld, fstride, chunks);
+                    ++g_fdfd_launches;
+                    const bool timing = g_phase_timing.on;
+                    g_phase_timing.on = false;                          // phase events belong to the main stream
+                    int rc = sym_invert_batch(s, Nx->Einv, (long long)k1 * k1, k1, k1, nb, s->fws_W, s->la_stream);
+                    g_phase_timing.on = timing;
+                    if (rc) return -1;
+                }
+                FDFD_CHECK(cudaEventRecord(s->la_done, s->la_stream));
+                lookahead_done = true;
+                const int reserve = nb <= 4 ? 8 : 16;
+                g_zgemm_max_ctas = 148 - reserve;
+                PhaseScope ph(PH_SCHUR, st);
+                // rows [k1, m): the rectangle left of the corner's columns, then the lower square
+                c = g;
+                c.lower = 0;
+                c.A = g.A + (size_t)k1 * kmax; c.C = g.C + (size_t)k1 * ld;
+                c.M = mmax - k1; c.N = k1;
+                int rc = zgemm_batched(c, st);
+                c.lower = 1;
+                c.B = g.B + (size_t)k1 * ld; c.C = g.C + (size_t)k1 * ld + k1;
+                c.M = mmax - k1; c.N = mmax - k1;
+                if (!rc) rc = zgemm_batched(c, st);
+                g_zgemm_max_ctas = 148;
+                if (rc) return -1;
+            } else {
                 PhaseScope ph(PH_SCHUR, st);
                 if (zgemm_batched(g, st)) return -1;
             }

@@ -86,6 +86,9 @@ struct NdSolver {
     FdfdComm* comm;
     cplx* xchg;
     size_t xchg_cap;
+    // look-ahead on chain levels: the next pivot block is inverted on a side stream under the current Schur update
+    cudaStream_t la_stream;
+    cudaEvent_t la_ready, la_done;
     // distributed fronts of the shared levels, in elimination order (front j + 1 is the parent of front j)
     std::vector<NdDistFront*> dist;
     cplx *dist_send, *dist_recv, *dist_panel;

@@ -437,6 +437,7 @@ struct ZgemmTiming {
     std::vector<int> big;             // 1: 64x64-tile kernel, 0: 32x32-tile kernel
 };
 extern ZgemmTiming g_zgemm_timing;
+extern int g_zgemm_max_ctas;  // CTAs of the persistent kernel (148 = one per SM; fewer leaves SMs to a side stream)
 extern int g_zgemm_variant;   // bit 0: always the tiled kernel (default: persistent kernel for large problems);
                               // bit 1: textbook 4M complex products (default: 3M)
 
@@ -466,7 +467,7 @@ static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
                                  (int)sm);
             attr_p = true;
         }
-        zgemm_dmma_persistent_kernel<ST, TB, M3><<<148, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+        zgemm_dmma_persistent_kernel<ST, TB, M3><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
     } else {
         constexpr size_t sm = zgemm_smem_bytes<4, 2, 3, TB>();
         static bool attr_set = false;
