@@ -80,7 +80,140 @@ __global__ void __launch_bounds__(1024) dmma_probe_clocked_kernel(double* out, u
     }
     if (s == 123.456) out[0] = s;
 }
+/* DMMA issue-ORDER probe: the 3M inner loop of the GEMM (2 x 4 accumulator tiles x 3 terms = 24 accumulators, operands
+ * in registers, two k-steps) with the same 48 DMMAs issued in different orders.
+ *   0: the k-step order of the GEMM (k-step outer; T1/T2 of every tile, then T3 of every tile)
+ *   1: accumulator-major (every accumulator takes its two k-steps back to back)
+ *   2: term-major inside a k-step (all T1, all T2, all T3)
+ *   3: tile-major inside a k-step (T1, T2, T3 of a tile back to back) */
+template <int PATTERN>
+__global__ void __launch_bounds__(256) dmma_pattern_kernel(double* out, unsigned long long* clk, int iters) {
+    double t[3][2][4][2];
+    double a[2][2][3], b[2][4][3];       // [k-step][tile][re, im, re + im]
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t[q][i][j][0] = threadIdx.x * 1e-9 * (q + 1); t[q][i][j][1] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) a[k][i][q] = 1.0 + 1e-12 * (threadIdx.x + 7 * k + 3 * i + q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) b[k][j][q] = 1.0 - 1e-12 * (threadIdx.x + 5 * k + 11 * j + q);
+    }
+    unsigned long long t0 = 0, c0 = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        c0 = clock64();
+    }
+    for (int it = 0; it < iters; ++it) {
+        if (PATTERN == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dmma884(t[0][i][j][0], t[0][i][j][1], a[k][i][0], b[k][j][0]);
+                        dmma884(t[1][i][j][0], t[1][i][j][1], a[k][i][1], b[k][j][1]);
+                    }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(t[2][i][j][0], t[2][i][j][1], a[k][i][2], b[k][j][2]);
+            }
+        } else if (PATTERN == 1) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) dmma884(t[q][i][j][0], t[q][i][j][1], a[k][i][q], b[k][j][q]);
+        } else if (PATTERN == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(t[q][i][j][0], t[q][i][j][1], a[k][i][q], b[k][j][q]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) dmma884(t[q][i][j][0], t[q][i][j][1], a[k][i][q], b[k][j][q]);
+        }
+        // keep the operands live and changing (one cheap op per iteration, as the fragment loads of the GEMM do)
+        a[0][0][0] += 1e-13;
+    }
+    double sacc = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sacc += t[q][i][j][0] + t[q][i][j][1];
+    if (threadIdx.x == 0) {
+        unsigned long long c1 = clock64(), t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        clk[2 * blockIdx.x] = c1 - c0 + (sacc == 123.456 ? 1 : 0);
+        clk[2 * blockIdx.x + 1] = t1 - t0;
+    }
+    if (sacc == 123.456) out[0] = sacc;
+}
+
 extern "C" {
+
+int fdfd_dmma_pattern_probe(int pattern, int warps, double* out4) {
+    if (warps < 1 || warps > 8) FDFD_FAIL("warps per SM: 1..8");
+    double* d = nullptr;
+    unsigned long long* clk = nullptr;
+    FDFD_CHECK(cudaMalloc(&d, sizeof(double)));
+    FDFD_CHECK(cudaMalloc(&clk, sizeof(unsigned long long) * 2 * 148));
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    const int iters = 8000;
+    auto launch = [&](int it) {
+        if (pattern == 0) dmma_pattern_kernel<0><<<148, warps * 32>>>(d, clk, it);
+        else if (pattern == 1) dmma_pattern_kernel<1><<<148, warps * 32>>>(d, clk, it);
+        else if (pattern == 2) dmma_pattern_kernel<2><<<148, warps * 32>>>(d, clk, it);
+        else dmma_pattern_kernel<3><<<148, warps * 32>>>(d, clk, it);
+    };
+    launch(100);
+    FDFD_CHECK(cudaDeviceSynchronize());
+    FDFD_CHECK(cudaEventRecord(e0));
+    launch(iters);
+    FDFD_CHECK(cudaEventRecord(e1));
+    FDFD_CHECK(cudaEventSynchronize(e1));
+    FDFD_CHECK(cudaGetLastError());
+    float ms = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    unsigned long long h[2 * 148];
+    FDFD_CHECK(cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost));
+    double mhz = 0;
+    for (int i = 0; i < 148; ++i) mhz += h[2 * i + 1] ? (double)h[2 * i] / (double)h[2 * i + 1] * 1e3 : 0.0;
+    const double fl = 148.0 * warps * (double)iters * 48.0 * 512.0;
+    out4[0] = fl / (ms * 1e-3) / 1e12;
+    out4[1] = mhz / 148.0;
+    out4[2] = ms;
+    out4[3] = out4[0] / (148 * 128 * out4[1] * 1e-6);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(clk);
+    return 0;
+}
 
 int fdfd_dmma_peak(double* tflops) {
     double* d = nullptr;

@@ -1210,7 +1210,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                 }
                 FDFD_CHECK(cudaEventRecord(s->la_done, s->la_stream));
                 lookahead_done = true;
-                const int reserve = nb <= 4 ? 8 : 16;
+                const int reserve = nb <= 4 ? 4 : (nb <= 8 ? 8 : 16);
                 g_zgemm_max_ctas = 148 - reserve;
                 PhaseScope ph(PH_SCHUR, st);
                 // rows [k1, m): the rectangle left of the corner's columns, then the lower square

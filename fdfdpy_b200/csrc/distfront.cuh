@@ -382,12 +382,16 @@ static int dist_factor(NdSolver* s, NdDistFront* f, const NdDistFront* child, co
         }
     }
     // ---- elimination steps
+    bool la_pending = false;        // this rank already inverted (is inverting) the coming pivot block on the side stream
     for (int sidx = 0; sidx < f->nsteps; ++sidx) {
         g_phase_timing.level = f->level0 + sidx;
         const int col0 = f->bstart[sidx], b1 = f->bstart[sidx + 1], k = b1 - col0, owner = f->bowner[sidx];
         const int mbelow = n - b1, r0 = f->r0[sidx], mloc = f->nloc - r0;
         if (!f->Einv[sidx]) FDFD_CHECK(cudaMalloc(&f->Einv[sidx], sizeof(cplx) * (size_t)k * k));
-        if (me == owner) {
+        if (me == owner && la_pending) {
+            FDFD_CHECK(cudaStreamWaitEvent(st, s->la_done, 0));
+            la_pending = false;
+        } else if (me == owner) {
             const cplx* piv = f->F + (size_t)f->lrow0[sidx] * n + col0;
             if (k <= 64) {
                 PhaseScope ph(PH_PIVOT, st);
@@ -437,17 +441,46 @@ static int dist_factor(NdSolver* s, NdDistFront* f, const NdDistFront* child, co
         {
             // S -= G F_RE^T on my block rows: columns from the first remaining slot up to the end of the block itself
             PhaseScope ph(PH_SCHUR, st);
-            for (int j = sidx + 1; j < f->nblk; ++j) {
-                if (f->bowner[j] != me) continue;
+            auto update_block = [&](int j) -> int {
                 const int rows_j = f->bstart[j + 1] - f->bstart[j], ncols = f->bstart[j + 1] - b1;
                 gb.transb = 1; gb.lower = 0; gb.mode = 1;
                 gb.A = f->G[sidx] + (size_t)(f->lrow0[j] - r0) * k; gb.sA = 0; gb.lda = k;
                 gb.B = s->dist_panel; gb.sB = 0; gb.ldb = k;
                 gb.C = f->F + (size_t)f->lrow0[j] * n + b1; gb.sC = 0; gb.ldc = n;
                 gb.M = rows_j; gb.N = ncols; gb.K = k;
-                if (zgemm_batched(gb, st)) return -1;
                 s->factor_flops += 8.0 * (double)rows_j * ncols * k;
+                return zgemm_batched(gb, st);
+            };
+            // LOOK-AHEAD: if the next pivot block is mine, its rows are updated first and it is inverted on the side
+            // stream while the other block rows (mine and everybody else's) are still being updated
+            const int nxt = sidx + 1;
+            const int k1 = nxt < f->nsteps ? f->bstart[nxt + 1] - f->bstart[nxt] : 0;
+            const bool la = g_lookahead_enabled && nxt < f->nsteps && f->bowner[nxt] == me && k1 > 64;
+            if (la) {
+                if (update_block(nxt)) return -1;
+                if (!f->Einv[nxt]) FDFD_CHECK(cudaMalloc(&f->Einv[nxt], sizeof(cplx) * (size_t)k1 * k1));
+                FDFD_CHECK(cudaEventRecord(s->la_ready, st));
+                FDFD_CHECK(cudaStreamWaitEvent(s->la_stream, s->la_ready, 0));
+                const cplx* piv = f->F + (size_t)f->lrow0[nxt] * n + f->bstart[nxt];
+                int chunks = chunks_for((long long)k1 * k1, 1);
+                sym_expand_kernel<<<(unsigned)chunks, 256, 0, s->la_stream>>>(piv, f->Einv[nxt], k1, n, 0, chunks);
+                ++g_fdfd_launches;
+                const bool timing = g_phase_timing.on;
+                g_phase_timing.on = false;
+                int rc = sym_invert_batch(s, f->Einv[nxt], (long long)k1 * k1, k1, k1, 1, s->fws_W, s->la_stream);
+                g_phase_timing.on = timing;
+                if (rc) return -1;
+                FDFD_CHECK(cudaEventRecord(s->la_done, s->la_stream));
+                la_pending = true;
+                g_zgemm_max_ctas = 148 - 8;
             }
+            int rc = 0;
+            for (int j = sidx + 1; j < f->nblk && !rc; ++j) {
+                if (f->bowner[j] != me || (la && j == nxt)) continue;
+                rc = update_block(j);
+            }
+            g_zgemm_max_ctas = 148;
+            if (rc) return -1;
         }
     }
     return 0;

@@ -227,10 +227,11 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned tile, unsigned tiles_p
     return t;
 }
 
-template <int STAGES, bool TB, bool M3>
+template <int STAGES, bool TB, bool M3, int BK>
 __global__ void __launch_bounds__(256, 1)
 zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles) {
-    constexpr int WN = 2, BM = 64, BN = 64, BK = 16;
+    constexpr int WN = 2, BM = 64, BN = 64;
+    constexpr int RPP = 256 / BK, NPASS = 64 / RPP;      // rows one pass of the 256 threads covers / passes per tile
     constexpr int LDA = BK + 4, LDB = TB ? BK + 4 : BN + 2;
     constexpr int A_ELEMS = BM * LDA, B_ELEMS = TB ? BN * LDB : BK * LDB;
     extern __shared__ __align__(16) unsigned char zg_smem[];
@@ -247,10 +248,11 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
     // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor).  Each thread copies four 16-byte
     // chunks of the A tile and four of the B tile per k-tile; their global pointers only advance by a
     // constant per k-tile, so the hot loop carries two pointers and two row masks and no index math.
-    const int a_r = tid >> 4, a_c = tid & 15;                       // A (and B^T): rows a_r + 16 i, k column a_c
+    const int a_r = tid / BK, a_c = tid % BK;                       // A (and B^T): rows a_r + RPP i, k column a_c
     const int b_r = TB ? a_r : tid >> 6, b_c = TB ? a_c : tid & 63; // B (K x N): k rows b_r + 4 i, n column b_c
-    const long long a_step = 16LL * g.lda, b_step = TB ? 16LL * g.ldb : 4LL * g.ldb;
-    const long long b_adv = TB ? 16LL : 16LL * g.ldb;
+    constexpr int BPASS = TB ? NPASS : BK / 4;
+    const long long a_step = (long long)RPP * g.lda, b_step = TB ? (long long)RPP * g.ldb : 4LL * g.ldb;
+    const long long b_adv = TB ? (long long)BK : (long long)BK * g.ldb;
     unsigned ld_tile = blockIdx.x;
     int ld_kt = 0, ld_stage = 0;
     unsigned amask = 0, bmask = 0;
@@ -261,15 +263,15 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         pa = g.A + (long long)t.b * g.sA + (long long)(ld_m + a_r) * g.lda + a_c;
         amask = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) amask |= (ld_m + a_r + 16 * i < g.M ? 1u : 0u) << i;
+        for (int i = 0; i < NPASS; ++i) amask |= (ld_m + a_r + RPP * i < g.M ? 1u : 0u) << i;
         if (TB) {
             pb = g.B + (long long)t.b * g.sB + (long long)(ld_n + b_r) * g.ldb + b_c;
             bmask = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bmask |= (ld_n + b_r + 16 * i < g.N ? 1u : 0u) << i;
+            for (int i = 0; i < NPASS; ++i) bmask |= (ld_n + b_r + RPP * i < g.N ? 1u : 0u) << i;
         } else {
             pb = g.B + (long long)t.b * g.sB + (long long)b_r * g.ldb + ld_n + b_c;
-            bmask = ld_n + b_c < g.N ? 0xFu : 0u;
+            bmask = ld_n + b_c < g.N ? 0xFFFFu : 0u;
         }
     };
     decode_load();
@@ -279,14 +281,14 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         cplx* bs = Bs + ld_stage * B_ELEMS + b_r * LDB + b_c;
         const bool kok = k0 + a_c < g.K;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NPASS; ++i) {
             bool ok = kok && ((amask >> i) & 1u);
-            cp_async16(as + i * 16 * LDA, ok ? pa + i * a_step : g.A, ok);
+            cp_async16(as + i * RPP * LDA, ok ? pa + i * a_step : g.A, ok);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < BPASS; ++i) {
             bool ok = TB ? (kok && ((bmask >> i) & 1u)) : (bmask && k0 + b_r + 4 * i < g.K);
-            cp_async16(bs + i * (TB ? 16 : 4) * LDB, ok ? pb + i * b_step : g.B, ok);
+            cp_async16(bs + i * (TB ? RPP : 4) * LDB, ok ? pb + i * b_step : g.B, ok);
         }
         pa += BK;
         pb += b_adv;
@@ -423,9 +425,9 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
     cp_async_wait<0>();
 }
 
-template <int WM, int WN, int STAGES, bool TB>
+template <int WM, int WN, int STAGES, bool TB, int BK = 16>
 constexpr size_t zgemm_smem_bytes() {
-    return sizeof(cplx) * STAGES * ((16 * WM) * (16 + 4) + (TB ? (32 * WN) * (16 + 4) : 16 * (32 * WN + 2)));
+    return sizeof(cplx) * STAGES * ((16 * WM) * (BK + 4) + (TB ? (32 * WN) * (BK + 4) : BK * (32 * WN + 2)));
 }
 
 // optional live timing of every GEMM launch (CUDA events on the launching stream); see capi.cu
@@ -439,7 +441,8 @@ struct ZgemmTiming {
 extern ZgemmTiming g_zgemm_timing;
 extern int g_zgemm_max_ctas;  // CTAs of the persistent kernel (148 = one per SM; fewer leaves SMs to a side stream)
 extern int g_zgemm_variant;   // bit 0: always the tiled kernel (default: persistent kernel for large problems);
-                              // bit 1: textbook 4M complex products (default: 3M)
+                              // bit 1: textbook 4M complex products (default: 3M); bit 2: persistent kernel with
+                              // k-tiles of 16 x 4 stages (default: 32 x 3 stages)
 
 template <bool TB, bool M3>
 static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
@@ -459,15 +462,29 @@ static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
         return -1;
     }
     if ((g_zgemm_variant & 1) == 0 && blocks >= 148) {
-        constexpr int ST = 4;
-        constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB>();
-        static bool attr_p = false;
-        if (!attr_p) {
-            cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sm);
-            attr_p = true;
+        // k-tiles of 32 with a 3-stage ring (221 KB): half the barriers and post-barrier bubbles of the 16 x 4-stage
+        // form (bit 2 of the variant keeps that one for A/B runs), the same bytes in flight
+        if ((g_zgemm_variant & 4) == 0) {
+            constexpr int ST = 3, BK = 32;
+            constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB, BK>();
+            static bool attr_p = false;
+            if (!attr_p) {
+                cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB, M3, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sm);
+                attr_p = true;
+            }
+            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+        } else {
+            constexpr int ST = 4, BK = 16;
+            constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB, BK>();
+            static bool attr_p = false;
+            if (!attr_p) {
+                cudaFuncSetAttribute(zgemm_dmma_persistent_kernel<ST, TB, M3, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sm);
+                attr_p = true;
+            }
+            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
         }
-        zgemm_dmma_persistent_kernel<ST, TB, M3><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
     } else {
         constexpr size_t sm = zgemm_smem_bytes<4, 2, 3, TB>();
         static bool attr_set = false;

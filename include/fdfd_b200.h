@@ -47,6 +47,9 @@ int fdfd_dmma_probe(int warps_per_sm, int independent_accumulators, double* tflo
 /* the same loop run for ~50 ms with the SM clock measured inside the kernel:
  * out4 = { TFLOP/s, SM MHz during the probe, ms, real flops } */
 int fdfd_dmma_probe_clocked(int warps_per_sm, int independent_accumulators, double* out4);
+/* issue-order probe of the 3M inner loop (24 accumulators, register operands); pattern 0..3, see capi.cu.
+ * out4 = { TFLOP/s executed, SM MHz, ms, fraction of the pipe at that clock } */
+int fdfd_dmma_pattern_probe(int pattern, int warps_per_sm, double* out4);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
 int fdfd_host_unregister(void* host);

@@ -83,6 +83,29 @@ def test_distributed_fronts_vs_oracle(world, pol, shape, knobs):
     assert max(r[4] for r in res) < 0.75 * total if world >= 4 else True
 
 
+def test_distributed_fronts_with_lookahead_size():
+    """A grid whose top separators are cut into pieces of several hundred nodes (the production regime: recursive
+    block inversion of the pivot blocks, look-ahead on the side stream, persistent GEMM kernel), 2 and 4 ranks,
+    against the single-rank solver and the residual contract."""
+    from fdfdpy_b200 import core
+    rng = np.random.default_rng(5)
+    nx, ny = 640, 600
+    eps = 1 + 5 * (rng.random((nx, ny)) > 0.6)
+    b = rng.standard_normal((2, nx, ny)) + 1j * rng.standard_normal((2, nx, ny))
+    op = core.MaxwellOperator(OMEGA, eps, 0.03, [10, 12], "Ez", 1e-6)
+    ref = np.array(op.direct().solve(b)).reshape(b.shape)
+    assert op.direct().last_relres < 1e-10
+    for world in (2, 4):
+        res = _sharded_solve(world, eps, [10, 12], "Ez", b, dl=0.03)
+        for x, x2, relres, ndist, _ in res:
+            assert relres < 1e-10
+            assert relerr(x, ref) < 1e-9, world
+            assert np.array_equal(x, res[0][0])
+    with env(FDFD_LOOKAHEAD=0):
+        res0 = _sharded_solve(2, eps, [10, 12], "Ez", b, dl=0.03)
+    assert relerr(res0[0][0], ref) < 1e-9
+
+
 def test_owner_per_front_scheme_still_works():
     """FDFD_DIST_FRONTS=0: the shared fronts live on the lowest rank of their group (round 1's scheme, one Schur block
     per level over the wire)."""
