@@ -345,21 +345,32 @@ __device__ __forceinline__ cplx small_front_gather(const SmallFrontArgs& a, cons
 
 // KT / MT > 0: front sizes known at compile time (the levels of a power-of-two grid), so the index arithmetic
 // folds to constants and the short inner products unroll; 0: taken from the arguments.
-template <int KMAX, int KT = 0, int MT = 0>
-__global__ void small_front_kernel(SmallFrontArgs a) {
+// A front is worked by WPF warps (1, 2 or 4); a CTA holds several fronts (blockDim.x / (32 WPF)), each group with its
+// own slice of shared memory and its own barrier -- the tiny leaf-side fronts no longer leave half a CTA idle while
+// one warp inverts, and a resident CTA carries 4-8 fronts instead of one.
+template <int WPF>
+__device__ __forceinline__ void front_sync(int group) {
+    if (WPF == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(WPF * 32) : "memory");
+}
+template <int KMAX, int KT, int MT, int WPF>
+__global__ void small_front_kernel(SmallFrontArgs a, long long nb, int front_smem_cplx) {
     extern __shared__ __align__(16) unsigned char sf_smem[];
     const int k = KT ? KT : a.kmax, m = MT ? MT : a.mmax, n = k + m, w2 = 2 * k;
-    cplx* W = reinterpret_cast<cplx*>(sf_smem);      // [k][2k]: row r = [ E[r][:] | Einv[r][:] ]
+    const int group = threadIdx.x / (32 * WPF), tid = threadIdx.x % (32 * WPF), nt = 32 * WPF;
+    const int fpc = blockDim.x / (32 * WPF);
+    const long long b = (long long)blockIdx.x * fpc + group;
+    if (b >= nb) return;                                // whole groups leave together: no barrier is left waiting
+    cplx* W = reinterpret_cast<cplx*>(sf_smem) + (size_t)group * front_smem_cplx;   // [k][2k]: row r = [ E[r][:] | Einv[r][:] ]
     cplx* R = W + (size_t)k * w2;                     // [m][k]   F_RE
     cplx* Gs = R + (size_t)m * k;                     // [m][k]   G
     cplx* Sm = Gs + (size_t)m * k;                    // [m][m]   F_RR, leaf levels only
-    __shared__ int s_i1[128], s_i2[128];
-    const long long b = blockIdx.x;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const bool leaf = a.kind == 0;
+    int* s_i1 = reinterpret_cast<int*>(W + (size_t)front_smem_cplx - (leaf ? 0 : 2 * ((n + 3) / 4)));   // [n] + [n] ints at the tail
+    int* s_i2 = s_i1 + n;
     const int c = a.cls[b];
     const int kcls = a.k_cls[c];
     const cplx zero = make_double2(0.0, 0.0);
-    const bool leaf = a.kind == 0;
     const cplx *S1 = nullptr, *S2 = nullptr;
     {
         const int nz = k * w2 + m * k + (leaf ? m * k + m * m : 0);      // W, R (and Gs, Sm for a leaf)
@@ -373,7 +384,7 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
         S1 = a.Sc + (long long)a.ch1[b] * a.sc;
         S2 = a.Sc + (long long)a.ch2[b] * a.sc;
     }
-    __syncthreads();
+    front_sync<WPF>(group);
     for (int r = kcls + tid; r < k; r += nt) W[r * w2 + r] = make_double2(1.0, 0.0);       // padded pivots
     // ---- assemble F_EE, F_RE (and F_RR for a leaf)
     if (leaf) {
@@ -399,10 +410,10 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
             small_front_put(W, R, Sm, k, m, p, q, v);
         }
     }
-    __syncthreads();
-    // ---- Einv (right half of W) by the first warp, one row per lane
+    front_sync<WPF>(group);
+    // ---- Einv (right half of W) by the group's first warp, one row per lane
     if (tid < 32) warp_invert<KMAX>(W, W + k, w2, k, a.info);
-    __syncthreads();
+    front_sync<WPF>(group);
     // ---- G = F_RE Einv
     cplx* Eo = a.Einv + b * (long long)k * k;
     for (int e = tid; e < k * k; e += nt) Eo[e] = W[(e / k) * w2 + k + e % k];
@@ -415,7 +426,7 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
         Gs[e] = acc;
         Go[e] = acc;
     }
-    __syncthreads();
+    front_sync<WPF>(group);
     // ---- S = F_RR - G F_RE^T (lower), F_RR gathered from the children on the fly
     cplx* So = a.S + b * (long long)m * m;
     for (int e = tid; e < m * m; e += nt) {
@@ -432,9 +443,11 @@ __global__ void small_front_kernel(SmallFrontArgs a) {
     }
 }
 
-static size_t small_front_smem(int k, int m, bool leaf) {
-    return sizeof(cplx) * ((size_t)k * 2 * k + 2 * (size_t)m * k + (leaf ? (size_t)m * m : 0));
+// complex entries of shared memory one front needs (the two child maps of a merge front ride at the tail)
+static size_t small_front_cplx(int k, int m, bool leaf) {
+    return (size_t)k * 2 * k + 2 * (size_t)m * k + (leaf ? (size_t)m * m : 2 * (size_t)((k + m + 3) / 4));
 }
+static size_t small_front_smem(int k, int m, bool leaf) { return sizeof(cplx) * small_front_cplx(k, m, leaf); }
 static bool small_front_ok(int k, int m, bool leaf) {
     return k <= 16 && k + m <= 128 && small_front_smem(k, m, leaf) <= 200 * 1024;
 }
@@ -1097,24 +1110,35 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             a.planes = op->planes; a.isxf = op->isxf; a.isyf = op->isyf;
             a.Sc = Fprev; a.sc = prev_stride; a.kc = prev_k; a.nc = prev_n;
             a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
-            size_t smem = small_front_smem(kmax, mmax, L.kind == 0);
-            int threads = nmax <= 40 ? 64 : (nmax <= 64 ? 128 : 256);
-            void (*kern)(SmallFrontArgs) = kmax <= 3 ? small_front_kernel<3>
-                                           : kmax <= 7 ? small_front_kernel<7>
-                                           : kmax <= 9 ? small_front_kernel<9>
-                                           : kmax <= 12 ? small_front_kernel<12> : small_front_kernel<16>;
+            // warps per front by front size, fronts per CTA by what fits (<= 8 groups, <= 200 KB, <= 512 threads)
+            const size_t fsm = small_front_cplx(kmax, mmax, L.kind == 0);
+            const int wpf = nmax <= 64 ? 1 : (nmax <= 96 ? 2 : 4);
+            int fpc = (int)std::min<size_t>(8, (200 * 1024) / (fsm * sizeof(cplx)));
+            fpc = std::max(1, std::min(fpc, 512 / (32 * wpf)));
+            const size_t smem = fsm * sizeof(cplx) * fpc;
+            const int threads = fpc * wpf * 32;
+            typedef void (*SfKern)(SmallFrontArgs, long long, int);
+            auto pick = [&](auto kmax_c, auto kt_c, auto mt_c) -> SfKern {
+                constexpr int KM = decltype(kmax_c)::value, KT = decltype(kt_c)::value, MT = decltype(mt_c)::value;
+                return wpf == 1 ? small_front_kernel<KM, KT, MT, 1> : wpf == 2 ? small_front_kernel<KM, KT, MT, 2>
+                                                                                : small_front_kernel<KM, KT, MT, 4>;
+            };
+#define SF_PICK(KM, KT, MT) pick(std::integral_constant<int, KM>(), std::integral_constant<int, KT>(), std::integral_constant<int, MT>())
+            SfKern kern = kmax <= 3 ? SF_PICK(3, 0, 0) : kmax <= 7 ? SF_PICK(7, 0, 0) : kmax <= 9 ? SF_PICK(9, 0, 0)
+                          : kmax <= 12 ? SF_PICK(12, 0, 0) : SF_PICK(16, 0, 0);
             // the bottom levels of a power-of-two grid (4-cell leaves): sizes as compile-time constants
-            if (kmax == 9 && mmax == 16) kern = small_front_kernel<9, 9, 16>;
-            else if (kmax == 3 && mmax == 24) kern = small_front_kernel<3, 3, 24>;
-            else if (kmax == 7 && mmax == 32) kern = small_front_kernel<7, 7, 32>;
-            else if (kmax == 7 && mmax == 48) kern = small_front_kernel<7, 7, 48>;
-            else if (kmax == 15 && mmax == 64) kern = small_front_kernel<16, 15, 64>;
-            else if (kmax == 15 && mmax == 96) kern = small_front_kernel<16, 15, 96>;
+            if (kmax == 9 && mmax == 16) kern = SF_PICK(9, 9, 16);
+            else if (kmax == 3 && mmax == 24) kern = SF_PICK(3, 3, 24);
+            else if (kmax == 7 && mmax == 32) kern = SF_PICK(7, 7, 32);
+            else if (kmax == 7 && mmax == 48) kern = SF_PICK(7, 7, 48);
+            else if (kmax == 15 && mmax == 64) kern = SF_PICK(16, 15, 64);
+            else if (kmax == 15 && mmax == 96) kern = SF_PICK(16, 15, 96);
+#undef SF_PICK
             if (smem > 48 * 1024)
                 FDFD_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 PhaseScope ph(PH_SMALL, st);
-                kern<<<(unsigned)nb, threads, smem, st>>>(a);
+                kern<<<(unsigned)((nb + fpc - 1) / fpc), threads, smem, st>>>(a, nb, (int)fsm);
                 ++g_fdfd_launches;
             }
             FDFD_CHECK(cudaGetLastError());
