@@ -59,6 +59,7 @@ SIGNATURES = {
     "fdfd_dmma_probe": (C.c_int, [C.c_int, C.c_int, _dp]),
     "fdfd_dmma_probe_clocked": (C.c_int, [C.c_int, C.c_int, _vp]),
     "fdfd_dmma_pattern_probe": (C.c_int, [C.c_int, C.c_int, _vp]),
+    "fdfd_dmma_smem_probe": (C.c_int, [C.c_int, _vp]),
     "fdfd_host_register": (C.c_int, [_vp, C.c_double]),
     "fdfd_host_unregister": (C.c_int, [_vp]),
     "fdfd_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_double]),

@@ -175,7 +175,121 @@ __global__ void __launch_bounds__(256) dmma_pattern_kernel(double* out, unsigned
     if (sacc == 123.456) out[0] = sacc;
 }
 
+/* the GEMM's k-step verbatim (fragments by LDS.128 from a shared-memory tile, re + im sums by DADD, 24 DMMAs) in an
+ * endless k loop over ONE resident tile: no global loads, no cp.async, MODE 0: no barrier at all; MODE 1: a CTA barrier
+ * every 8 k-steps (the k-tile cadence of the kernel); MODE 2: barrier + 16 cp.async of 16 bytes per thread per k-tile
+ * into a second buffer (the ring's traffic without its latency). */
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) dmma_smem_kernel(double* out, unsigned long long* clk, const double2* src, int iters) {
+    constexpr int BK = 32, LDA = BK + 4;
+    extern __shared__ __align__(16) unsigned char ps_smem[];
+    double2* As = reinterpret_cast<double2*>(ps_smem);           // [64][LDA]
+    double2* Bs = As + 64 * LDA;                                   // [64][LDA]
+    double2* Dump = Bs + 64 * LDA;                                 // cp.async landing zone, 2 x 64 x LDA
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp / 2, wn = warp % 2, gq = lane >> 2, tq = lane & 3;
+    for (int i = tid; i < 2 * 64 * LDA; i += 256) As[i] = make_double2(1.0 + 1e-9 * i, 1.0 - 1e-9 * i);
+    __syncthreads();
+    double t1[2][4][2], t2[2][4][2], t3[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { t1[i][j][0] = t1[i][j][1] = t2[i][j][0] = t2[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0; }
+    unsigned long long t0 = 0, c0 = 0;
+    if (tid == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        c0 = clock64();
+    }
+    struct Frag { double2 a[2], b[4]; double as_[2], bs_[4]; };
+    auto load_frag = [&](Frag& f, int kk) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { f.a[mt] = As[(wm * 16 + mt * 8 + gq) * LDA + kk + tq]; f.as_[mt] = f.a[mt].x + f.a[mt].y; }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { f.b[nt] = Bs[(wn * 32 + nt * 8 + gq) * LDA + kk + tq]; f.bs_[nt] = f.b[nt].x + f.b[nt].y; }
+    };
+    for (int it = 0; it < iters; ++it) {
+        if (MODE >= 1) __syncthreads();
+        if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cp_async16(Dump + (i * 256 + tid) % (2 * 64 * LDA), src + (i * 256 + tid), true);
+            cp_async_commit();
+            cp_async_wait<1>();
+        }
+        Frag f[2];
+        load_frag(f[0], 0);
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            if (ks + 1 < BK / 4) load_frag(f[(ks + 1) & 1], 4 * (ks + 1));
+            const Frag& c = f[ks & 1];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(t1[mt][nt][0], t1[mt][nt][1], c.a[mt].x, c.b[nt].x);
+                    dmma884(t2[mt][nt][0], t2[mt][nt][1], c.a[mt].y, c.b[nt].y);
+                }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], c.as_[mt], c.bs_[nt]);
+        }
+    }
+    cp_async_wait<0>();
+    double sacc = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sacc += t1[i][j][0] + t1[i][j][1] + t2[i][j][0] + t2[i][j][1] + t3[i][j][0] + t3[i][j][1];
+    if (tid == 0) {
+        unsigned long long c1 = clock64(), tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        clk[2 * blockIdx.x] = c1 - c0 + (sacc == 123.456 ? 1 : 0);
+        clk[2 * blockIdx.x + 1] = tt - t0;
+    }
+    if (sacc == 123.456) out[0] = sacc;
+}
+
 extern "C" {
+
+int fdfd_dmma_smem_probe(int mode, double* out4) {
+    double* d = nullptr;
+    double2* src = nullptr;
+    unsigned long long* clk = nullptr;
+    FDFD_CHECK(cudaMalloc(&d, sizeof(double)));
+    FDFD_CHECK(cudaMalloc(&src, sizeof(double2) * 4096));
+    FDFD_CHECK(cudaMemset(src, 0, sizeof(double2) * 4096));
+    FDFD_CHECK(cudaMalloc(&clk, sizeof(unsigned long long) * 2 * 148));
+    cudaEvent_t e0, e1;
+    FDFD_CHECK(cudaEventCreate(&e0));
+    FDFD_CHECK(cudaEventCreate(&e1));
+    const int iters = 4000;
+    const size_t sm = sizeof(double2) * 4 * 64 * 36;
+    auto launch = [&](int it) {
+        if (mode == 0) { cudaFuncSetAttribute(dmma_smem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); dmma_smem_kernel<0><<<148, 256, sm>>>(d, clk, src, it); }
+        else if (mode == 1) { cudaFuncSetAttribute(dmma_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); dmma_smem_kernel<1><<<148, 256, sm>>>(d, clk, src, it); }
+        else { cudaFuncSetAttribute(dmma_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); dmma_smem_kernel<2><<<148, 256, sm>>>(d, clk, src, it); }
+    };
+    launch(50);
+    FDFD_CHECK(cudaDeviceSynchronize());
+    FDFD_CHECK(cudaEventRecord(e0));
+    launch(iters);
+    FDFD_CHECK(cudaEventRecord(e1));
+    FDFD_CHECK(cudaEventSynchronize(e1));
+    FDFD_CHECK(cudaGetLastError());
+    float ms = 0;
+    FDFD_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    unsigned long long h[2 * 148];
+    FDFD_CHECK(cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost));
+    double mhz = 0;
+    for (int i = 0; i < 148; ++i) mhz += h[2 * i + 1] ? (double)h[2 * i] / (double)h[2 * i + 1] * 1e3 : 0.0;
+    const double fl = 148.0 * 8 * (double)iters * 8.0 * 24.0 * 512.0;
+    out4[0] = fl / (ms * 1e-3) / 1e12;
+    out4[1] = mhz / 148.0;
+    out4[2] = ms;
+    out4[3] = out4[0] / (148 * 128 * out4[1] * 1e-6);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(clk); cudaFree(src);
+    return 0;
+}
 
 int fdfd_dmma_pattern_probe(int pattern, int warps, double* out4) {
     if (warps < 1 || warps > 8) FDFD_FAIL("warps per SM: 1..8");

@@ -345,7 +345,7 @@ __device__ __forceinline__ cplx small_front_gather(const SmallFrontArgs& a, cons
 
 // KT / MT > 0: front sizes known at compile time (the levels of a power-of-two grid), so the index arithmetic
 // folds to constants and the short inner products unroll; 0: taken from the arguments.
-// A front is worked by WPF warps (1, 2 or 4); a CTA holds several fronts (blockDim.x / (32 WPF)), each group with its
+// A front is worked by WPF warps (1, 2, 4 or 8); a CTA holds several fronts (blockDim.x / (32 WPF)), each group with its
 // own slice of shared memory and its own barrier -- the tiny leaf-side fronts no longer leave half a CTA idle while
 // one warp inverts, and a resident CTA carries 4-8 fronts instead of one.
 template <int WPF>
@@ -1112,7 +1112,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             a.Einv = L.Einv; a.G = L.G; a.S = F; a.info = s->d_info;
             // warps per front by front size, fronts per CTA by what fits (<= 8 groups, <= 200 KB, <= 512 threads)
             const size_t fsm = small_front_cplx(kmax, mmax, L.kind == 0);
-            const int wpf = nmax <= 64 ? 1 : (nmax <= 96 ? 2 : 4);
+            const int wpf = nmax <= 40 ? 1 : (nmax <= 64 ? 4 : 8);
             int fpc = (int)std::min<size_t>(8, (200 * 1024) / (fsm * sizeof(cplx)));
             fpc = std::max(1, std::min(fpc, 512 / (32 * wpf)));
             const size_t smem = fsm * sizeof(cplx) * fpc;
@@ -1121,7 +1121,7 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
             auto pick = [&](auto kmax_c, auto kt_c, auto mt_c) -> SfKern {
                 constexpr int KM = decltype(kmax_c)::value, KT = decltype(kt_c)::value, MT = decltype(mt_c)::value;
                 return wpf == 1 ? small_front_kernel<KM, KT, MT, 1> : wpf == 2 ? small_front_kernel<KM, KT, MT, 2>
-                                                                                : small_front_kernel<KM, KT, MT, 4>;
+                       : wpf == 4 ? small_front_kernel<KM, KT, MT, 4> : small_front_kernel<KM, KT, MT, 8>;
             };
 #define SF_PICK(KM, KT, MT) pick(std::integral_constant<int, KM>(), std::integral_constant<int, KT>(), std::integral_constant<int, MT>())
             SfKern kern = kmax <= 3 ? SF_PICK(3, 0, 0) : kmax <= 7 ? SF_PICK(7, 0, 0) : kmax <= 9 ? SF_PICK(9, 0, 0)

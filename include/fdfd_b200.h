@@ -50,6 +50,8 @@ int fdfd_dmma_probe_clocked(int warps_per_sm, int independent_accumulators, doub
 /* issue-order probe of the 3M inner loop (24 accumulators, register operands); pattern 0..3, see capi.cu.
  * out4 = { TFLOP/s executed, SM MHz, ms, fraction of the pipe at that clock } */
 int fdfd_dmma_pattern_probe(int pattern, int warps_per_sm, double* out4);
+/* the GEMM's k-step from a resident shared-memory tile: mode 0 no barrier, 1 barrier per k-tile, 2 barrier + cp.async */
+int fdfd_dmma_smem_probe(int mode, double* out4);
 /* page-lock / unlock an existing host buffer so the *_host entry points copy at full PCIe rate */
 int fdfd_host_register(void* host, double bytes);
 int fdfd_host_unregister(void* host);
