@@ -378,11 +378,12 @@ def run_ours(args):
     e2e_val = world * ncell / e2e_max / 1e6
     peaks, peak_src = measured_peaks()
     big_ms, big_fl, big_n = gt[0] + gt[3], gt[1] + gt[4], gt[2] + gt[5]
-    # The GEMMs compute a complex multiply-add with THREE real tensor products (3M / Karatsuba, zgemm.cuh): the
-    # algorithm's flop count is 6 per complex MAC, and that is what is held against the pipe; the textbook count
-    # (8 per complex MAC, what cuBLAS ZGEMM executes) is reported next to it as the 4M-equivalent rate.
-    achieved = exec_fl.value / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
-    achieved_4m = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
+    # ALGORITHMIC flops of a complex GEMM = 8 per complex multiply-add (4 real mul + 4 real add: the count LAPACK, cuBLAS
+    # ZGEMM and every FP64 peak figure use).  `achieved` is that count over the measured kernel time.  The kernels
+    # EXECUTE only 6 tensor flops per complex MAC (3M / Karatsuba form, zgemm.cuh); the executed rate is what occupies
+    # the pipe and is reported next to it (`achieved_executed`, `frac_executed` = tensor-pipe utilisation).
+    achieved_exec = exec_fl.value / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
+    achieved = big_fl / (big_ms * 1e-3) / 1e12 if big_ms > 0 else 0.0
     # FP64 tensor-pipe ceiling: 128 flop/clk/SM (one m8n8k4 DMMA per SM sub-partition every 16 clocks) x 148 SMs at
     # the SM clock sampled under load.  MEASURED_PEAKS.json has no FP64 entry, so the denominator is this pipe rate;
     # the register-resident probe next to it shows how much of it an ideal instruction stream reaches on this board.
@@ -421,11 +422,14 @@ def run_ours(args):
                                    "clock = clock64 / globaltimer measured inside the same kernel"},
             "launches_timed": int(big_n), "kernel_ms_per_step": big_ms / args.steps,
             "share_of_step": big_ms / dev_ms if dev_ms else None,
-            "algorithmic_flops_per_step": exec_fl.value / args.steps,
-            "flops_per_complex_mac": 6,
-            "achieved_4m_equivalent": achieved_4m,
-            "achieved_4m_equivalent_note": "8 flops per complex multiply-add, the count cuBLAS ZGEMM executes "
-                                           "(tools/zgemm_vs_cublas.py: cuBLAS ZGEMM 8192^3 = 36.9 TFLOP/s on this board)",
+            "algorithmic_flops_per_step": big_fl / args.steps,
+            "algorithmic_flops_per_complex_mac": 8,
+            "executed_flops_per_step": exec_fl.value / args.steps, "executed_flops_per_complex_mac": 6,
+            "achieved_executed": achieved_exec,
+            "frac_executed": achieved_exec / fp64_peak if fp64_peak else None,
+            "note": "achieved = algorithmic flops (8 per complex multiply-add, the ZGEMM count; cuBLAS ZGEMM 8192^3 "
+                    "reaches 36.9 TFLOP/s on this board, tools/zgemm_vs_cublas.py) / kernel time; the 3M kernels "
+                    "execute 6 per complex MAC, so frac_executed (= tensor-pipe utilisation) is 3/4 of frac",
         },
         "roofline_stencil": {"kernel": "stencil_fused_ez_kernel", "bound": "hbm", "achieved": stencil_gbs,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stencil_gbs / peaks["hbm_gbs"],
