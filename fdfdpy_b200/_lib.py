@@ -94,6 +94,8 @@ SIGNATURES = {
     "fdfd_direct_add_dist_front": (C.c_int, [_vp, C.POINTER(DistFrontDesc)]),
     "fdfd_comm_create_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "fdfd_comm_abort": (None, [_vp]),
+    "fdfd_schwarz_sub_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int]),
+    "fdfd_slab_set_schwarz": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "fdfd_slab_op_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                       C.c_int, C.c_int, C.c_int, C.c_double]),
     "fdfd_krylov_solve_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
@@ -110,6 +112,7 @@ SIGNATURES = {
     "fdfd_zgemm_batched_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int]),
     "fdfd_stencil_set_variant": (C.c_int, [C.c_int, C.c_int]),
+    "fdfd_stencil_set_hz_variant": (C.c_int, [C.c_int, C.c_int]),
     "fdfd_zgemm_set_variant": (C.c_int, [C.c_int]),
     "fdfd_direct_set_small_fronts": (C.c_int, [C.c_int]),
     "fdfd_zgemm_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),

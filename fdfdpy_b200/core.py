@@ -54,6 +54,22 @@ class MaxwellOperator:
         self.preconditioner = None      # optional DirectSolver of a nearby operator (same grid)
         self.assemble(eps_r, eps_nl, averaging)
 
+    @classmethod
+    def _adopt(cls, handle, nx, ny, omega, dl, NPML, pol, L0):
+        """Wrap an operator handle the library created itself (fdfd_schwarz_sub_create); not assembled yet."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.nx, self.ny = int(nx), int(ny)
+        self.shape = (self.nx * self.ny, self.nx * self.ny)
+        self.pol = pol
+        self.omega, self.dl, self.L0 = float(omega), float(dl), float(L0)
+        self.NPML = [int(NPML[0]), int(NPML[1])]
+        self.h = handle
+        self._direct = None
+        self.preconditioner = None
+        self.has_nl = False
+        return self
+
     def assemble(self, eps_r, eps_nl=None, averaging=True):
         eps_r = np.asarray(eps_r)
         if eps_r.shape != (self.nx, self.ny):

@@ -685,6 +685,13 @@ int fdfd_slab_op_create(fdfd_op** out, fdfd_comm* comm, int gnx, int ny, int x0,
     if (npml_x < 0 || npml_y < 0) FDFD_FAIL("NPML entries must be >= 0");
     return op_create_slab(out, comm, gnx, ny, x0, nxl, omega, dl, npml_x, npml_y, pol, L0);
 }
+int fdfd_schwarz_sub_create(fdfd_op** out, fdfd_op* slab, int overlap, int npml_sub) {
+    return op_create_schwarz_sub(out, slab, overlap, npml_sub);
+}
+int fdfd_slab_set_schwarz(fdfd_op* slab, fdfd_op* sub, fdfd_direct* sub_factors, int overlap, int npml_sub) {
+    if (sub && (!sub_factors || !sub_factors->factored)) FDFD_FAIL("factorise the Schwarz subdomain before attaching it");
+    return schwarz_attach(slab, sub, sub_factors, overlap, npml_sub);
+}
 int fdfd_comm_create_local(fdfd_comm** out, int world) { return comm_create_local(out, world); }
 void fdfd_comm_abort(fdfd_comm* c) { comm_abort(c); }
 int fdfd_direct_add_dist_front(fdfd_direct* s, const fdfd_dist_front_desc* d) {
@@ -823,11 +830,18 @@ int fdfd_zgemm_batched_host(const double* A, const double* B, double* Cm, int M,
     return 0;
 }
 
-extern int g_fused_rows, g_fused_rows32;
+extern int g_fused_rows, g_fused_rows32, g_hz_halo_lanes, g_hz_chunk;
 int fdfd_stencil_set_variant(int rows_per_thread, int complex64) {
     if (rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8) FDFD_FAIL("rows per thread: 2, 4 or 8");
     if (complex64) g_fused_rows32 = rows_per_thread;
     else g_fused_rows = rows_per_thread;
+    return 0;
+}
+int fdfd_stencil_set_hz_variant(int chunk_rows, int halo_lanes) {
+    if (chunk_rows != 0 && chunk_rows != -4 && chunk_rows != -8 && (chunk_rows < 4 || chunk_rows > 1024 || (chunk_rows & 3)))
+        FDFD_FAIL("Hz stencil: 0 (auto), a multiple of 4 in 4 ... 1024 (rows per CTA), or -4 / -8 (one-shot kernel)");
+    g_hz_chunk = chunk_rows;
+    g_hz_halo_lanes = halo_lanes != 0;
     return 0;
 }
 int fdfd_zgemm_set_variant(int v) { g_zgemm_variant = v; return 0; }

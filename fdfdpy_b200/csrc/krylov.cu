@@ -269,17 +269,97 @@ static int residual_A(const FdfdOp* op, const V* b, const V* x, V* r, const cplx
     return c12 ? couple(op, r, c12, x, 1) : 0;
 }
 
-static int precond_solve(NdSolver* nd, const FdfdOp* op, const cplx* in, cplx* out) { return nd_solve(nd, op, in, out, 1); }
+// ------------------------------------------------------------------------------------------
+// Restricted additive Schwarz preconditioner of the slab path (one subdomain per rank).
+// Subdomain = the rank's rows + `ov` overlap rows + `npml_s` artificial PML rows on both sides, a local torus
+// factorised by the direct solver (op_create_schwarz_sub).  z = M^-1 r:
+//   1. r on the owned rows is copied into the subdomain right-hand side, the overlap rows arrive from the two
+//      neighbouring ranks (one grouped send/recv of ov rows each way), the PML rows stay zero;
+//   2. one substitution pass with the local factors;
+//   3. only the owned rows of the local solution are kept (the "restricted" part: no second exchange, no double
+//      counting in the overlap).
+// Information crosses one subdomain boundary per application, so the iteration count of the preconditioned
+// BiCGSTAB grows with the number of slabs (measured: DESIGN.md section 5).
+// ------------------------------------------------------------------------------------------
+struct SchwarzPre {
+    FdfdOp* sub;          // not owned (the host keeps the handle it assembled and factorised)
+    NdSolver* nd;         // not owned
+    int ov, npml_s, ext, nxl;
+    cplx *rin, *zout;     // subdomain right-hand side / solution, (nxl + 2 ext) x ny
+    cudaEvent_t ev_in, ev_out;
+};
+
+int schwarz_attach(FdfdOp* slab, FdfdOp* sub, NdSolver* nd, int overlap, int npml_sub) {
+    if (!slab->halo) FDFD_FAIL("the Schwarz preconditioner belongs to a slab operator");
+    if (slab->schwarz) { schwarz_destroy(slab->schwarz); slab->schwarz = nullptr; }
+    if (!sub) return 0;                                   // detach
+    const int nxl = slab->nx - 2, ext = overlap + npml_sub;
+    if (!nd || sub->nx != nxl + 2 * ext || sub->ny != slab->ny || nd->nx != sub->nx || nd->ny != sub->ny)
+        FDFD_FAIL("Schwarz subdomain / factor shape does not match the slab (%d + 2 x %d rows)", nxl, ext);
+    if (overlap > nxl) FDFD_FAIL("Schwarz overlap exceeds the slab");
+    SchwarzPre* s = new SchwarzPre();
+    s->sub = sub; s->nd = nd; s->ov = overlap; s->npml_s = npml_sub; s->ext = ext; s->nxl = nxl;
+    s->rin = s->zout = nullptr; s->ev_in = s->ev_out = nullptr;
+    slab->schwarz = s;
+    const size_t ne = sub->n();
+    FDFD_CHECK(cudaMalloc(&s->rin, sizeof(cplx) * ne));
+    FDFD_CHECK(cudaMalloc(&s->zout, sizeof(cplx) * ne));
+    FDFD_CHECK(cudaMemset(s->rin, 0, sizeof(cplx) * ne));          // the PML rows of the right-hand side are never written
+    FDFD_CHECK(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
+    FDFD_CHECK(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
+    return 0;
+}
+void schwarz_destroy(SchwarzPre* s) {
+    if (!s) return;
+    cudaFree(s->rin); cudaFree(s->zout);
+    if (s->ev_in) cudaEventDestroy(s->ev_in);
+    if (s->ev_out) cudaEventDestroy(s->ev_out);
+    delete s;
+}
+static int schwarz_apply(const FdfdOp* op, const cplx* in, cplx* out) {
+    SchwarzPre* s = op->schwarz;
+    cudaStream_t st = op->stream;
+    const size_t ny = (size_t)op->ny, n = (size_t)s->nxl * ny;
+    cplx* owned = s->rin + (size_t)s->ext * ny;
+    FDFD_CHECK(cudaMemcpyAsync(owned, in, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
+    if (s->ov > 0) {
+        const size_t cnt = (size_t)s->ov * ny;
+        cplx *first = owned, *last = owned + (size_t)(s->nxl - s->ov) * ny;
+        cplx *lo = s->rin + (size_t)s->npml_s * ny, *hi = owned + n;
+        if (!op->comm || op->comm->world == 1) {          // one slab: its neighbours are itself
+            FDFD_CHECK(cudaMemcpyAsync(lo, last, sizeof(cplx) * cnt, cudaMemcpyDeviceToDevice, st));
+            FDFD_CHECK(cudaMemcpyAsync(hi, first, sizeof(cplx) * cnt, cudaMemcpyDeviceToDevice, st));
+        } else {
+            const int w = op->comm->world, r = op->comm->rank;
+            if (comm_halo_exchange(op->comm, first, last, lo, hi, (r + w - 1) % w, (r + 1) % w, 2 * cnt, st)) return -1;
+        }
+    }
+    // the substitution runs on the subdomain operator's stream
+    FDFD_CHECK(cudaEventRecord(s->ev_in, st));
+    FDFD_CHECK(cudaStreamWaitEvent(s->sub->stream, s->ev_in, 0));
+    if (nd_solve(s->nd, s->sub, s->rin, s->zout, 1)) return -1;
+    FDFD_CHECK(cudaEventRecord(s->ev_out, s->sub->stream));
+    FDFD_CHECK(cudaStreamWaitEvent(st, s->ev_out, 0));
+    FDFD_CHECK(cudaMemcpyAsync(out, s->zout + (size_t)s->ext * ny, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+static int precond_solve(NdSolver* nd, const FdfdOp* op, const cplx* in, cplx* out) {
+    return nd ? nd_solve(nd, op, in, out, 1) : schwarz_apply(op, in, out);
+}
 static int precond_solve(NdSolver*, const FdfdOp*, const cplx32*, cplx32*) { return 0; }   // rejected at entry
 
 template <class V>
-int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond, const V* d_b, V* d_x, double tol, int maxiter, int fused,
+int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond_nd, const V* d_b, V* d_x, double tol, int maxiter, int fused,
                       int check_every, const cplx* c12, int real_inner, KrylovResult* res) {
     const int RI = (real_inner || c12) ? 1 : 0;   // an R-linear operator needs the real inner product
     const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
-    if (op->halo && (precond || c12)) FDFD_FAIL("slab operators take neither a preconditioner nor an anti-linear term");
-    if (!std::is_same<V, cplx>::value && (precond || c12))
+    if (op->halo && (precond_nd || c12))
+        FDFD_FAIL("slab operators take no whole-grid factors and no anti-linear term (their preconditioner is the attached Schwarz one)");
+    if (!std::is_same<V, cplx>::value && (precond_nd || c12))
         FDFD_FAIL("the complex64 solver takes neither a preconditioner nor an anti-linear term");
+    // right preconditioner: whole-grid factors handed in, or the Schwarz preconditioner attached to a slab operator
+    const bool precond = precond_nd != nullptr || (std::is_same<V, cplx>::value && op->halo && op->schwarz != nullptr);
     FdfdComm* comm = op->comm;
     d_b += pad; d_x += pad;
     cudaStream_t st = op->stream;
@@ -322,11 +402,11 @@ int krylov_bicgstab_t(const FdfdOp* op, NdSolver* precond, const V* d_b, V* d_x,
     if (res->relres <= tol) { res->converged = 1; return 0; }
     for (int it = 1; it <= maxiter; ++it) {
         { bicg_p_kernel<V><<<nblk, 256, 0, st>>>(p, r, v, sc, n); ++g_fdfd_launches; }
-        if (precond && precond_solve(precond, op, p, ph)) return -1;
+        if (precond && precond_solve(precond_nd, op, p, ph)) return -1;
         if (apply_A<V>(op, ph, v, fused, c12)) return -1;
         if (dots<V>(st, r0, v, 1, nullptr, nullptr, 0, n, partial, sc, POST_BICG_ALPHA, 0, 0, RI, comm)) return -1;
         { bicg_s_kernel<V><<<nblk, 256, 0, st>>>(s, r, v, sc, n); ++g_fdfd_launches; }
-        if (precond && precond_solve(precond, op, s, sh)) return -1;
+        if (precond && precond_solve(precond_nd, op, s, sh)) return -1;
         if (apply_A<V>(op, sh, t, fused, c12)) return -1;
         if (dots<V>(st, t, s, 1, t, t, 1, n, partial, sc, POST_BICG_OMEGA, 0, 0, RI, comm)) return -1;
         { bicg_xr_dots_kernel<V><<<RED_BLOCKS, RED_THREADS, 0, st>>>(d_x, r, ph, sh, s, t, r0, sc, n, partial); ++g_fdfd_launches; }

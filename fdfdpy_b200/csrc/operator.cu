@@ -13,11 +13,9 @@ PhaseTiming g_phase_timing;
 // PML: inverse stretch factors for one axis.  Restates create_sfactor's index rules
 // (pml.py:29-40): low side i <= npml, high side i > n - npml, 'f' half-cell, 'b' full-cell.
 // ------------------------------------------------------------------------------------------
-__global__ void pml_axis_kernel(cplx* __restrict__ inv_f, cplx* __restrict__ inv_b, int n, int npml,
-                                double hw, double omega, double L0) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cplx sf = cmake(1.0, 0.0), sb = cmake(1.0, 0.0);
+__device__ __forceinline__ void pml_stretch(int i, int n, int npml, double hw, double omega, double L0, cplx& sf, cplx& sb) {
+    sf = cmake(1.0, 0.0);
+    sb = cmake(1.0, 0.0);
     if (npml >= 1) {
         const double eta0 = sqrt(FDFD_MU0 / FDFD_EPS0);
         double dw = npml * hw;
@@ -36,6 +34,42 @@ __global__ void pml_axis_kernel(cplx* __restrict__ inv_f, cplx* __restrict__ inv
             sf = cmake(1.0, -(sig_max * (tf * tf * tf * tf)) / den);
             sb = cmake(1.0, -(sig_max * (tb * tb * tb * tb)) / den);
         }
+    }
+}
+__global__ void pml_axis_kernel(cplx* __restrict__ inv_f, cplx* __restrict__ inv_b, int n, int npml,
+                                double hw, double omega, double L0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx sf, sb;
+    pml_stretch(i, n, npml, hw, omega, L0, sf, sb);
+    inv_f[i] = crecip(sf);
+    inv_b[i] = crecip(sb);
+}
+
+// Stretch factors of a Schwarz subdomain: local row i is global row (x0e + i) mod gnx and keeps that row's factor; the
+// first and last npml_s rows add an artificial absorber with the reference's own grading (pml.py:7-18: m = 4,
+// ln R = -12) on top of it, so what leaves the overlap region is absorbed instead of wrapping round the local torus.
+__global__ void schwarz_sfactor_kernel(cplx* __restrict__ inv_f, cplx* __restrict__ inv_b, int nxe, int gnx, int x0e,
+                                       int npml_g, int npml_s, double hw, double omega, double L0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nxe) return;
+    const int g = ((x0e + i) % gnx + gnx) % gnx;
+    cplx sf, sb;
+    pml_stretch(g, gnx, npml_g, hw, omega, L0, sf, sb);
+    double df = 0.0, db = 0.0;                       // depth into the artificial layer, in cells
+    if (i < npml_s) {
+        df = npml_s - i - 0.5;
+        db = npml_s - i;
+    } else if (i >= nxe - npml_s) {
+        df = i - (nxe - npml_s) + 0.5;
+        db = i - (nxe - npml_s) + 1.0;
+    }
+    if (db > 0.0) {
+        const double eta0 = sqrt(FDFD_MU0 / FDFD_EPS0);
+        const double dw = npml_s * hw, sig_max = 5.0 * 12.0 / (2 * eta0 * dw), den = omega * FDFD_EPS0 * L0;
+        const double tf = df / npml_s, tb = db / npml_s;
+        sf.y -= sig_max * (tf * tf * tf * tf) / den;
+        sb.y -= sig_max * (tb * tb * tb * tb) / den;
     }
     inv_f[i] = crecip(sf);
     inv_b[i] = crecip(sb);
@@ -126,6 +160,9 @@ stencil_planes_kernel(const cplx* __restrict__ planes, const V* __restrict__ x, 
 // y column and marches ROWS consecutive rows keeping the x-neighbours in registers.
 // ------------------------------------------------------------------------------------------
 int g_fused_rows = 4;          // A/B switch (fdfd_stencil_set_variant): rows marched per thread
+int g_hz_chunk = 0;            // Hz: 0 = marching kernel, rows per CTA chosen from the grid size; 4 ... 128 = that many rows;
+                               // -4 / -8 = the one-shot kernel with 4 / 8 rows per thread (round-2 baseline, kept for A/B runs)
+int g_hz_halo_lanes = 1;       // marching Hz kernel: 30 stored columns per warp + 2 halo lanes (0: edge lanes load their neighbours)
 int g_fused_rows32 = 4;        // complex64 vectors: 4 or 8 rows with two columns per thread (float4); 2 = one column per thread
 
 __device__ __forceinline__ cplx shfl_up_c(cplx v) {
@@ -337,6 +374,162 @@ stencil_fused_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
             cfma(acc, ayp, fy_hi);
             cfma(acc, cneg(aym), fy_lo);
             if (active) vstore(y + voff + (rowo + iy), acc);
+        }
+    }
+}
+
+// Marching variant of the Hz kernel: a CTA walks CHUNK consecutive rows in groups of four and issues the loads of the
+// NEXT group (4 rows of x and eps) before the arithmetic of the current one, so every warp keeps 8 x 16 B of loads in
+// flight under its own ~600-instruction compute phase instead of relying on other resident warps to cover it (the
+// one-shot kernel above: 24 warps/SM, each alternating between a load phase and a long dependent fp64 phase, reached
+// 0.68 of the HBM rate).  The x-face flux and the two boundary rows of a group carry over to the next group in
+// registers, so a chunk re-reads only 2 rows per CHUNK.  The reciprocal uses one cubic correction step (3 DFMA)
+// and the fluxes are subtracted with negated-operand FMAs (no DNEG), 40 fp64 instructions per cell instead of 63.
+__device__ __forceinline__ double fast_rcp64c(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));      // >= 20 good bits
+    const double e = fma(-d, r, 1.0);                           // 1/d = r (1 + e + e^2 + ...)
+    const double t = fma(e, e, e);
+    return fma(r, t, r);                                        // relative error e^3 <= 2^-60
+}
+template <bool AVG> __device__ __forceinline__ void face_weight_c(cplx e_lo, cplx e, cplx& w) {
+    const cplx z = AVG ? make_double2(0.5 * (e_lo.x + e.x), 0.5 * (e_lo.y + e.y)) : e;
+    const double r = fast_rcp64c(fma(z.x, z.x, z.y * z.y));
+    w = make_double2(z.x * r, -z.y * r);
+}
+template <bool AVG> __device__ __forceinline__ void face_weight_c(cplx e_lo, cplx e, double& w) {
+    w = fast_rcp64c(AVG ? fma(0.5, e_lo.x, 0.5 * e.x) : e.x);
+}
+__device__ __forceinline__ void cfms(cplx& a, cplx b, cplx c) {   // a -= b * c
+    a.x = fma(-b.x, c.x, a.x);
+    a.x = fma(b.y, c.y, a.x);
+    a.y = fma(-b.x, c.y, a.y);
+    a.y = fma(-b.y, c.x, a.y);
+}
+__device__ __forceinline__ double shfl_up_w(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ cplx shfl_up_w(cplx v) { return shfl_up_c(v); }
+template <class W> __device__ __forceinline__ W eps_part(cplx e);
+template <> __device__ __forceinline__ double eps_part<double>(cplx e) { return e.x; }
+template <> __device__ __forceinline__ cplx eps_part<cplx>(cplx e) { return e; }
+__device__ __forceinline__ cplx eps_full(double e) { return make_double2(e, 0.0); }
+__device__ __forceinline__ cplx eps_full(cplx e) { return e; }
+
+// HALO: a warp covers 30 columns plus one halo column on each side (lanes 0 and 31 load and compute their lower-face
+// flux but do not store), so there is no divergent edge-lane code: without it EVERY warp executes the two predicated
+// neighbour loads and a third face weight per cell because lanes 0 and 31 exist in every warp.
+template <class V, bool AVG, class W, bool HALO>
+__global__ void __launch_bounds__(128, 4)
+stencil_march_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_nl,
+                        const cplx* __restrict__ axm_t, const cplx* __restrict__ axp_t,
+                        const cplx* __restrict__ aym_t, const cplx* __restrict__ ayp_t,
+                        const V* __restrict__ x, V* __restrict__ y, int nx, int ny, double w2m0, double w2e0,
+                        int row0, int row1, int chunk) {
+    const int ix0 = row0 + blockIdx.y * chunk;
+    const int nrows = min(chunk, row1 - ix0);
+    const int lane = threadIdx.x & 31;
+    const unsigned uny = (unsigned)ny;
+    int iy_raw;
+    bool active;
+    unsigned iy;
+    if (HALO) {
+        iy_raw = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 30 + lane - 1;          // -1 .. : 30 stored columns per warp
+        active = lane >= 1 && lane <= 30 && iy_raw < ny;
+        int c = iy_raw < 0 ? iy_raw + ny : iy_raw;
+        c = c >= ny ? c - ny : c;                                                // the periodic neighbour of column ny - 1
+        iy = (unsigned)min(c, ny - 1);                                           // lanes further out: any valid column
+    } else {
+        iy_raw = blockIdx.x * blockDim.x + threadIdx.x;
+        active = iy_raw < ny;
+        iy = active ? (unsigned)iy_raw : uny - 1u;
+    }
+    const size_t voff = (size_t)blockIdx.z * nx * ny;
+    const V* xv = x + voff;
+    V* yv = y + voff;
+    const unsigned iym = iy == 0 ? uny - 1u : iy - 1u, iyp = iy + 1u == uny ? 0u : iy + 1u;
+    const bool load_dn = !HALO && (lane == 0 || iy == 0), load_up = !HALO && (lane == 31 || iy_raw >= ny - 1);
+    const cplx aym = ldg_c(aym_t + iy), ayp = ldg_c(ayp_t + iy);
+    const int last = ix0 + nrows;                        // the row above the chunk (its lower face belongs to the chunk)
+    auto rowoff = [&](int ix) -> unsigned {              // rows past `last` are never used: clamp, then wrap
+        ix = min(ix, last);
+        if (ix < 0) ix += nx;
+        if (ix >= nx) ix -= nx;
+        return (unsigned)ix * uny;
+    };
+    // window: rows ix0 - 1 .. ix0 + 4 of x and eps (eps keeps only its real part when W = double)
+    cplx xw[6];
+    W ew[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const unsigned o = rowoff(ix0 - 1 + r) + iy;
+        xw[r] = vload(xv + o);
+        ew[r] = eps_part<W>(vload(eps_r + o));
+    }
+    cplx fx0;                                            // flux through the face below the group's first row
+    {
+        W w;
+        face_weight_c<AVG>(eps_full(ew[0]), eps_full(ew[1]), w);
+        fx0 = wmul(w, csub(xw[1], xw[0]));
+    }
+    for (int g = 0; g < nrows; g += 4) {
+        const int ixg = ix0 + g;
+        const bool more = g + 4 < nrows;                 // block-uniform
+        cplx xn[4], en[4];
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const unsigned o = rowoff(ixg + 5 + r) + iy;
+                xn[r] = vload(xv + o);
+                en[r] = vload(eps_r + o);
+            }
+        }
+        cplx fx[5];
+        fx[0] = fx0;
+#pragma unroll
+        for (int r = 1; r <= 4; ++r) {
+            W w;
+            face_weight_c<AVG>(eps_full(ew[r]), eps_full(ew[r + 1]), w);
+            fx[r] = wmul(w, csub(xw[r + 1], xw[r]));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (g + r < nrows) {                         // block-uniform
+                const unsigned rowo = (unsigned)(ixg + r) * uny;
+                const cplx axm = ldg_c(axm_t + ixg + r), axp = ldg_c(axp_t + ixg + r);
+                const cplx xcc = xw[r + 1];
+                const W ec = ew[r + 1];
+                cplx xd = shfl_up_c(xcc);
+                W ed = shfl_up_w(ec);
+                if (!HALO && load_dn) {
+                    xd = vload(xv + (rowo + iym));
+                    ed = eps_part<W>(vload(eps_r + (rowo + iym)));
+                }
+                W wlo;
+                face_weight_c<AVG>(eps_full(ed), eps_full(ec), wlo);
+                const cplx fy_lo = wmul(wlo, csub(xcc, xd));
+                cplx fy_hi = shfl_down_c(fy_lo);
+                if (!HALO && load_up) {
+                    W whi;
+                    face_weight_c<AVG>(eps_full(ec), vload(eps_r + (rowo + iyp)), whi);
+                    fy_hi = wmul(whi, csub(vload(xv + (rowo + iyp)), xcc));
+                }
+                cplx acc = make_double2(w2m0 * xcc.x, w2m0 * xcc.y);
+                if (eps_nl) cfma(acc, cscale(vload(eps_nl + (rowo + iy)), w2e0), xcc);
+                cfma(acc, axp, fx[r + 1]);
+                cfms(acc, axm, fx[r]);
+                cfma(acc, ayp, fy_hi);
+                cfms(acc, aym, fy_lo);
+                if (active) vstore(yv + (rowo + iy), acc);
+            }
+        }
+        fx0 = fx[4];
+        xw[0] = xw[4];
+        xw[1] = xw[5];
+        ew[0] = ew[4];
+        ew[1] = ew[5];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            xw[r + 2] = xn[r];
+            ew[r + 2] = eps_part<W>(en[r]);
         }
     }
 }
@@ -569,6 +762,29 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
     return op_create_impl(out, nxl + 2, ny, omega, dl, npml_x, npml_y, pol, L0, 1, gnx, x0, comm);
 }
 
+int op_create_schwarz_sub(FdfdOp** out, const FdfdOp* slab, int overlap, int npml_sub) {
+    if (!slab->halo) FDFD_FAIL("the Schwarz subdomain belongs to a slab operator");
+    const int nxl = slab->nx - 2, ext = overlap + npml_sub;
+    if (overlap < 0 || npml_sub < 1) FDFD_FAIL("Schwarz subdomain: overlap >= 0 and npml_sub >= 1");
+    if (overlap > nxl) FDFD_FAIL("Schwarz overlap (%d rows) exceeds the slab (%d rows)", overlap, nxl);
+    FdfdOp* op = nullptr;
+    // created like a whole-grid operator (own stream, y factors, tables), then the x factors are replaced
+    if (op_create_impl(&op, nxl + 2 * ext, slab->ny, slab->omega, slab->dl, 0, slab->npml_y, slab->pol, slab->L0, 0,
+                       nxl + 2 * ext, 0, nullptr))
+        return -1;
+    AsmParams p = make_params(op);
+    const int nx = op->nx;
+    { schwarz_sfactor_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->isxf, op->isxb, nx, slab->gnx, slab->x0 - ext,
+                                                                        slab->npml_x, npml_sub, p.dx, op->omega, op->L0); ++g_fdfd_launches; }
+    const double med = op->pol == 0 ? p.m0 : p.e0;
+    { pml_products_kernel<<<ceil_div(nx, 128), 128, 0, op->stream>>>(op->ax, op->ax + nx, op->isxf, op->isxb, nx, 1.0 / (med * p.dx * p.dx)); ++g_fdfd_launches; }
+    { narrow_table_kernel<<<ceil_div(2 * nx, 128), 128, 0, op->stream>>>(op->ax, op->ax32, 2 * nx); ++g_fdfd_launches; }
+    FDFD_CHECK(cudaGetLastError());
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    *out = op;
+    return 0;
+}
+
 int op_halo_exchange(const FdfdOp* op, void* xv, size_t elem, cudaStream_t st) {
     if (!op->halo) return 0;
     const size_t row = elem * op->ny;                 // bytes per row (elem = 16: complex128, 8: complex64)
@@ -586,6 +802,7 @@ int op_halo_exchange(const FdfdOp* op, void* xv, size_t elem, cudaStream_t st) {
 
 void op_destroy(FdfdOp* op) {
     if (!op) return;
+    if (op->schwarz) schwarz_destroy(op->schwarz);
     cudaFree(op->isxf); cudaFree(op->isxb); cudaFree(op->isyf); cudaFree(op->isyb);
     cudaFree(op->eps_r); cudaFree(op->eps_nl); cudaFree(op->planes); cudaFree(op->d_eps_flag);
     if (op->io_buf) cudaFree(op->io_buf);
@@ -746,7 +963,7 @@ int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
     AsmParams p = make_params(op);
     if (op->pol != 0 && op->n() >= (1ull << 31)) return op_apply_planes_t<V>(op, d_x, d_y, nvec);   // 32-bit offsets
     if (op->pol != 0) {
-        const int rows = g_fused_rows == 8 ? 8 : 4;
+        const int rows = g_hz_chunk == -8 ? 8 : 4;
         int real_eps = 0;
         if (op_eps_is_real(op, &real_eps)) return -1;
         void (*kern)(const V*, const V*, const cplx*, const cplx*, const cplx*, const cplx*, const V*, V*, int, int, double,
@@ -757,6 +974,34 @@ int op_apply_fused_t(const FdfdOp* op, const V* d_x, V* d_y, int nvec) {
         } else {
             if (op->averaging) kern = rows == 8 ? stencil_fused_hz_kernel<8, V, true, cplx> : stencil_fused_hz_kernel<4, V, true, cplx>;
             else kern = rows == 8 ? stencil_fused_hz_kernel<8, V, false, cplx> : stencil_fused_hz_kernel<4, V, false, cplx>;
+        }
+        if (g_hz_chunk >= 0) {
+            // marching kernel.  Rows per CTA: long chunks amortise the two re-read rows and keep the prefetch pipeline
+            // full, but the grid must still fill the machine (4 CTAs of 128 threads per SM x 148 SMs) about twice over
+            const bool halo = g_hz_halo_lanes != 0;
+            int chunk = g_hz_chunk;
+            if (chunk == 0) {
+                const long long cols = ceil_div(op->ny, halo ? 120 : 128), nrow = op->nx - 2 * op->halo;
+                chunk = 4;
+                for (int c = 64; c >= 8; c >>= 1)
+                    if (cols * ((nrow + c - 1) / c) * nvec >= 2 * 4 * 148) { chunk = c; break; }
+            }
+            void (*mk)(const V*, const V*, const cplx*, const cplx*, const cplx*, const cplx*, const V*, V*, int, int,
+                       double, double, int, int, int);
+            if (real_eps) mk = op->averaging ? (halo ? stencil_march_hz_kernel<V, true, double, true> : stencil_march_hz_kernel<V, true, double, false>)
+                                             : (halo ? stencil_march_hz_kernel<V, false, double, true> : stencil_march_hz_kernel<V, false, double, false>);
+            else mk = op->averaging ? (halo ? stencil_march_hz_kernel<V, true, cplx, true> : stencil_march_hz_kernel<V, true, cplx, false>)
+                                    : (halo ? stencil_march_hz_kernel<V, false, cplx, true> : stencil_march_hz_kernel<V, false, cplx, false>);
+            for (int i = 0; i < plan.nranges; ++i) {
+                if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));
+                dim3 grid(ceil_div(op->ny, halo ? 120 : 128), ceil_div(plan.r1[i] - plan.r0[i], chunk), nvec);
+                mk<<<grid, 128, 0, op->stream>>>(er, enl, op->ax, op->ax + op->nx, op->ay, op->ay + op->ny, d_x, d_y, op->nx,
+                                                 op->ny, p.omega * p.omega * p.m0, p.omega * p.omega * p.e0, plan.r0[i],
+                                                 plan.r1[i], chunk);
+                ++g_fdfd_launches;
+            }
+            FDFD_CHECK(cudaGetLastError());
+            return 0;
         }
         for (int i = 0; i < plan.nranges; ++i) {
             if (plan.wait_halo_before[i]) FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_halo, 0));

@@ -38,6 +38,7 @@ struct FdfdOp {
     cudaStream_t comm_stream;        // halo exchange runs here, overlapped with the interior rows
     cudaEvent_t ev_in, ev_halo;
     FdfdComm* comm;     // not owned; null with halo = 1 means a single slab wrapping onto itself
+    struct SchwarzPre* schwarz;   // slab operators: restricted additive Schwarz preconditioner (krylov.cu), owned
     size_t n() const { return (size_t)nx * ny; }
 };
 
@@ -46,7 +47,12 @@ int op_create(FdfdOp** out, int nx, int ny, double omega, double dl, int npml_x,
 // slab operator: rows [x0, x0 + nxl) of a gnx x ny grid
 int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nxl, double omega, double dl,
                    int npml_x, int npml_y, int pol, double L0);
+// Subdomain operator of a slab for the Schwarz preconditioner: a torus of nxl + 2 (overlap + npml_sub) rows whose
+// x stretch factors are the global ones of rows x0 - ext ... (periodic) plus an artificial PML of npml_sub cells at
+// both ends.  Assemble it with the permittivity of those rows.
+int op_create_schwarz_sub(FdfdOp** out, const FdfdOp* slab, int overlap, int npml_sub);
 void op_destroy(FdfdOp* op);
+void schwarz_destroy(struct SchwarzPre* s);     // krylov.cu
 // fills the two halo rows of an extended-layout vector from the neighbouring slabs
 int op_halo_exchange(const FdfdOp* op, void* d_x_ext, size_t elem_bytes, cudaStream_t st);
 // eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes

@@ -5,7 +5,9 @@ The reference is single-process; this is the multi-GPU extension of its hot path
 
 * ``DirectSolver(op, comm=...)``   one grid's elimination tree split over the ranks (subtree per
   GPU, binary reduction tree above; ndplan.shard_plan);
-* ``SlabOperator`` / ``slab_krylov``  the matrix-free stencil on slabs with halo exchange.
+* ``SlabOperator``  the matrix-free stencil and the Krylov solvers on slabs with halo exchange;
+  ``SlabOperator.setup_schwarz`` adds the restricted additive Schwarz preconditioner (per-slab direct
+  factors with PML transmission) that turns the slab path into a solver for large grids.
 
 The 128-byte NCCL id has to reach every rank once; ``Communicator.from_torch()`` uses an
 initialised ``torch.distributed`` process group for that (torch is plumbing here, nothing else),
@@ -143,6 +145,8 @@ class SlabOperator:
         self.x0, self.x1 = rows if rows is not None else slab_rows(self.gnx, world, rank)
         self.nxl = self.x1 - self.x0
         self.pol = pol
+        self.omega, self.dl, self.L0, self.npml = float(omega), float(dl), float(L0), [int(NPML[0]), int(NPML[1])]
+        self._schwarz = None
         self.h = C.c_void_p()
         check(self.lib.fdfd_slab_op_create(C.byref(self.h), comm.h if comm is not None else None, self.gnx, self.ny,
                                            self.x0, self.nxl, float(omega), float(dl), int(NPML[0]), int(NPML[1]),
@@ -181,7 +185,36 @@ class SlabOperator:
                                               None, 0, C.byref(it), C.byref(rr), C.byref(conv)))
         return xe[1:-1].copy(), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
 
+    # ---- restricted additive Schwarz preconditioner: what makes the slab path a solver at scale
+    def setup_schwarz(self, eps_r, overlap=4, npml_sub=12, averaging=True):
+        """Build, assemble and factorise this rank's subdomain (the slab + ``overlap`` rows of each neighbour +
+        ``npml_sub`` rows of artificial PML on both sides, as a local torus) and attach it as the right
+        preconditioner of ``krylov(method='bicgstab')``.  ``eps_r`` is the whole permittivity array again.
+        Local work only (no collective).  Returns the subdomain's DirectSolver (factor bytes, timings)."""
+        from .core import DirectSolver, MaxwellOperator
+        self.drop_schwarz()
+        ext = int(overlap) + int(npml_sub)
+        h = C.c_void_p()
+        check(self.lib.fdfd_schwarz_sub_create(C.byref(h), self.h, int(overlap), int(npml_sub)))
+        sub = MaxwellOperator._adopt(h, self.nxl + 2 * ext, self.ny, self.omega, self.dl, [0, self.npml[1]], self.pol, self.L0)
+        rows = np.arange(self.x0 - ext, self.x1 + ext) % self.gnx
+        sub.assemble(np.asarray(eps_r)[rows], averaging=averaging)
+        d = DirectSolver(sub)
+        d.factor()
+        check(self.lib.fdfd_slab_set_schwarz(self.h, sub.h, d.h, int(overlap), int(npml_sub)))
+        self._schwarz = (sub, d)
+        return d
+
+    def drop_schwarz(self):
+        if getattr(self, "_schwarz", None) is not None:
+            check(self.lib.fdfd_slab_set_schwarz(self.h, None, None, 0, 0))
+            self._schwarz = None
+
     def __del__(self):
+        try:
+            self.drop_schwarz()
+        except Exception:
+            pass
         try:
             if getattr(self, "h", None) and self.h.value:
                 self.lib.fdfd_op_destroy(self.h)

@@ -172,13 +172,25 @@ void fdfd_comm_abort(fdfd_comm* c);
 /* slab operator: rows [x0, x0 + nxl) of a gnx x ny grid (rows = the slow index of the reference's
  * C-ordered fields; a split along the other axis is the same call on the transposed problem).
  * Every array of a slab operator -- eps_r for fdfd_op_assemble_*, x / y / b of fdfd_op_apply_* and
- * fdfd_krylov_solve_* (precond and c12 must be NULL) -- has the EXTENDED layout (nxl + 2) x ny:
+ * fdfd_krylov_solve_* (precond and c12 must be NULL; see fdfd_slab_set_schwarz) -- has the EXTENDED layout (nxl + 2) x ny:
  * row 0 and row nxl + 1 mirror the neighbouring slabs' boundary rows (periodic in the rank index).
  * eps_r must be given with its halo rows filled; vector halos are exchanged by the library (NCCL
  * send/recv on the operator's stream) before every stencil application, and inner products are
  * summed over ranks on the device.  comm == NULL: a single slab that wraps onto itself.          */
 int fdfd_slab_op_create(fdfd_op** out, fdfd_comm* comm, int gnx, int ny, int x0, int nxl, double omega,
                         double dl, int npml_x, int npml_y, int pol, double L0);
+/* Restricted additive Schwarz preconditioner for the Krylov solve on slabs (what makes the slab path a SOLVER for
+ * grids whose whole-grid factors do not fit: the reference call it serves is still Simulation.solve_fields,
+ * simulation.py:113-178 -> linalg.py:123 solver_direct).  One subdomain per rank: the slab's rows plus `overlap`
+ * rows of each neighbour plus `npml_sub` rows of artificial PML on both sides, a torus of nxl + 2 (overlap + npml_sub)
+ * rows.  fdfd_schwarz_sub_create builds that subdomain's operator (an ordinary fdfd_op: assemble it with the
+ * permittivity of global rows x0 - overlap - npml_sub ... periodic, factorise it with fdfd_direct_*);
+ * fdfd_slab_set_schwarz attaches operator + factors to the slab operator (NULL, NULL detaches), after which
+ * fdfd_krylov_solve_* with method 0 on the slab operator is right-preconditioned by it.  Per application: one
+ * exchange of `overlap` rows with each neighbour and one substitution pass with the local factors.  The caller keeps
+ * ownership of `sub` and `sub_factors` and must keep them alive while attached. */
+int fdfd_schwarz_sub_create(fdfd_op** out, fdfd_op* slab, int overlap, int npml_sub);
+int fdfd_slab_set_schwarz(fdfd_op* slab, fdfd_op* sub, fdfd_direct* sub_factors, int overlap, int npml_sub);
 
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).
@@ -236,8 +248,13 @@ int fdfd_mode_solve_host(const double* eps_line, int n, double omega, double dl,
 int fdfd_zgemm_batched_host(const double* A, const double* B, double* C, int M, int N, int K, int batch,
                             int mode, int transb, int lower);
 
-/* rows each thread of the fused Ez stencil marches (2, 4, 8; defaults 4 for complex128, 8 for complex64) */
+/* rows each thread of the fused Ez stencil marches (2, 4, 8; default 4) */
 int fdfd_stencil_set_variant(int rows_per_thread, int complex64);
+/* fused Hz stencil, A/B switch: chunk_rows 0 (default) = marching kernel with the rows per CTA chosen from the grid size,
+ * 4 ... 1024 (multiple of 4) = that many rows per CTA, -4 / -8 = the one-shot kernel with 4 / 8 rows per thread;
+ * halo_lanes 1 (default) = 30 stored columns per warp plus one halo lane on each side, 0 = 32 columns per warp with the
+ * edge lanes loading their neighbours */
+int fdfd_stencil_set_hz_variant(int chunk_rows, int halo_lanes);
 /* kernel selection for A/B measurements (bit mask): bit 0 = tiled kernel only (default: persistent kernel for large
  * problems); bit 1 = textbook 4M complex products (default: 3M Karatsuba products, 6 tensor flops per complex MAC) */
 int fdfd_zgemm_set_variant(int v);

@@ -169,3 +169,38 @@ def test_slab_operator_in_process_ranks(world, pol):
         full = np.concatenate([r[method][0] for r in res])
         assert all(r[method][1]["relres"] < 1e-10 for r in res), [r[method][1] for r in res]
         assert relerr(full, sol) < 1e-8, method
+
+
+@pytest.mark.parametrize("world,pol,overlap", [(1, "Ez", 4), (2, "Ez", 4), (4, "Ez", 4), (4, "Hz", 3), (3, "Ez", 2)])
+def test_slab_schwarz_preconditioner(world, pol, overlap):
+    """Restricted additive Schwarz on the slabs (per-slab direct factors, artificial PML at the cut faces): the
+    preconditioned distributed BiCGSTAB reaches north_star's bars (fields 1e-8 against the oracle's direct solve,
+    residual 1e-10) on a strongly scattering grid in a small fraction of the unpreconditioned iterations."""
+    from fdfdpy_b200.distributed import SlabOperator, run_ranks
+    rng = np.random.default_rng(11)
+    nx, ny = 232, 96
+    eps = 1 + 11 * (rng.random((nx // 8, ny // 8)) > 0.6).repeat(8, 0).repeat(8, 1)
+    npml = [10, 10]
+    dl = 0.04
+    A = orc.construct_A(OMEGA, eps, dl, npml, pol, 1e-6)
+    b = np.zeros((nx, ny), dtype=complex)
+    b[nx // 2, ny // 2] = 1j * OMEGA
+    b[nx // 5, ny // 3] = -0.5j * OMEGA
+    sol = orc.sparse_solve(A, b).reshape(nx, ny)
+
+    def rank_body(comm):
+        slab = SlabOperator(OMEGA, eps, dl, npml, pol, 1e-6, comm=comm if world > 1 else None)
+        sl = slice(slab.x0, slab.x1)
+        d = slab.setup_schwarz(eps, overlap=overlap, npml_sub=10)
+        xs, info = slab.krylov(b[sl], method="bicgstab", tol=1e-11, maxiter=400, check_every=2)
+        slab.drop_schwarz()
+        _, plain = slab.krylov(b[sl], method="bicgstab", tol=1e-11, maxiter=400, check_every=50)
+        return xs, info, plain, d.stats()["factor_bytes"]
+
+    res = run_ranks(world, rank_body)
+    full = np.concatenate([r[0] for r in res])
+    info = res[0][1]
+    assert all(r[1]["relres"] < 1e-10 and r[1]["converged"] for r in res), [r[1] for r in res]
+    assert relerr(full, sol) < 1e-8
+    assert info["iters"] <= 40 * max(world, 2), info      # measured: 22 / 39 / 86 iterations for 2 / 4 / 3 (overlap 2) slabs
+    assert not res[0][2]["converged"] or res[0][2]["iters"] > 4 * info["iters"], (info, res[0][2])

@@ -25,8 +25,13 @@ for n in sizes:
     _lib.check(lib.fdfd_malloc(C.byref(d_x), 16.0 * n * n))
     _lib.check(lib.fdfd_malloc(C.byref(d_y), 16.0 * n * n))
     _lib.check(lib.fdfd_memcpy_h2d(d_x, _lib.ptr(x), 16.0 * n * n))
-    for rows in ((2, 4, 8) if POL == "Ez" else (4, 8)):
-        _lib.check(lib.fdfd_stencil_set_variant(rows, 0))
+    # Hz: (-4, -8) = one-shot kernel, 0 = marching kernel with automatic rows per CTA, > 0 = rows per CTA
+    variants = [(2, 1), (4, 1), (8, 1)] if POL == "Ez" else [(-4, 1), (0, 1), (4, 1), (8, 1), (16, 1), (32, 1), (64, 1), (32, 0)]
+    for rows, halo in variants:
+        if POL == "Ez":
+            _lib.check(lib.fdfd_stencil_set_variant(rows, 0))
+        else:
+            _lib.check(lib.fdfd_stencil_set_hz_variant(rows, halo))
         err = np.linalg.norm(op.dot(x, fused=True) - ref) / np.linalg.norm(ref)
         for _ in range(5):
             _lib.check(lib.fdfd_op_apply_dev(op.h, d_x, d_y, 1, 1))
@@ -36,9 +41,10 @@ for n in sizes:
         for _ in range(reps):
             _lib.check(lib.fdfd_op_apply_dev(op.h, d_x, d_y, 1, 1))
         _lib.check(lib.fdfd_timer_stop(op.h, C.byref(ms)))
-        print(f"n={n} {POL} rows={rows}: {ms.value / reps * 1e3:.1f} us  {48.0 * n * n * reps / ms.value / 1e6:.0f} GB/s  "
+        print(f"n={n} {POL} rows={rows} halo={halo}: {ms.value / reps * 1e3:.1f} us  {48.0 * n * n * reps / ms.value / 1e6:.0f} GB/s  "
               f"rel diff vs planes kernel {err:.2e}", flush=True)
     _lib.check(lib.fdfd_stencil_set_variant(4, 0))
+    _lib.check(lib.fdfd_stencil_set_hz_variant(0, 1))
     if POL != "Ez" or os.environ.get("STENCIL_ONLY"):
         lib.fdfd_free(d_x)
         lib.fdfd_free(d_y)
