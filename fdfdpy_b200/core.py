@@ -20,8 +20,12 @@ def get_plan(nx, ny):
     splitting of ndplan.build_plan for A/B measurements."""
     import os
     sm, sp = os.environ.get("FDFD_SPLIT_MIN"), os.environ.get("FDFD_SPLIT_PARTS")
-    key = (int(nx), int(ny), sm, sp)
+    ms = os.environ.get("FDFD_SPLIT_MAX_STEPS")
+    key = (int(nx), int(ny), sm, sp, ms)
     if key not in _plan_cache:
+        if ms:
+            from . import ndplan
+            ndplan.SPLIT_MAX_STEPS = int(ms)
         _plan_cache[key] = build_plan(int(nx), int(ny), split_min=int(sm) if sm else None,
                                       split_parts=int(sp) if sp else None)
     return _plan_cache[key]
@@ -152,10 +156,11 @@ class MaxwellOperator:
         return self.direct().solve(b, max_refine=max_refine, tol=tol)
 
     def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10,
-               precondition=False, c12=None, real_inner=False):
+               precondition=False, c12=None, real_inner=False, restart=50):
         """Krylov solve of A x (+ c12 conj(x)) = b.  ``precondition=True`` uses whatever factorisation
         the direct-solver handle currently caches (it may belong to a nearby operator).
-        A complex64 ``b`` selects complex64 vector storage (fp64 arithmetic and scalars)."""
+        A complex64 ``b`` selects complex64 vector storage (fp64 arithmetic and scalars).
+        ``method='gmres'``: right-preconditioned GMRES(``restart``), one preconditioner application per iteration."""
         if np.asarray(b).dtype == np.complex64:
             if precondition or c12 is not None:
                 raise ValueError("the complex64 solver takes neither a preconditioner nor an anti-linear term")
@@ -176,8 +181,9 @@ class MaxwellOperator:
                 d.factor()
             pre = d.h
         c12a = None if c12 is None else as_c128(c12)
-        check(self.lib.fdfd_krylov_solve_host(self.h, pre, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1}[method],
-                                              float(tol), int(maxiter), int(fused), int(check_every), ptr(c12a),
+        check(self.lib.fdfd_krylov_solve_host(self.h, pre, ptr(b), ptr(x), {"bicgstab": 0, "cocg": 1, "gmres": 2}[method],
+                                              float(tol), int(maxiter), int(fused),
+                                              int(restart if method == "gmres" else check_every), ptr(c12a),
                                               int(bool(real_inner)), C.byref(it), C.byref(rr), C.byref(conv)))
         return x.reshape(b.shape), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
 

@@ -1,4 +1,5 @@
 // extern "C" surface of libfdfd_b200.so; declarations and reference citations in include/fdfd_b200.h
+#include <mutex>
 #include <vector>
 #include "krylov.cuh"
 #include "mode.cuh"
@@ -18,7 +19,23 @@ struct DevBuf {
 
 ZgemmTiming g_zgemm_timing;
 int g_zgemm_variant = 0;
-int g_zgemm_max_ctas = 148;
+thread_local int g_zgemm_max_ctas = 148;          // per host thread: in-process ranks factorise concurrently
+thread_local ZgemmHelper* g_zgemm_helper = nullptr;
+unsigned* zgemm_tile_counter(cudaStream_t stream) {
+    // ring of counters per device: launches in flight at the same time (main / side streams, several solver handles,
+    // in-process ranks on several threads) never share one
+    constexpr int RING = 4096, MAXDEV = 16;
+    static std::mutex mu;
+    static unsigned* pool[MAXDEV] = {nullptr};
+    static int next[MAXDEV] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;   // falls back to static hand-out
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pool[dev] && cudaMalloc(&pool[dev], sizeof(unsigned) * RING) != cudaSuccess) { pool[dev] = nullptr; return nullptr; }
+    unsigned* c = pool[dev] + (next[dev]++ % RING);
+    cudaMemsetAsync(c, 0, sizeof(unsigned), stream);
+    return c;
+}
 
 // register-resident DMMA loop: the practical FP64 tensor-pipe ceiling at the clocks the board runs at
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
@@ -717,6 +734,9 @@ int fdfd_krylov_solve_dev(fdfd_op* op, fdfd_direct* precond, const void* d_b, vo
     else if (method == 1) {
         if (precond || d_c12) FDFD_FAIL("COCG takes neither a preconditioner nor an anti-linear term");
         rc = krylov_cocg(op, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, fused, check_every, &r);
+    } else if (method == 2) {
+        if (d_c12) FDFD_FAIL("GMRES takes no anti-linear term");
+        rc = krylov_gmres(op, precond, (const cplx*)d_b, (cplx*)d_x, tol, maxiter, check_every, fused, &r);
     } else FDFD_FAIL("unknown Krylov method %d", method);
     if (rc) return -1;
     FDFD_CHECK(cudaStreamSynchronize(op->stream));

@@ -793,6 +793,8 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
         FDFD_CHECK(cudaStreamCreateWithPriority(&s->la_stream, cudaStreamNonBlocking, hi));
         FDFD_CHECK(cudaEventCreateWithFlags(&s->la_ready, cudaEventDisableTiming));
         FDFD_CHECK(cudaEventCreateWithFlags(&s->la_done, cudaEventDisableTiming));
+        FDFD_CHECK(cudaEventCreateWithFlags(&s->zg_fork, cudaEventDisableTiming));
+        FDFD_CHECK(cudaEventCreateWithFlags(&s->zg_join, cudaEventDisableTiming));
     }
     FDFD_CHECK(cudaMalloc(&s->d_info, sizeof(int)));
     *out = s;
@@ -885,10 +887,13 @@ void nd_destroy(NdSolver* s) {
     cudaStreamDestroy(s->la_stream);
     cudaEventDestroy(s->la_ready);
     cudaEventDestroy(s->la_done);
+    cudaEventDestroy(s->zg_fork);
+    cudaEventDestroy(s->zg_join);
     delete s;
 }
 
 int g_lookahead_enabled = 1;       // A/B switch (FDFD_LOOKAHEAD=0): pivot-block look-ahead on chain levels
+int g_lookahead_helper = 1;        // A/B switch (FDFD_LA_HELPER=0): the SMs reserved for the look-ahead chain rejoin the Schur update
 int g_small_front_enabled = 1;     // A/B switch (fdfd_direct_set_small_fronts): 0 = generic path on every level
 
 static int chunks_for(long long per_front_elems, long long nb) {
@@ -1038,6 +1043,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
     {
         const char* e = getenv("FDFD_LOOKAHEAD");
         g_lookahead_enabled = !(e && e[0] == '0');
+        e = getenv("FDFD_LA_HELPER");
+        g_lookahead_helper = !(e && e[0] == '0');
     }
     FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
     // the previous level's Schur blocks: batch base, first ring entry at (prev_k, prev_k), leading dimension
@@ -1246,7 +1253,12 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
                 c.lower = 1;
                 c.B = g.B + (size_t)k1 * ld; c.C = g.C + (size_t)k1 * ld + k1;
                 c.M = mmax - k1; c.N = mmax - k1;
+                // the SMs left to the look-ahead chain join this update once that chain is through (helper launch on
+                // the look-ahead stream, tiles handed out dynamically)
+                ZgemmHelper helper = {s->la_stream, reserve, s->zg_fork, s->zg_join};
+                if (g_lookahead_helper) g_zgemm_helper = &helper;
                 if (!rc) rc = zgemm_batched(c, st);
+                g_zgemm_helper = nullptr;
                 g_zgemm_max_ctas = 148;
                 if (rc) return -1;
             } else {

@@ -89,6 +89,7 @@ struct NdSolver {
     // look-ahead on chain levels: the next pivot block is inverted on a side stream under the current Schur update
     cudaStream_t la_stream;
     cudaEvent_t la_ready, la_done;
+    cudaEvent_t zg_fork, zg_join;     // helper launch of a Schur update on the look-ahead stream (zgemm.cuh)
     // distributed fronts of the shared levels, in elimination order (front j + 1 is the parent of front j)
     std::vector<NdDistFront*> dist;
     cplx *dist_send, *dist_recv, *dist_panel;

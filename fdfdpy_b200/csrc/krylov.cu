@@ -12,6 +12,7 @@
 //   two reduction stages, halo rows are exchanged inside the stencil application.
 #include <algorithm>
 #include <type_traits>
+#include <vector>
 #include "krylov.cuh"
 
 #define RED_BLOCKS 1184   // 148 SMs x 8
@@ -517,6 +518,218 @@ int krylov_cocg_t(const FdfdOp* op, const V* d_b, V* d_x, double tol, int maxite
     double rn = sqrt(h.x);
     if (host_scalar(st, sc + S_TT, &h)) return -1;
     res->relres = rn / sqrt(h.x);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Restarted GMRES, right-preconditioned (whole-grid factors of a nearby operator, or the Schwarz preconditioner of a
+// slab operator): ONE preconditioner application per iteration against BiCGSTAB's two, a monotone residual and no
+// breakdowns -- on the Schwarz-preconditioned slab systems BiCGSTAB needs 2-5x the applications and occasionally
+// breaks down (tests/schwarz_model.py).  Arnoldi with classical Gram-Schmidt applied twice (CGS2): the j + 1 inner
+// products of a pass come from one kernel (four basis vectors per CTA pass, so w is re-read j / 4 times, not j),
+// are summed over the ranks with one all-reduce and cross to the host once (the Hessenberg least-squares problem is
+// updated there with Givens rotations: O(j) flops).  Basis vectors keep the slab's extended layout.
+// ------------------------------------------------------------------------------------------
+#define GM_NV 4
+__global__ void __launch_bounds__(RED_THREADS)
+gmres_dots_kernel(const cplx* __restrict__ V, size_t vs, const cplx* __restrict__ w, int k, size_t n,
+                  cplx* __restrict__ partial, int kpad) {
+    // partial[blk][i] = sum over the CTA's elements of conj(V_i) w, i in [4 y, 4 y + 4); slot k (y == 0) = |w|^2
+    const int i0 = blockIdx.y * GM_NV;
+    cplx acc[GM_NV], ww = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < GM_NV; ++q) acc[q] = make_double2(0.0, 0.0);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const cplx wv = w[e];
+        if (blockIdx.y == 0) ww.x += wv.x * wv.x + wv.y * wv.y;
+#pragma unroll
+        for (int q = 0; q < GM_NV; ++q)
+            if (i0 + q < k) dot_acc(acc[q], __ldg(V + (size_t)(i0 + q) * vs + e), wv, true);
+    }
+    block_reduce2(acc[0], acc[1]);
+    __syncthreads();
+    block_reduce2(acc[2], acc[3]);
+    __syncthreads();
+    cplx dummy = make_double2(0.0, 0.0);
+    if (blockIdx.y == 0) block_reduce2(ww, dummy);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < GM_NV; ++q)
+            if (i0 + q < k) partial[(size_t)blockIdx.x * kpad + i0 + q] = acc[q];
+        if (blockIdx.y == 0) partial[(size_t)blockIdx.x * kpad + k] = ww;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS)
+gmres_dots_final_kernel(const cplx* __restrict__ partial, int nblk, int kpad, cplx* __restrict__ out) {
+    cplx a = make_double2(0.0, 0.0), dummy = make_double2(0.0, 0.0);
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) a = cadd(a, partial[(size_t)b * kpad + blockIdx.x]);
+    block_reduce2(a, dummy);
+    if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+// w = beta w - sum_i c[i] V_i   (beta = 1: Gram-Schmidt update; beta = 0 with negated c: a combination of the basis)
+__global__ void __launch_bounds__(256)
+gmres_axpy_kernel(cplx* __restrict__ w, const cplx* __restrict__ V, size_t vs, const cplx* __restrict__ c, int k,
+                  size_t n, double beta) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    cplx acc = beta != 0.0 ? w[e] : make_double2(0.0, 0.0);
+    for (int i = 0; i < k; ++i) {
+        const cplx h = __ldg(c + i), v = __ldg(V + (size_t)i * vs + e);
+        acc.x -= h.x * v.x - h.y * v.y;
+        acc.y -= h.x * v.y + h.y * v.x;
+    }
+    w[e] = acc;
+}
+__global__ void __launch_bounds__(256) gmres_scale_kernel(cplx* __restrict__ w, size_t n, double s) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) w[e] = make_double2(w[e].x * s, w[e].y * s);
+}
+__global__ void __launch_bounds__(256) gmres_add_kernel(cplx* __restrict__ x, const cplx* __restrict__ z, size_t n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) x[e] = cadd(x[e], z[e]);
+}
+
+int krylov_gmres(const FdfdOp* op, NdSolver* precond_nd, const cplx* d_b, cplx* d_x, double tol, int maxiter, int restart,
+                 int fused, KrylovResult* res) {
+    if (op->halo && precond_nd) FDFD_FAIL("slab operators take no whole-grid factors (their preconditioner is the attached Schwarz one)");
+    const bool precond = precond_nd != nullptr || (op->halo && op->schwarz != nullptr);
+    const size_t n = kn(op), pad = kpad(op), vs = n + 2 * pad;
+    FdfdComm* comm = op->comm;
+    const bool dist = comm && comm->world > 1;
+    cudaStream_t st = op->stream;
+    if (restart < 2) restart = 50;
+    if (restart > maxiter) restart = maxiter > 1 ? maxiter : 2;
+    const int m = restart, kpad_ = m + 2;
+    constexpr int GM_BLOCKS = 592;
+    d_b += pad; d_x += pad;
+    Scratch wsV, wsS;
+    FDFD_CHECK(cudaMalloc(&wsV.base, sizeof(cplx) * vs * (size_t)(m + 3)));
+    FDFD_CHECK(cudaMalloc(&wsS.base, sizeof(cplx) * ((size_t)GM_BLOCKS * kpad_ + 2 * kpad_ + 2 * RED_BLOCKS + S_COUNT)));
+    if (pad) FDFD_CHECK(cudaMemsetAsync(wsV.base, 0, sizeof(cplx) * vs * (size_t)(m + 3), st));
+    cplx* V = static_cast<cplx*>(wsV.base) + pad;           // basis vector i at V + i vs
+    cplx* z = V + (size_t)(m + 1) * vs;                      // M^-1 v_j
+    cplx* u = z + vs;                                        // residual / basis combination
+    cplx* gpart = static_cast<cplx*>(wsS.base);
+    cplx* dh = gpart + (size_t)GM_BLOCKS * kpad_;            // device copy of one pass's inner products
+    cplx* dc = dh + kpad_;                                   // device copy of the coefficients of an update
+    cplx* partial = dc + kpad_;
+    cplx* sc = partial + 2 * RED_BLOCKS;
+    const unsigned nblk = (unsigned)ceil_div(n, 256);
+    std::vector<cplx> hh(kpad_), h1(kpad_);
+    std::vector<cplx> H((size_t)(m + 1) * m), cs(m), g(m + 1), y(m);
+    std::vector<double> cc(m);
+    cplx hs;
+    if (dots<cplx>(st, d_b, d_b, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 0, comm)) return -1;
+    if (host_scalar(st, sc + S_RR, &hs)) return -1;
+    const double bnorm = sqrt(hs.x);
+    res->iters = 0; res->converged = 0; res->relres = 1.0;
+    if (bnorm == 0.0) {
+        FDFD_CHECK(cudaMemsetAsync(d_x, 0, sizeof(cplx) * n, st));
+        res->converged = 1; res->relres = 0.0;
+        return 0;
+    }
+    // one Gram-Schmidt pass: hh[0..k) = V^H w, hh[k] = |w|^2 (before the update), then w -= V hh
+    auto gs_pass = [&](cplx* w, int k) -> int {
+        dim3 grid(GM_BLOCKS, (unsigned)ceil_div(k, GM_NV));
+        gmres_dots_kernel<<<grid, RED_THREADS, 0, st>>>(V, vs, w, k, n, gpart, kpad_);
+        gmres_dots_final_kernel<<<k + 1, RED_THREADS, 0, st>>>(gpart, GM_BLOCKS, kpad_, dh);
+        g_fdfd_launches += 2;
+        if (dist && comm_allreduce_sum(comm, dh, 2 * (size_t)(k + 1), st)) return -1;
+        FDFD_CHECK(cudaMemcpyAsync(hh.data(), dh, sizeof(cplx) * (k + 1), cudaMemcpyDeviceToHost, st));
+        gmres_axpy_kernel<<<nblk, 256, 0, st>>>(w, V, vs, dh, k, n, 1.0);
+        ++g_fdfd_launches;
+        FDFD_CHECK(cudaStreamSynchronize(st));
+        FDFD_CHECK(cudaGetLastError());
+        return 0;
+    };
+    int total = 0;
+    while (total < maxiter) {
+        // r = b - A x ; v_0 = r / |r|
+        if (residual_A<cplx>(op, d_b, d_x, V, nullptr)) return -1;
+        if (dots<cplx>(st, V, V, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 0, comm)) return -1;
+        if (host_scalar(st, sc + S_RR, &hs)) return -1;
+        const double beta = sqrt(hs.x);
+        res->relres = beta / bnorm;
+        if (!(res->relres == res->relres)) FDFD_FAIL("GMRES: the residual is not finite");
+        if (res->relres <= tol) { res->converged = 1; break; }
+        gmres_scale_kernel<<<nblk, 256, 0, st>>>(V, n, 1.0 / beta);
+        ++g_fdfd_launches;
+        for (auto& e : g) e = make_double2(0.0, 0.0);
+        g[0] = make_double2(beta, 0.0);
+        int j = 0;
+        bool done = false;
+        for (; j < m && total < maxiter && !done; ++j, ++total) {
+            cplx* vj = V + (size_t)j * vs;
+            cplx* w = V + (size_t)(j + 1) * vs;
+            if (precond) {
+                if (precond_solve(precond_nd, op, vj, z)) return -1;
+                if (apply_A<cplx>(op, z, w, fused, nullptr)) return -1;
+            } else if (apply_A<cplx>(op, vj, w, fused, nullptr)) return -1;
+            const int k = j + 1;
+            if (gs_pass(w, k)) return -1;
+            for (int i = 0; i < k; ++i) h1[i] = hh[i];
+            if (gs_pass(w, k)) return -1;                 // second pass: hh = corrections, hh[k] = |w'|^2 before it
+            double corr = 0.0;
+            for (int i = 0; i < k; ++i) {
+                corr += hh[i].x * hh[i].x + hh[i].y * hh[i].y;
+                H[(size_t)i * m + j] = cadd(h1[i], hh[i]);
+            }
+            const double hn2 = hh[k].x - corr;
+            const double hnext = hn2 > 0.0 ? sqrt(hn2) : 0.0;
+            H[(size_t)k * m + j] = make_double2(hnext, 0.0);
+            // Givens rotations of the new column, then the one that annihilates its sub-diagonal entry
+            for (int i = 0; i < j; ++i) {
+                const cplx a = H[(size_t)i * m + j], b2 = H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = cadd(cscale(a, cc[i]), cmul(cs[i], b2));
+                H[(size_t)(i + 1) * m + j] = csub(cscale(b2, cc[i]), cmul(cconj(cs[i]), a));
+            }
+            {
+                const cplx a = H[(size_t)j * m + j];
+                const double an = sqrt(a.x * a.x + a.y * a.y), t = sqrt(an * an + hnext * hnext);
+                if (t == 0.0) FDFD_FAIL("GMRES: breakdown with a zero Hessenberg column");
+                cc[j] = an / t;
+                // G = [c s; -conj(s) c] with c = |a| / t, s = (a / |a|) hnext / t maps (a, hnext) to (a t / |a|, 0); a = 0: swap
+                cs[j] = an > 0.0 ? cscale(a, hnext / (an * t)) : make_double2(1.0, 0.0);
+                H[(size_t)j * m + j] = an > 0.0 ? cscale(a, t / an) : make_double2(t, 0.0);
+                H[(size_t)(j + 1) * m + j] = make_double2(0.0, 0.0);
+                const cplx gj = g[j];
+                g[j] = cscale(gj, cc[j]);
+                g[j + 1] = cneg(cmul(cconj(cs[j]), gj));
+            }
+            res->iters = total + 1;
+            res->relres = sqrt(g[j + 1].x * g[j + 1].x + g[j + 1].y * g[j + 1].y) / bnorm;
+            if (res->relres <= tol || hnext == 0.0) done = true;
+            else {
+                gmres_scale_kernel<<<nblk, 256, 0, st>>>(w, n, 1.0 / hnext);
+                ++g_fdfd_launches;
+            }
+        }
+        // y = R^-1 g (host), x += M^-1 (V y)
+        for (int i = j - 1; i >= 0; --i) {
+            cplx t = g[i];
+            for (int l = i + 1; l < j; ++l) t = csub(t, cmul(H[(size_t)i * m + l], y[l]));
+            y[i] = cdiv(t, H[(size_t)i * m + i]);
+        }
+        for (int i = 0; i < j; ++i) hh[i] = cneg(y[i]);
+        FDFD_CHECK(cudaMemcpyAsync(dc, hh.data(), sizeof(cplx) * j, cudaMemcpyHostToDevice, st));
+        gmres_axpy_kernel<<<nblk, 256, 0, st>>>(u, V, vs, dc, j, n, 0.0);
+        ++g_fdfd_launches;
+        if (precond) {
+            if (precond_solve(precond_nd, op, u, z)) return -1;
+            gmres_add_kernel<<<nblk, 256, 0, st>>>(d_x, z, n);
+        } else {
+            gmres_add_kernel<<<nblk, 256, 0, st>>>(d_x, u, n);
+        }
+        ++g_fdfd_launches;
+        FDFD_CHECK(cudaStreamSynchronize(st));          // hh is reused by the next cycle
+        if (done) break;
+    }
+    // the TRUE residual of the returned iterate
+    if (residual_A<cplx>(op, d_b, d_x, u, nullptr)) return -1;
+    if (dots<cplx>(st, u, u, 1, nullptr, nullptr, 0, n, partial, sc, POST_STORE, S_RR, -1, 0, comm)) return -1;
+    if (host_scalar(st, sc + S_RR, &hs)) return -1;
+    res->relres = sqrt(hs.x) / bnorm;
+    res->converged = res->relres <= tol * 10 ? 1 : 0;
     return 0;
 }
 

@@ -20,6 +20,9 @@ int krylov_bicgstab(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* 
                     int fused, int check_every, const cplx* c12, int real_inner, KrylovResult* res);
 int krylov_cocg(const FdfdOp* op, const cplx* d_b, cplx* d_x, double tol, int maxiter, int fused, int check_every,
                 KrylovResult* res);
+// restarted GMRES, right-preconditioned by `precond` (whole-grid factors) or by a slab operator's Schwarz preconditioner
+int krylov_gmres(const FdfdOp* op, NdSolver* precond, const cplx* d_b, cplx* d_x, double tol, int maxiter, int restart,
+                 int fused, KrylovResult* res);
 // restricted additive Schwarz preconditioner of a slab operator (sub == nullptr detaches); see krylov.cu
 int schwarz_attach(FdfdOp* slab, FdfdOp* sub, NdSolver* nd, int overlap, int npml_sub);
 int refine_solve(NdSolver* nd, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs, int max_refine, double tol,

@@ -229,7 +229,8 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned tile, unsigned tiles_p
 
 template <int STAGES, bool TB, bool M3, int BK>
 __global__ void __launch_bounds__(256, 1)
-zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles) {
+zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned tiles_per_batch, long long total_tiles,
+                             unsigned* __restrict__ counter) {
     constexpr int WN = 2, BM = 64, BN = 64;
     constexpr int RPP = 256 / BK, NPASS = 64 / RPP;      // rows one pass of the 256 threads covers / passes per tile
     constexpr int LDA = BK + 4, LDB = TB ? BK + 4 : BN + 2;
@@ -243,7 +244,25 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
     const int gq = lane >> 2, tq = lane & 3;
     const int KT = (g.K + BK - 1) / BK;
     const unsigned ntiles = (unsigned)total_tiles;
-    if (blockIdx.x >= ntiles) return;
+    // Tile hand-out.  counter == nullptr: static, CTA b walks tiles b, b + gridDim.x, ...  Otherwise DYNAMIC: tiles come
+    // from a global atomic counter, so CTAs that start late (an SM still busy with look-ahead work of another stream)
+    // or that belong to a second, helper launch on another stream sharing the same counter simply take fewer tiles.
+    // Thread 0 draws tile q + 2 of this CTA when the load cursor moves on to tile q; the draw reaches the other
+    // threads through shared memory behind the k-loop's barrier (every move of the load cursor is at least one
+    // barrier after the previous one), eight slots so that the compute cursor (<= 3 tiles behind) still finds its own.
+    __shared__ unsigned s_tiles[8];
+    const bool dyn = counter != nullptr;
+    if (!dyn && blockIdx.x >= ntiles) return;
+    if (dyn) {
+        if (tid == 0) {
+            s_tiles[0] = atomicAdd(counter, 1u);
+            s_tiles[1] = atomicAdd(counter, 1u);
+            s_tiles[2] = atomicAdd(counter, 1u);
+        }
+        __syncthreads();
+        if (s_tiles[0] >= ntiles) return;
+    }
+    unsigned q_ld = 0;                                    // sequence number of the tile the load cursor is on
 
     // load cursor (runs STAGES-1 k-tiles ahead of the compute cursor).  Each thread copies four 16-byte
     // chunks of the A tile and four of the B tile per k-tile; their global pointers only advance by a
@@ -253,7 +272,7 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
     constexpr int BPASS = TB ? NPASS : BK / 4;
     const long long a_step = (long long)RPP * g.lda, b_step = TB ? (long long)RPP * g.ldb : 4LL * g.ldb;
     const long long b_adv = TB ? (long long)BK : (long long)BK * g.ldb;
-    unsigned ld_tile = blockIdx.x;
+    unsigned ld_tile = dyn ? s_tiles[0] : blockIdx.x;
     int ld_kt = 0, ld_stage = 0;
     unsigned amask = 0, bmask = 0;
     const cplx *pa = g.A, *pb = g.B;
@@ -295,7 +314,13 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
         ld_stage = ld_stage + 1 == STAGES ? 0 : ld_stage + 1;
         if (++ld_kt == KT) {
             ld_kt = 0;
-            ld_tile += gridDim.x;
+            if (dyn) {
+                ++q_ld;
+                ld_tile = s_tiles[q_ld & 7u];
+                if (tid == 0) s_tiles[(q_ld + 2u) & 7u] = atomicAdd(counter, 1u);
+            } else {
+                ld_tile += gridDim.x;
+            }
             if (ld_tile < ntiles) decode_load();
             else amask = bmask = 0;         // past the end: the copies degenerate to zero fills of a dead stage
         }
@@ -324,7 +349,8 @@ zgemm_dmma_persistent_kernel(GemmBatch g, int tiles_m, int tiles_n, unsigned til
             for (int nt = 0; nt < 4; ++nt) f.bs_[nt] = f.b[nt].x + f.b[nt].y;
         }
     };
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned q_c = 0;
+    for (unsigned tile = dyn ? s_tiles[0] : blockIdx.x; tile < ntiles; tile = dyn ? s_tiles[++q_c & 7u] : tile + gridDim.x) {
         const TileCoord tc = decode_tile(tile, tiles_per_batch, (unsigned)tiles_n, g.lower);
         cplx* __restrict__ C = g.C + (long long)tc.b * g.sC;
         const int m_base = (int)tc.tm * BM, n_base = (int)tc.tn * BN;
@@ -439,10 +465,21 @@ struct ZgemmTiming {
     std::vector<int> big;             // 1: 64x64-tile kernel, 0: 32x32-tile kernel
 };
 extern ZgemmTiming g_zgemm_timing;
-extern int g_zgemm_max_ctas;  // CTAs of the persistent kernel (148 = one per SM; fewer leaves SMs to a side stream)
+extern thread_local int g_zgemm_max_ctas;  // CTAs of the persistent kernel (148 = one per SM; fewer leaves SMs to a side stream)
+// Helper launch: while set, a persistent GEMM issued on stream S is also launched with `ctas` CTAs on `stream` (ordered
+// after whatever that stream already holds, i.e. the look-ahead work the main launch left SMs free for); both launches
+// draw their tiles from one atomic counter, and S waits for the helper before it goes on.
+struct ZgemmHelper {
+    cudaStream_t stream;
+    int ctas;
+    cudaEvent_t ev_fork, ev_join;
+};
+extern thread_local ZgemmHelper* g_zgemm_helper;
+unsigned* zgemm_tile_counter(cudaStream_t stream);     // a zeroed (stream-ordered) counter out of a device ring; capi.cu
 extern int g_zgemm_variant;   // bit 0: always the tiled kernel (default: persistent kernel for large problems);
                               // bit 1: textbook 4M complex products (default: 3M); bit 2: persistent kernel with
-                              // k-tiles of 16 x 4 stages (default: 32 x 3 stages)
+                              // k-tiles of 16 x 4 stages (default: 32 x 3 stages); bit 3: static tile hand-out
+                              // (default: dynamic, from an atomic counter)
 
 template <bool TB, bool M3>
 static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
@@ -473,7 +510,19 @@ static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
                                      (int)sm);
                 attr_p = true;
             }
-            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+            unsigned* cnt = (g_zgemm_variant & 8) ? nullptr : zgemm_tile_counter(stream);
+            ZgemmHelper* h = cnt ? g_zgemm_helper : nullptr;
+            if (h) {
+                cudaEventRecord(h->ev_fork, stream);                     // the counter is zero from here on
+                cudaStreamWaitEvent(h->stream, h->ev_fork, 0);
+            }
+            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks, cnt);
+            if (h) {
+                zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<h->ctas, 256, sm, h->stream>>>(g, tm, tn, (unsigned)per_batch, blocks, cnt);
+                ++g_fdfd_launches;
+                cudaEventRecord(h->ev_join, h->stream);
+                cudaStreamWaitEvent(stream, h->ev_join, 0);
+            }
         } else {
             constexpr int ST = 4, BK = 16;
             constexpr size_t sm = zgemm_smem_bytes<4, 2, ST, TB, BK>();
@@ -483,7 +532,7 @@ static inline int zgemm_launch(const GemmBatch& g, cudaStream_t stream) {
                                      (int)sm);
                 attr_p = true;
             }
-            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks);
+            zgemm_dmma_persistent_kernel<ST, TB, M3, BK><<<g_zgemm_max_ctas, 256, sm, stream>>>(g, tm, tn, (unsigned)per_batch, blocks, nullptr);
         }
     } else {
         constexpr size_t sm = zgemm_smem_bytes<4, 2, 3, TB>();

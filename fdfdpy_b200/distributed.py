@@ -175,13 +175,17 @@ class SlabOperator:
         check(self.lib.fdfd_op_apply_host(self.h, _lib.ptr(xe), _lib.ptr(ye), 1, int(fused)))
         return ye[1:-1]
 
-    def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10):
-        """Distributed BiCGSTAB / COCG on the slabs (collective)."""
+    def krylov(self, b, method="bicgstab", x0=None, tol=1e-10, maxiter=20000, fused=True, check_every=10, restart=50):
+        """Distributed BiCGSTAB / COCG / GMRES(restart) on the slabs (collective).  With ``setup_schwarz`` done,
+        BiCGSTAB and GMRES are right-preconditioned by the Schwarz preconditioner; GMRES is the robust choice there
+        (one preconditioner application per iteration, no breakdowns)."""
         be = self.to_ext(b)
         xe = self.to_ext(np.zeros_like(be[1:-1]) if x0 is None else x0)
         it, rr, conv = C.c_int(0), C.c_double(0), C.c_int(0)
-        check(self.lib.fdfd_krylov_solve_host(self.h, None, _lib.ptr(be), _lib.ptr(xe), {"bicgstab": 0, "cocg": 1}[method],
-                                              float(tol), int(maxiter), int(bool(fused)), int(check_every),
+        check(self.lib.fdfd_krylov_solve_host(self.h, None, _lib.ptr(be), _lib.ptr(xe),
+                                              {"bicgstab": 0, "cocg": 1, "gmres": 2}[method],
+                                              float(tol), int(maxiter), int(bool(fused)),
+                                              int(restart if method == "gmres" else check_every),
                                               None, 0, C.byref(it), C.byref(rr), C.byref(conv)))
         return xe[1:-1].copy(), dict(iters=it.value, relres=rr.value, converged=bool(conv.value))
 

@@ -23,7 +23,8 @@ import numpy as np
 
 WMIN = 3          # smallest leaf interval (cells); leaves are WMIN..2*WMIN-1 cells wide
 SPLIT_MIN = 1000  # separators with at least this many nodes are eliminated in several steps
-SPLIT_PARTS = -512   # > 0: that many steps; < 0: pieces of about -SPLIT_PARTS nodes (at most 8 steps)
+SPLIT_PARTS = -512   # > 0: that many steps; < 0: pieces of about -SPLIT_PARTS nodes (at most SPLIT_MAX_STEPS steps)
+SPLIT_MAX_STEPS = 8
 
 
 def _parts(k, p):
@@ -212,7 +213,7 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
             fronts.append((elim, pring, p1, p2))
             new_rings[(pw, ph)] = pring
         kfull = max(len(f[0]) for f in fronts)
-        want = split_parts if split_parts > 0 else max(1, min(8, int(round(kfull / float(-split_parts)))))
+        want = split_parts if split_parts > 0 else max(1, min(SPLIT_MAX_STEPS, int(round(kfull / float(-split_parts)))))
         nparts = want if (want > 1 and kfull >= split_min and min(len(f[0]) for f in fronts) >= want) else 1
         # pieces are identical for every shape class except the last one, which absorbs the (<= 2 node) size
         # differences: the intermediate chain levels then have no padded pivots and are factorised in place

@@ -194,8 +194,9 @@ int fdfd_slab_set_schwarz(fdfd_op* slab, fdfd_op* sub, fdfd_direct* sub_factors,
 
 /* ---- Krylov solvers on the matrix-free stencil (no reference counterpart: the reference is
  * direct-only; these serve perturbed operators and the slab-decomposed multi-GPU path).
- * method: 0 = BiCGSTAB, 1 = COCG on the symmetrised operator.  precond may be NULL; when given
- * (BiCGSTAB only) its cached factorisation is the right preconditioner -- it may belong to a
+ * method: 0 = BiCGSTAB, 1 = COCG on the symmetrised operator, 2 = restarted GMRES (check_every is
+ * then the restart length, <= 1 means 50; no c12).  precond may be NULL; when given (BiCGSTAB and
+ * GMRES) its cached factorisation is the right preconditioner -- it may belong to a
  * nearby operator (previous Born iterate, linear part of the Newton Jacobian).  c12 (may be NULL)
  * adds the anti-linear term  c12 .* conj(x)  of the Newton Jacobian (nonlinear_solvers.py:134-135;
  * replaces linalg.py:152 solver_complex2real): the system is then only R-linear and is solved with

@@ -240,3 +240,22 @@ def test_slab_rows_cover_the_grid():
             assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
             sizes = [b - a for a, b in rows]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_schwarz_model_converges_and_matches_direct():
+    """The restricted additive Schwarz preconditioner of the slab path, as a numpy model (tests/schwarz_model.py: the
+    subdomains, overlap, artificial PML and stretch factors of csrc/operator.cu / csrc/krylov.cu): preconditioned
+    BiCGSTAB reaches the oracle's direct solution on a waveguide device in a few iterations per slab."""
+    from oracle import fdfd_oracle as orc
+    from tests import schwarz_model as sm
+    omega, dl, L0, npml = 2 * np.pi * 200e12, 0.02, 1e-6, [10, 10]
+    nx, ny = 192, 96
+    eps = sm.device_eps(nx, ny)
+    b = np.zeros((nx, ny), complex)
+    b[nx // 5, ny // 2] = 1j * omega
+    x, its, rr, A = sm.solve(omega, eps, dl, npml, L0, b, slabs=3, overlap=4, npml_s=10, tol=1e-11)
+    A0 = orc.construct_A(omega, eps, dl, npml, "Ez", L0)
+    assert abs(A - A0).max() <= 1e-12 * abs(A0).max()          # the model's global operator IS the oracle's
+    ref = orc.sparse_solve(A0, b).reshape(nx, ny)
+    assert rr < 1e-10 and its <= 30, (its, rr)
+    assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-8

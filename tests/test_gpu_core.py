@@ -276,6 +276,20 @@ def test_krylov_small(core):
     ref2 = orc.sparse_solve(A2, b).reshape(nx, ny)
     assert info["iters"] <= 10, info
     assert relerr(x, ref2) < 1e-9
+    # restarted GMRES: unpreconditioned with a restart long enough to be full GMRES on this 1440-unknown grid (Ez and
+    # Hz), with a short restart (several cycles), and right-preconditioned by the stale factors
+    for pol in ("Ez", "Hz"):
+        opg = op if pol == "Ez" else core.MaxwellOperator(OMEGA, eps, 0.05, npml, "Hz", 1e-6)
+        refg = ref if pol == "Ez" else orc.sparse_solve(orc.construct_A(OMEGA, eps, 0.05, npml, "Hz", 1e-6), b).reshape(nx, ny)
+        x, info = opg.krylov(b, method="gmres", tol=1e-12, maxiter=1500, restart=700)
+        assert info["relres"] < 1e-10 and info["iters"] <= 1440, info
+        assert relerr(x, refg) < 1e-8, pol
+    x, info = op.krylov(b, method="gmres", tol=1e-11, maxiter=20000, restart=150)
+    assert info["relres"] < 1e-10 and info["iters"] > 150, info       # went through restarts
+    assert relerr(x, ref) < 1e-8
+    x, info = op2.krylov(b, method="gmres", tol=1e-12, maxiter=50, restart=20, precondition=True)
+    assert info["iters"] <= 10 and info["relres"] < 1e-11, info
+    assert relerr(x, ref2) < 1e-9
 
 
 def test_krylov_preconditioned_512(core):
@@ -299,6 +313,9 @@ def test_krylov_preconditioned_512(core):
     assert info["relres"] < 1e-10 and info["iters"] <= 40, info
     ref = orc.sparse_solve(orc.construct_A(OMEGA, eps2, 0.02, npml, "Ez", 1e-6), b).reshape(n, n)
     assert relerr(x, ref) < 1e-8
+    xg, infog = op.krylov(b, method="gmres", tol=1e-12, maxiter=60, restart=30, precondition=True, fused=True)
+    assert infog["relres"] < 1e-10 and infog["iters"] <= 2 * info["iters"], (infog, info)
+    assert relerr(xg, ref) < 1e-8
 
 
 def test_residual_guard(core):

@@ -193,9 +193,10 @@ def test_slab_schwarz_preconditioner(world, pol, overlap):
         sl = slice(slab.x0, slab.x1)
         d = slab.setup_schwarz(eps, overlap=overlap, npml_sub=10)
         xs, info = slab.krylov(b[sl], method="bicgstab", tol=1e-11, maxiter=400, check_every=2)
+        xg, infog = slab.krylov(b[sl], method="gmres", tol=1e-11, maxiter=400, restart=60)
         slab.drop_schwarz()
         _, plain = slab.krylov(b[sl], method="bicgstab", tol=1e-11, maxiter=400, check_every=50)
-        return xs, info, plain, d.stats()["factor_bytes"]
+        return xs, info, plain, d.stats()["factor_bytes"], xg, infog
 
     res = run_ranks(world, rank_body)
     full = np.concatenate([r[0] for r in res])
@@ -204,3 +205,8 @@ def test_slab_schwarz_preconditioner(world, pol, overlap):
     assert relerr(full, sol) < 1e-8
     assert info["iters"] <= 40 * max(world, 2), info      # measured: 22 / 39 / 86 iterations for 2 / 4 / 3 (overlap 2) slabs
     assert not res[0][2]["converged"] or res[0][2]["iters"] > 4 * info["iters"], (info, res[0][2])
+    # GMRES on the same preconditioner: one application per iteration, so at most BiCGSTAB's application count
+    infog = res[0][5]
+    assert all(r[5]["relres"] < 1e-10 and r[5]["converged"] for r in res), [r[5] for r in res]
+    assert relerr(np.concatenate([r[4] for r in res]), sol) < 1e-8
+    assert infog["iters"] <= 2 * info["iters"], (infog, info)

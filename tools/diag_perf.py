@@ -11,6 +11,9 @@ OMEGA = 2 * np.pi * 200e12
 sizes = [int(a) for a in sys.argv[1:]] or [512, 1024]
 import os
 tile = int(os.environ.get("FDFD_TILE", "64"))
+if os.environ.get("ZGEMM_VARIANT"):
+    from fdfdpy_b200 import _lib as _l
+    _l.check(_l.load().fdfd_zgemm_set_variant(int(os.environ["ZGEMM_VARIANT"])))
 for n in sizes:
     rng = np.random.default_rng(0)
     eps = 1 + 11 * (rng.random((n, n)) > 0.5)

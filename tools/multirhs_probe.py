@@ -10,15 +10,18 @@ import bench
 from fdfdpy_b200 import _lib, core
 
 lib = _lib.load()
-n, nrhs = 2048, int(sys.argv[1]) if len(sys.argv) > 1 else 16
-op = core.MaxwellOperator(bench.OMEGA0, bench.synthetic_eps(n), bench.DL, bench.NPML, "Hz", bench.L0)
+nrhs = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+nx, ny = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (2048, 2048)
+pol = sys.argv[4] if len(sys.argv) > 4 else "Hz"
+n = max(nx, ny)
+op = core.MaxwellOperator(bench.OMEGA0, bench.synthetic_eps(n)[:nx, :ny], bench.DL, bench.NPML, pol, bench.L0)
 d = core.DirectSolver(op)
 d.factor()
 rng = np.random.default_rng(0)
-b = np.zeros((nrhs, n, n), dtype=np.complex128)
+b = np.zeros((nrhs, nx, ny), dtype=np.complex128)
 for j in range(nrhs):
-    b[j, rng.integers(n // 4, 3 * n // 4), rng.integers(n // 4, 3 * n // 4)] = 1j * bench.OMEGA0
-nbytes = 16.0 * n * n * nrhs
+    b[j, rng.integers(nx // 4, 3 * nx // 4), rng.integers(ny // 4, 3 * ny // 4)] = 1j * bench.OMEGA0
+nbytes = 16.0 * nx * ny * nrhs
 d_b, d_x = C.c_void_p(), C.c_void_p()
 _lib.check(lib.fdfd_malloc(C.byref(d_b), nbytes))
 _lib.check(lib.fdfd_malloc(C.byref(d_x), nbytes))
@@ -35,7 +38,7 @@ for refine in (-1, 3):
         ph = np.zeros(13)
         lib.fdfd_phase_timing_read(_lib.ptr(ph))
         lib.fdfd_phase_timing(0)
-    print(f"nrhs={nrhs} max_refine={refine}: {ms.value:.1f} ms  relres {rr.value:.1e} steps {st.value}  phases: " +
+    print(f"{nx}x{ny} {pol} factor {d.stats()['factor_bytes'] / 1e9:.2f} GB nrhs={nrhs} max_refine={refine}: {ms.value:.1f} ms  relres {rr.value:.1e} steps {st.value}  phases: " +
           " ".join(f"{k}={v:.1f}" for k, v in zip(names, ph) if v > 0), flush=True)
 nl = len(d.levels)
 lib.fdfd_phase_timing(1)
