@@ -927,6 +927,159 @@ static int launch_transpose(const cplx* src, long long s_stride, int s_ld, cplx*
     return 0;
 }
 
+// ---- block Gauss-Jordan inversion -----------------------------------------------------------
+// The recursive scheme above is all large-K GEMMs but a long serial chain of tiny launches (64 for a 512 block:
+// ~1.4 ms, which at the top of the tree -- and on every step of a distributed front -- sits on the critical path).
+// Block Gauss-Jordan with 64-wide pivot tiles needs TWO launches per pivot tile: the register-resident tile inverse
+// P = M_pp^-1 (in-tile pivoting, as before) and one update kernel over all 64 x 64 tiles, out of place (src -> dst,
+// ping-pong, so no tile is read after it was overwritten):
+//     dst_pp = P        dst_pj = P src_pj        dst_ip = -src_ip P        dst_ij = src_ij - src_ip (P src_pj)
+// n^3 complex MACs instead of n^3 / 2 (the symmetry is not used), which is nothing next to the latency it removes:
+// the two 64^3 products of a tile run on the tensor pipe (DMMA, 3M) out of shared memory.
+__device__ __forceinline__ void gj_load_tile(cplx* dst, int ld, const cplx* src, int n, int r0, int c0, int tid) {
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        dst[r * ld + c] = (r0 + r < n && c0 + c < n) ? src[(size_t)(r0 + r) * n + c0 + c] : make_double2(0.0, 0.0);
+    }
+}
+// acc = A (64 x 64, row-major, lda) * B (64 x 64, row-major, ldb); warp (wm, wn) owns rows 16 wm.., columns 32 wn..
+__device__ __forceinline__ void gj_tile_mm(const cplx* As, int lda, const cplx* Bs, int ldb, int wm, int wn, int gq, int tq,
+                                           cplx (&out)[2][4][2]) {
+    double cr[2][4][2], ci[2][4][2], t3[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < 64; kk += 4) {
+        cplx a[2], b[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) a[mt] = As[(wm * 16 + mt * 8 + gq) * lda + kk + tq];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(kk + tq) * ldb + wn * 32 + nt * 8 + gq];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                dmma884(cr[mt][nt][0], cr[mt][nt][1], a[mt].x, b[nt].x);
+                dmma884(ci[mt][nt][0], ci[mt][nt][1], a[mt].y, b[nt].y);
+                dmma884(t3[mt][nt][0], t3[mt][nt][1], a[mt].x + a[mt].y, b[nt].x + b[nt].y);
+            }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                out[mt][nt][e] = make_double2(cr[mt][nt][e] - ci[mt][nt][e], t3[mt][nt][e] - cr[mt][nt][e] - ci[mt][nt][e]);
+}
+#define GJ_LDA 68
+#define GJ_LDB 66
+__global__ void __launch_bounds__(256)
+gj_update_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst, const cplx* __restrict__ Pinv, int n, int p, int tw) {
+    extern __shared__ __align__(16) unsigned char gj_smem[];
+    cplx* Ps = reinterpret_cast<cplx*>(gj_smem);        // P, A-operand layout (also read as a B operand)
+    cplx* Ys = Ps + 64 * GJ_LDA;                        // src_ip, A operand
+    cplx* Xs = Ys + 64 * GJ_LDA;                        // src_pj, then R = P src_pj, B operand
+    const int ti = blockIdx.y, tj = blockIdx.x, tid = threadIdx.x;
+    const long long b = blockIdx.z;
+    const cplx* S = src + b * (long long)n * n;
+    cplx* D = dst + b * (long long)n * n;
+    const cplx* P = Pinv + b * 4096;
+    const int warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1, gq = lane >> 2, tq = lane & 3;
+    const int r0 = ti * 64, c0 = tj * 64, p0 = p * 64;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        Ps[r * GJ_LDA + c] = (r < tw && c < tw) ? P[e] : make_double2(0.0, 0.0);
+    }
+    if (ti == p && tj == p) {                            // the pivot tile itself: dst = P
+        __syncthreads();
+        for (int e = tid; e < 64 * 64; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            if (r < tw && c < tw) D[(size_t)(p0 + r) * n + p0 + c] = Ps[r * GJ_LDA + c];
+        }
+        return;
+    }
+    if (tj != p) gj_load_tile(Xs, GJ_LDB, S, n, p0, c0, tid);
+    if (ti != p) gj_load_tile(Ys, GJ_LDA, S, n, r0, p0, tid);
+    __syncthreads();
+    cplx acc[2][4][2];
+    if (tj != p) {
+        gj_tile_mm(Ps, GJ_LDA, Xs, GJ_LDB, wm, wn, gq, tq, acc);            // R = P src_pj
+        if (ti != p) {
+            __syncthreads();                                               // every warp is done reading src_pj
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        Xs[(wm * 16 + mt * 8 + gq) * GJ_LDB + wn * 32 + nt * 8 + 2 * tq + e] = acc[mt][nt][e];
+            __syncthreads();
+            gj_tile_mm(Ys, GJ_LDA, Xs, GJ_LDB, wm, wn, gq, tq, acc);        // src_ip R
+        }
+    } else {
+        gj_tile_mm(Ys, GJ_LDA, Ps, GJ_LDA, wm, wn, gq, tq, acc);            // src_ip P
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int row = r0 + wm * 16 + mt * 8 + gq;
+        if (row >= n) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = c0 + wn * 32 + nt * 8 + 2 * tq + e;
+                if (col >= n) continue;
+                cplx v = acc[mt][nt][e];
+                if (ti == p) { /* row tile: R itself */ }
+                else if (tj == p) v = make_double2(-v.x, -v.y);
+                else {
+                    const cplx o = S[(size_t)row * n + col];
+                    v = make_double2(o.x - v.x, o.y - v.y);
+                }
+                D[(size_t)row * n + col] = v;
+            }
+    }
+}
+static size_t gj_ws_need(int n) { return n <= 64 ? 0 : (size_t)n * n + 4096; }
+int g_block_gj = 1;                // A/B switch (FDFD_BLOCK_GJ=0): block Gauss-Jordan (default) or the recursive inversion
+int g_block_gj_max_tiles = 256;    // ... used while one step's grid (fronts x tiles) stays within a few waves of CTAs: it trades
+                                   // flops (2x, in latency-bound 64^3 products, one CTA per SM) for a short launch chain, which
+                                   // pays at the top of the tree and on distributed fronts, not on levels of many fronts
+
+// E (packed [nb][n][n], full storage) <- E^-1 in place; ws holds nb (n^2 + 4096) entries
+static int gj_invert_batch(NdSolver* s, cplx* E, int n, long long nb, cplx* ws, cudaStream_t st) {
+    PhaseScope ph(PH_PIVOT, st);
+    if (nb > 65535) FDFD_FAIL("block inversion batch too large");
+    const int nt = (n + 63) / 64;
+    cplx* W = ws;
+    cplx* Pscr = ws + (size_t)nb * n * n;
+    constexpr size_t sm = sizeof(cplx) * (2 * 64 * GJ_LDA + 64 * GJ_LDB);
+    static bool attr = false;
+    if (!attr) {
+        FDFD_CHECK(cudaFuncSetAttribute(gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr = true;
+    }
+    cplx *src = E, *dst = W;
+    if (nt & 1) {                                      // an odd number of ping-pong steps must START in the workspace
+        FDFD_CHECK(cudaMemcpyAsync(W, E, sizeof(cplx) * (size_t)nb * n * n, cudaMemcpyDeviceToDevice, st));
+        src = W; dst = E;
+    }
+    for (int p = 0; p < nt; ++p) {
+        const int tw = std::min(64, n - 64 * p);
+        launch_tile_inverse(src + (size_t)p * 64 * (n + 1), (long long)n * n, n, tw, Pscr, 4096, 64, s->d_info, 0, nb, st);
+        dim3 grid(nt, nt, (unsigned)nb);
+        gj_update_kernel<<<grid, 256, sm, st>>>(src, dst, Pscr, n, p, tw);
+        ++g_fdfd_launches;
+        std::swap(src, dst);
+    }
+    FDFD_CHECK(cudaGetLastError());
+    s->factor_flops += 8.0 * (double)nb * (double)n * n * n;
+    return 0;
+}
+
 static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, long long nb, cplx* ws,
                             cudaStream_t st) {
     if (n <= 64) {
@@ -935,6 +1088,11 @@ static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, l
         FDFD_CHECK(cudaGetLastError());
         return 0;
     }
+    // (not on the look-ahead stream: there the inversion shares the machine with a persistent GEMM that leaves it 4-16
+    // SMs, and a step's 64-256 one-per-SM CTAs would crawl through them; measured: 5.8 -> 7.5 ms on the level it delays)
+    if (g_block_gj && ld == n && sE == (long long)n * n && st != s->la_stream &&
+        nb * (long long)((n + 63) / 64) * ((n + 63) / 64) <= g_block_gj_max_tiles)
+        return gj_invert_batch(s, E, n, nb, ws, st);
     const int n1 = inv_split(n), n2 = n - n1;
     cplx *A = E, *B = E + (size_t)n1 * ld, *D = B + n1, *Bt = E + n1;
     cplx *T = ws, *Tt = ws + (size_t)nb * n1 * n2, *ws_next = ws + 2 * (size_t)nb * n1 * n2;
@@ -1009,10 +1167,10 @@ static int ensure_factor_workspace(NdSolver* s) {
         const bool extra = lj < s->levels.size() && s->levels[lj].recv_from >= 0;
         const size_t nb = L.nb + (extra ? 1 : 0), nmax = L.nmax;
         maxF = std::max(maxF, nb * nmax * nmax);
-        maxW = std::max(maxW, (size_t)L.nb * inv_ws_need(L.kmax));
+        maxW = std::max(maxW, (size_t)L.nb * std::max(inv_ws_need(L.kmax), gj_ws_need(L.kmax)));
         if (L.send_to >= 0 || L.recv_from >= 0) maxX = std::max(maxX, (size_t)L.child_mmax * L.child_mmax);
     }
-    for (const NdDistFront* f : s->dist) maxW = std::max(maxW, inv_ws_need(f->kmax_step));
+    for (const NdDistFront* f : s->dist) maxW = std::max(maxW, std::max(inv_ws_need(f->kmax_step), gj_ws_need(f->kmax_step)));
     if (maxX > s->xchg_cap) {
         if (s->xchg) cudaFree(s->xchg);
         s->xchg = nullptr;
@@ -1045,6 +1203,10 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         g_lookahead_enabled = !(e && e[0] == '0');
         e = getenv("FDFD_LA_HELPER");
         g_lookahead_helper = !(e && e[0] == '0');
+        e = getenv("FDFD_BLOCK_GJ");
+        g_block_gj = !(e && e[0] == '0');
+        e = getenv("FDFD_BLOCK_GJ_MAXTILES");
+        if (e && atoi(e) > 0) g_block_gj_max_tiles = atoi(e);
     }
     FDFD_CHECK(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
     // the previous level's Schur blocks: batch base, first ring entry at (prev_k, prev_k), leading dimension
