@@ -21,9 +21,10 @@ cat gpurun_out/r02_launches_bench_step_summary.txt
 rm -f gpurun_out/r02_launches_all.csv
 # full captures: 3M persistent zgemm on a chain-step Schur update, Ez / Hz fused stencils, the 16-RHS substitution kernel
 PROFILE_ONLY=zgemm timeout 600 ncu --set full --import-source on --clock-control none -k regex:zgemm_dmma_persistent -s 2 -c 1 -f -o gpurun_out/r02_zgemm3m python tools/profile_kernels.py > gpurun_out/r02_ncu_zgemm.log 2>&1
-PROFILE_ONLY=stencil timeout 600 ncu --set full --clock-control none -k regex:stencil_fused -c 4 -f -o gpurun_out/r02_stencils python tools/profile_kernels.py > gpurun_out/r02_ncu_stencil.log 2>&1
+PROFILE_ONLY=stencil timeout 600 ncu --set full --clock-control none -k "regex:stencil_fused_ez|stencil_march_hz" -c 4 -f -o gpurun_out/r02_stencils python tools/profile_kernels.py > gpurun_out/r02_ncu_stencil.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:mrhs_dmma -s 40 -c 2 -f -o gpurun_out/r02_mrhs python tools/multirhs_probe.py 16 > gpurun_out/r02_ncu_mrhs.log 2>&1
-for f in r02_zgemm3m r02_stencils r02_mrhs; do ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null; done
+for f in r02_zgemm3m r02_stencils r02_mrhs; do ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null; python tools/ncu_summary.py gpurun_out/$f.raw.csv > gpurun_out/${f/r02_/r02_full_capture_}.txt; done
+rm -f gpurun_out/r02_zgemm3m.ncu-rep gpurun_out/r02_stencils.ncu-rep gpurun_out/r02_mrhs.ncu-rep
 python tools/ncu_traffic.py gpurun_out/r02_zgemm3m.raw.csv zgemm_dmma_persistent --flops 2.923e11 --bytes 1.76e9 --round 2 \
   --launch "chain-step Schur update S(9727x9727, lower) -= G(9727x512) F_RE^T: 6 flops per complex MAC (3M) x 9727 x 9791/2 x 512; bytes = S read+write + G + F_RE" --out gpurun_out/zgemm_capture.json
 python -c "
