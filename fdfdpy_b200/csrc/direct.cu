@@ -429,6 +429,42 @@ __global__ void small_front_kernel(SmallFrontArgs a, long long nb, int front_sme
     front_sync<WPF>(group);
     // ---- S = F_RR - G F_RE^T (lower), F_RR gathered from the children on the fly
     cplx* So = a.S + b * (long long)m * m;
+    if ((m & 1) == 0) {
+        // 2 x 2 register blocks over the lower triangle only: 4 shared-memory loads feed 4 complex MACs (the scalar loop
+        // below needs 8), and no thread is parked on the unused upper half
+        const int mb = m >> 1, nblk2 = mb * (mb + 1) / 2;
+        for (int e = tid; e < nblk2; e += nt) {
+            int bi = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= e) ++bi;
+            while (bi * (bi + 1) / 2 > e) --bi;
+            const int bj = e - bi * (bi + 1) / 2, i0 = 2 * bi, j0 = 2 * bj;
+            const bool diag = bi == bj;
+            cplx a00, a01 = zero, a10, a11;
+            if (leaf) {
+                a00 = Sm[i0 * m + j0]; a10 = Sm[(i0 + 1) * m + j0]; a11 = Sm[(i0 + 1) * m + j0 + 1];
+                if (!diag) a01 = Sm[i0 * m + j0 + 1];
+            } else {
+                a00 = small_front_gather(a, S1, S2, s_i1, s_i2, k + i0, k + j0);
+                a10 = small_front_gather(a, S1, S2, s_i1, s_i2, k + i0 + 1, k + j0);
+                a11 = small_front_gather(a, S1, S2, s_i1, s_i2, k + i0 + 1, k + j0 + 1);
+                if (!diag) a01 = small_front_gather(a, S1, S2, s_i1, s_i2, k + i0, k + j0 + 1);
+            }
+            const cplx *g0p = Gs + i0 * k, *g1p = g0p + k, *r0p = R + j0 * k, *r1p = r0p + k;
+#pragma unroll
+            for (int l = 0; l < (KT ? KT : k); ++l) {
+                const cplx g0 = g0p[l], g1 = g1p[l], r0 = r0p[l], r1 = r1p[l];
+                a00.x -= g0.x * r0.x - g0.y * r0.y; a00.y -= g0.x * r0.y + g0.y * r0.x;
+                a01.x -= g0.x * r1.x - g0.y * r1.y; a01.y -= g0.x * r1.y + g0.y * r1.x;
+                a10.x -= g1.x * r0.x - g1.y * r0.y; a10.y -= g1.x * r0.y + g1.y * r0.x;
+                a11.x -= g1.x * r1.x - g1.y * r1.y; a11.y -= g1.x * r1.y + g1.y * r1.x;
+            }
+            So[i0 * m + j0] = a00;
+            if (!diag) So[i0 * m + j0 + 1] = a01;
+            So[(i0 + 1) * m + j0] = a10;
+            So[(i0 + 1) * m + j0 + 1] = a11;
+        }
+        return;
+    }
     for (int e = tid; e < m * m; e += nt) {
         int i = e / m, j = e - i * m;
         if (j > i) continue;
