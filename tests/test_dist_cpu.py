@@ -245,7 +245,7 @@ def test_slab_rows_cover_the_grid():
 def test_schwarz_model_converges_and_matches_direct():
     """The restricted additive Schwarz preconditioner of the slab path, as a numpy model (tests/schwarz_model.py: the
     subdomains, overlap, artificial PML and stretch factors of csrc/operator.cu / csrc/krylov.cu): preconditioned
-    BiCGSTAB reaches the oracle's direct solution on a waveguide device in a few iterations per slab."""
+    GMRES reaches the oracle's direct solution on a waveguide device in a few iterations per slab."""
     from oracle import fdfd_oracle as orc
     from tests import schwarz_model as sm
     omega, dl, L0, npml = 2 * np.pi * 200e12, 0.02, 1e-6, [10, 10]
