@@ -1081,6 +1081,8 @@ gj_update_kernel(const cplx* __restrict__ src, cplx* __restrict__ dst, const cpl
 }
 static size_t gj_ws_need(int n) { return n <= 64 ? 0 : (size_t)n * n + 4096; }
 int g_block_gj = 1;                // A/B switch (FDFD_BLOCK_GJ=0): block Gauss-Jordan (default) or the recursive inversion
+thread_local int g_gj_on_lookahead = 0;   // set by the distributed fronts where the concurrent update is short (see distfront.cuh)
+int g_dist_gj_group = 8;           // FDFD_DIST_GJ_GROUP: distributed fronts of at least this many ranks invert look-ahead blocks by block GJ (0: never)
 int g_block_gj_max_tiles = 256;    // ... used while one step's grid (fronts x tiles) stays within a few waves of CTAs: it trades
                                    // flops (2x, in latency-bound 64^3 products, one CTA per SM) for a short launch chain, which
                                    // pays at the top of the tree and on distributed fronts, not on levels of many fronts
@@ -1126,7 +1128,7 @@ static int sym_invert_batch(NdSolver* s, cplx* E, long long sE, int ld, int n, l
     }
     // (not on the look-ahead stream: there the inversion shares the machine with a persistent GEMM that leaves it 4-16
     // SMs, and a step's 64-256 one-per-SM CTAs would crawl through them; measured: 5.8 -> 7.5 ms on the level it delays)
-    if (g_block_gj && ld == n && sE == (long long)n * n && st != s->la_stream &&
+    if (g_block_gj && ld == n && sE == (long long)n * n && (st != s->la_stream || g_gj_on_lookahead) &&
         nb * (long long)((n + 63) / 64) * ((n + 63) / 64) <= g_block_gj_max_tiles)
         return gj_invert_batch(s, E, n, nb, ws, st);
     const int n1 = inv_split(n), n2 = n - n1;
@@ -1241,6 +1243,8 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         g_lookahead_helper = !(e && e[0] == '0');
         e = getenv("FDFD_BLOCK_GJ");
         g_block_gj = !(e && e[0] == '0');
+        e = getenv("FDFD_DIST_GJ_GROUP");
+        if (e) g_dist_gj_group = atoi(e);
         e = getenv("FDFD_BLOCK_GJ_MAXTILES");
         if (e && atoi(e) > 0) g_block_gj_max_tiles = atoi(e);
     }

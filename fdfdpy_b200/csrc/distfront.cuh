@@ -467,7 +467,11 @@ static int dist_factor(NdSolver* s, NdDistFront* f, const NdDistFront* child, co
                 ++g_fdfd_launches;
                 const bool timing = g_phase_timing.on;
                 g_phase_timing.on = false;
+                // wide groups: a rank's share of the update is shorter than the inversion, which is then the critical
+                // path and has the machine almost to itself -> the short-chain block Gauss-Jordan form
+                g_gj_on_lookahead = g_dist_gj_group > 0 && f->gsize >= g_dist_gj_group;
                 int rc = sym_invert_batch(s, f->Einv[nxt], (long long)k1 * k1, k1, k1, 1, s->fws_W, s->la_stream);
+                g_gj_on_lookahead = 0;
                 g_phase_timing.on = timing;
                 if (rc) return -1;
                 FDFD_CHECK(cudaEventRecord(s->la_done, s->la_stream));

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--slab-parity", default="")
     ap.add_argument("--slab-size", type=int, default=0)
     ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--phases", action="store_true", help="one extra factorisation with per-level phase timing, every rank prints its top levels")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -89,6 +90,28 @@ def main():
         fb, tb = C.c_double(0), C.c_double(0)
         lib.fdfd_mem_info(C.byref(fb), C.byref(tb))
         out["hbm_used_gb_this_rank"] = (tb.value - fb.value) / 1e9
+        if args.phases:
+            names = "assemble pivot panel rowgemm copy update expand solve_fwd solve_bwd stencil ggemm schur small".split()
+            nl = len(d.levels)
+            dist.barrier()
+            lib.fdfd_phase_timing(1)
+            d.factor()
+            pl = np.zeros((nl, 13))
+            lib.fdfd_phase_timing_read_levels(_lib.ptr(pl), nl)
+            lib.fdfd_phase_timing(0)
+            keep = [i for i in (0, 1, 4, 5, 6, 10, 11, 12)]
+            first_top = next((i for i, lv in enumerate(d.levels) if lv.nb <= 1 and lv.kmax >= 256), nl)
+            lines = ["rank %d: local levels (nb > 1 or small) sum %.1f ms; phases " % (rank, pl[:first_top].sum()) +
+                     " ".join("%s=%.1f" % (names[i], pl[:, i].sum()) for i in keep)]
+            for li in range(first_top, nl):
+                lv = d.levels[li]
+                lines.append("   r%d L%02d nb=%d k=%d m=%d | " % (rank, li, lv.nb, lv.kmax, lv.mmax) +
+                             " ".join("%s=%.2f" % (names[i], pl[li, i]) for i in keep) + " | sum %.2f" % pl[li].sum())
+            allp = [None] * world
+            dist.all_gather_object(allp, "\n".join(lines))
+            if rank == 0:
+                for r in (0, world // 2, world - 1):
+                    print(allp[r], file=sys.stderr, flush=True)
     if args.slab_parity:
         from fdfdpy_b200.distributed import SlabOperator
         from oracle import fdfd_oracle as orc
