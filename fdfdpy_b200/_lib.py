@@ -65,6 +65,9 @@ SIGNATURES = {
     "fdfd_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_double]),
     "fdfd_host_free": (C.c_int, [_vp]),
     "fdfd_op_assemble_host_f64": (C.c_int, [_vp, _vp, C.c_int]),
+    "fdfd_factor_solve_fields_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, C.c_int,
+                                                C.c_int, C.c_double, _dp, _ip, _dp]),
+    "fdfd_op_eps_flags": (C.c_int, [_vp, _ip]),
     "fdfd_solve_fields_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, C.c_int,
                                          C.c_int, C.c_double, _dp, _ip]),
     "fdfd_op_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,

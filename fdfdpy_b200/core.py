@@ -119,6 +119,12 @@ class MaxwellOperator:
         check(self.lib.fdfd_op_get_planes_host(self.h, ptr(out)))
         return out
 
+    def eps_flags(self):
+        """Device-side flags of the assembled permittivity: bit 0 = complex entries, bit 1 = negative real parts."""
+        f = C.c_int(0)
+        check(self.lib.fdfd_op_eps_flags(self.h, C.byref(f)))
+        return f.value
+
     def sfactors(self):
         arrs = [np.empty(n, dtype=np.complex128) for n in (self.nx, self.nx, self.ny, self.ny)]
         check(self.lib.fdfd_op_get_sfactors_host(self.h, *[ptr(a) for a in arrs]))
@@ -274,8 +280,6 @@ class DirectSolver:
         """x = A^-1 (scale * src) and the two in-plane fields in ONE library call
         (simulation.py:113-178): src crosses PCIe once (as float64 when it is real), x never comes
         back up for the derived fields, and the three results land in page-locked arrays."""
-        if not self.factored:
-            self.factor()
         src = np.asarray(src)
         shape = (self.op.nx, self.op.ny)
         if src.size != shape[0] * shape[1]:
@@ -283,12 +287,23 @@ class DirectSolver:
         real = np.isrealobj(src)
         s = np.ascontiguousarray(src, dtype=np.float64 if real else np.complex128)
         x, f1, f2 = pinned_empty(shape), pinned_empty(shape), pinned_empty(shape)
-        rr, steps = C.c_double(0), C.c_int(0)
+        rr, steps, fms = C.c_double(0), C.c_int(0), C.c_double(0)
         av = -1 if averaging is None else int(bool(averaging))
         scale = complex(scale)
-        check(self.lib.fdfd_solve_fields_host(self.h, self.op.h, ptr(s), int(real), scale.real, scale.imag, ptr(x),
-                                              ptr(f1), ptr(f2), av, int(max_refine), float(tol), C.byref(rr),
-                                              C.byref(steps)))
+        # a missing factorisation is done INSIDE the call (queued first; src crosses PCIe while it runs)
+        self.last_factor_ms = None
+        factoring = not self.factored
+        try:
+            check(self.lib.fdfd_factor_solve_fields_host(self.h, self.op.h, ptr(s), int(real), scale.real, scale.imag,
+                                                         ptr(x), ptr(f1), ptr(f2), av, int(max_refine), float(tol),
+                                                         C.byref(rr), C.byref(steps), C.byref(fms)))
+        except Exception:
+            if factoring:
+                self.factored = self.has_factors = False
+            raise
+        if factoring:
+            self.factored = self.has_factors = True
+            self.last_factor_ms = fms.value
         self.last_relres, self.last_refine_steps = rr.value, steps.value
         return x, f1, f2
 

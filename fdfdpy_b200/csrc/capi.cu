@@ -687,6 +687,56 @@ int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int s
     return 0;
 }
 
+int fdfd_factor_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
+                                  double scale_im, double* x, double* f1, double* f2, int averaging, int max_refine,
+                                  double tol, double* relres, int* refine_steps, double* factor_ms) {
+    // solve_fields with the factorisation inside the call: the factorisation is QUEUED first, the source then crosses
+    // PCIe on a second stream while it runs (a pageable 134 MB array at 4096^2 keeps the host busy for ~12 ms), and the
+    // singular-pivot flag is read at the call's own final synchronisation.  An all-zero source still returns zero
+    // fields (linalg.py:129-130), the host does not have to scan for it.
+    if (op->halo) FDFD_FAIL("the direct solver takes the whole-grid operator, not a slab");
+    const size_t n = op->n();
+    cplx* io = nullptr;
+    if (op_io_buffer(op, &io)) return -1;
+    cplx *b = io, *xx = io + n, *g1 = io + 2 * n, *g2 = io + 3 * n;
+    if (!op->up_stream) {
+        FDFD_CHECK(cudaStreamCreateWithFlags(&op->up_stream, cudaStreamNonBlocking));
+        FDFD_CHECK(cudaEventCreateWithFlags(&op->ev_up, cudaEventDisableTiming));
+    }
+    // factors of another operator, or of this operator before its last assembly, are not this system's factors
+    const bool factor = !s->factored || s->fact_op != op || s->fact_version != op->version;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (factor) {
+        FDFD_CHECK(cudaEventCreate(&e0));
+        FDFD_CHECK(cudaEventCreate(&e1));
+        FDFD_CHECK(cudaEventRecord(e0, op->stream));
+        if (nd_factor(s, op, true)) return -1;
+        FDFD_CHECK(cudaEventRecord(e1, op->stream));
+    }
+    FDFD_CHECK(cudaMemcpyAsync(g1, src, (src_is_real ? sizeof(double) : sizeof(cplx)) * n, cudaMemcpyHostToDevice,
+                               op->up_stream));
+    FDFD_CHECK(cudaEventRecord(op->ev_up, op->up_stream));
+    FDFD_CHECK(cudaStreamWaitEvent(op->stream, op->ev_up, 0));
+    if (op_scale_expand(op, g1, src_is_real, make_double2(scale_re, scale_im), b, n)) return -1;
+    int rc = fdfd_direct_solve_dev(s, op, b, xx, 1, max_refine, tol, relres, refine_steps);
+    if (factor) {
+        // (the solve synchronised the stream more than once; a singular pivot shows up here first, whatever the solve said)
+        if (nd_factor_check(s, op)) rc = -1;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && factor_ms) *factor_ms = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } else if (factor_ms) *factor_ms = 0.0;
+    if (rc) return -1;
+    if (op_derive_fields(op, xx, g1, g2, averaging)) return -1;
+    FDFD_CHECK(cudaMemcpyAsync(x, xx, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(f1, g1, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaMemcpyAsync(f2, g2, sizeof(cplx) * n, cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    return 0;
+}
+int fdfd_op_eps_flags(fdfd_op* op, int* flags) { return op_eps_flags(op, flags); }
+
 int fdfd_comm_load(const char* libnccl_path) { return comm_load(libnccl_path); }
 int fdfd_comm_unique_id(void* id128) { return comm_unique_id(id128); }
 int fdfd_comm_create(fdfd_comm** out, const void* id128, int rank, int world) {

@@ -808,6 +808,7 @@ int nd_create(NdSolver** out, int nx, int ny, int tile) {
     if (tile < 1 || tile > 64) FDFD_FAIL("tile must be in 1..64");
     NdSolver* s = new NdSolver();
     s->nx = nx; s->ny = ny; s->tile = tile; s->factored = false;
+    s->fact_op = nullptr; s->fact_version = 0;
     s->factor_bytes = 0; s->factor_flops = 0;
     s->ws_a = s->ws_b = s->ws_ring_a = s->ws_ring_b = s->ws_ye = nullptr;
     s->ws_vec_cap = s->ws_ring_cap = s->ws_ye_cap = 0;
@@ -1230,7 +1231,7 @@ static int ensure_factor_workspace(NdSolver* s) {
     return 0;
 }
 
-int nd_factor(NdSolver* s, const FdfdOp* op) {
+int nd_factor(NdSolver* s, const FdfdOp* op, bool defer_check) {
     if (s->levels.empty()) FDFD_FAIL("no levels in the plan");
     if (op->nx != s->nx || op->ny != s->ny) FDFD_FAIL("operator / plan shape mismatch");
     cudaStream_t st = op->stream;
@@ -1477,12 +1478,23 @@ int nd_factor(NdSolver* s, const FdfdOp* op) {
         prev_stride = fstride;
     }
     g_phase_timing.level = -1;
-    int info = 0;
     if (s->comm && s->comm->world > 1 && comm_allreduce_max_i32(s->comm, s->d_info, 1, st)) return -1;
-    FDFD_CHECK(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FDFD_CHECK(cudaStreamSynchronize(st));
-    if (info) FDFD_FAIL("direct solver: a pivot block is numerically singular (no inter-block pivoting)");
     s->factored = true;
+    s->fact_op = op;
+    s->fact_version = op->version;
+    if (defer_check) return 0;          // the caller keeps queueing work and calls nd_factor_check at its own sync point
+    return nd_factor_check(s, op);
+}
+
+// waits for the factorisation and reads the singular-pivot flag
+int nd_factor_check(NdSolver* s, const FdfdOp* op) {
+    int info = 0;
+    FDFD_CHECK(cudaMemcpyAsync(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, op->stream));
+    FDFD_CHECK(cudaStreamSynchronize(op->stream));
+    if (info) {
+        s->factored = false;
+        FDFD_FAIL("direct solver: a pivot block is numerically singular (no inter-block pivoting)");
+    }
     return 0;
 }
 

@@ -69,6 +69,8 @@ struct NdSolver {
     int tile;                         // (kept for ABI compatibility; the block inversion uses 64-wide base tiles)
     std::vector<NdLevel> levels;
     bool factored;
+    const void* fact_op;              // operator and assembly version the factors belong to (fdfd_factor_solve_fields_host)
+    unsigned long long fact_version;
     size_t factor_bytes;
     double factor_flops;              // real flops of the last factorisation (8 per complex MAC)
     int* d_info;                      // device flag: non-zero if a pivot tile was singular
@@ -100,6 +102,7 @@ int nd_create(NdSolver** out, int nx, int ny, int tile);
 int nd_add_level(NdSolver* s, const NdLevelDesc* d);
 int nd_add_dist_front(NdSolver* s, const NdDistFrontDesc* d);   // after fdfd_direct_set_comm and all levels
 void nd_destroy(NdSolver* s);
-int nd_factor(NdSolver* s, const FdfdOp* op);
+int nd_factor(NdSolver* s, const FdfdOp* op, bool defer_check = false);
+int nd_factor_check(NdSolver* s, const FdfdOp* op);     // after a deferred factorisation: sync + singular-pivot flag
 // d_b, d_x: [nrhs][nx*ny] device vectors
 int nd_solve(NdSolver* s, const FdfdOp* op, const cplx* d_b, cplx* d_x, int nrhs);

@@ -537,9 +537,12 @@ stencil_march_hz_kernel(const V* __restrict__ eps_r, const V* __restrict__ eps_n
 // flag[0] = 1 if some entry of eps (n values) has a non-zero imaginary part
 __global__ void eps_imag_kernel(const cplx* __restrict__ eps, size_t n, int* __restrict__ flag) {
     int any = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        any |= eps[i].y != 0.0;
-    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const cplx e = eps[i];
+        any |= (e.y != 0.0 ? 1 : 0) | (e.x < 0.0 ? 2 : 0);
+    }
+    any = __reduce_or_sync(0xffffffffu, any);
+    if (any && (threadIdx.x & 31) == 0) atomicOr(flag, any);
 }
 
 // complex64 variant with TWO adjacent y columns per thread: every access is a 16-byte float4 (the same bytes
@@ -810,6 +813,7 @@ void op_destroy(FdfdOp* op) {
     if (op->eps32) cudaFree(op->eps32);
     if (op->comm_stream) { cudaStreamDestroy(op->comm_stream); cudaEventDestroy(op->ev_in); cudaEventDestroy(op->ev_halo); }
     if (op->ev0) { cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1); }
+    if (op->up_stream) { cudaStreamDestroy(op->up_stream); cudaEventDestroy(op->ev_up); }
     cudaStreamDestroy(op->stream);
     delete op;
 }
@@ -845,16 +849,19 @@ int op_assemble_dev(FdfdOp* op, const cplx* d_eps_r, const cplx* d_eps_nl, int a
     op->averaging = averaging;
     op->has_nl = d_eps_nl != nullptr;
     op->eps32_valid = 0;
+    ++op->version;
     if (d_eps_r != op->eps_r)
         FDFD_CHECK(cudaMemcpyAsync(op->eps_r, d_eps_r, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
     if (d_eps_nl && d_eps_nl != op->eps_nl)
         FDFD_CHECK(cudaMemcpyAsync(op->eps_nl, d_eps_nl, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, op->stream));
     AsmParams p = make_params(op);
-    if (op->pol != 0) {                  // lossless permittivity gets the real-weight Hz stencil
-        FDFD_CHECK(cudaMemsetAsync(op->d_eps_flag, 0, sizeof(int), op->stream));
-        { eps_imag_kernel<<<592, 256, 0, op->stream>>>(op->eps_r, n, op->d_eps_flag); ++g_fdfd_launches; }
-        op->eps_real = -1;
-    }
+    // one pass over eps_r sets two flags on the device: bit 0 = some entry has an imaginary part (lossless permittivity
+    // gets the real-weight Hz stencil), bit 1 = some real part is negative (Simulation's argument check for large
+    // arrays reads it here instead of scanning 134 MB on the host: 17 ms at 4096^2)
+    FDFD_CHECK(cudaMemsetAsync(op->d_eps_flag, 0, sizeof(int), op->stream));
+    { eps_imag_kernel<<<592, 256, 0, op->stream>>>(op->eps_r, n, op->d_eps_flag); ++g_fdfd_launches; }
+    op->eps_real = -1;
+    op->eps_flags = -1;
     { assemble_planes_kernel<<<ceil_div(n, 256), 256, 0, op->stream>>>(
         op->planes, op->eps_r, op->has_nl ? op->eps_nl : nullptr, op->isxf, op->isxb, op->isyf, op->isyb, p); ++g_fdfd_launches; }
     FDFD_CHECK(cudaGetLastError());
@@ -869,9 +876,16 @@ static int op_eps_is_real(const FdfdOp* cop, int* out) {
         int h = 1;
         FDFD_CHECK(cudaMemcpyAsync(&h, op->d_eps_flag, sizeof(int), cudaMemcpyDeviceToHost, op->stream));
         FDFD_CHECK(cudaStreamSynchronize(op->stream));
-        op->eps_real = h ? 0 : 1;
+        op->eps_flags = h;
+        op->eps_real = (h & 1) ? 0 : 1;
     }
     *out = op->eps_real;
+    return 0;
+}
+int op_eps_flags(const FdfdOp* op, int* flags) {
+    int real_eps = 0;
+    if (op_eps_is_real(op, &real_eps)) return -1;
+    *flags = op->eps_flags;
     return 0;
 }
 

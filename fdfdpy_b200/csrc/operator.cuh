@@ -29,6 +29,10 @@ struct FdfdOp {
     cplx *io_buf;
     int* d_eps_flag;    // device flag: some eps_r entry has an imaginary part (Hz fused stencil: complex face weights)
     int eps_real;       // host copy: 1 all real, 0 not, -1 not read back yet
+    unsigned long long version;   // bumped by every assembly: a factorisation remembers the version it belongs to
+    int eps_flags;      // host copy of the device flags (bit 0: imaginary part present, bit 1: negative real part), -1 not read yet
+    cudaStream_t up_stream;   // host -> device copies that run next to work already queued on `stream` (lazily created)
+    cudaEvent_t ev_up;
     cplx32* eps32;      // complex64 copy of eps_r (| eps_nl) for the complex64 stencil, built on first use
     int eps32_valid;
     // slab of a grid split over several GPUs (halo = 1): nx counts the slab's rows PLUS one halo row on each
@@ -53,6 +57,8 @@ int op_create_slab(FdfdOp** out, FdfdComm* comm, int gnx, int ny, int x0, int nx
 int op_create_schwarz_sub(FdfdOp** out, const FdfdOp* slab, int overlap, int npml_sub);
 void op_destroy(FdfdOp* op);
 void schwarz_destroy(struct SchwarzPre* s);     // krylov.cu
+// flags of the permittivity of the last assembly: bit 0 = an imaginary part is present, bit 1 = a real part is negative
+int op_eps_flags(const FdfdOp* op, int* flags);
 // fills the two halo rows of an extended-layout vector from the neighbouring slabs
 int op_halo_exchange(const FdfdOp* op, void* d_x_ext, size_t elem_bytes, cudaStream_t st);
 // eps_r / eps_nl are device pointers (eps_nl may be null); builds the five planes

@@ -132,6 +132,18 @@ int fdfd_direct_solve_dev(fdfd_direct* s, fdfd_op* op, const void* d_b, void* d_
 int fdfd_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
                            double scale_im, double* x_c128, double* f1_c128, double* f2_c128, int averaging,
                            int max_refine, double tol, double* relres, int* refine_steps);
+/* The same with the factorisation inside the call when the handle holds none for the operator's current planes (the
+ * whole of Simulation.solve_fields after an eps_r change, simulation.py:80-89 + 113-178): the factorisation is
+ * queued first, src crosses PCIe on a second stream while it runs, the singular-pivot flag is read at the call's final
+ * synchronisation.  An all-zero src returns zero fields (linalg.py:129-130).  factor_ms (may be NULL): device time of
+ * the factorisation, 0 when the cached one was used. */
+int fdfd_factor_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src, int src_is_real, double scale_re,
+                                  double scale_im, double* x_c128, double* f1_c128, double* f2_c128, int averaging,
+                                  int max_refine, double tol, double* relres, int* refine_steps, double* factor_ms);
+/* flags of the permittivity of the last assembly, evaluated on the device: bit 0 = some entry has an imaginary part,
+ * bit 1 = some real part is negative (the argument check of simulation.py:256-265 for arrays too large to scan on the
+ * host inside a timed solve) */
+int fdfd_op_eps_flags(fdfd_op* op, int* flags);
 
 /* ---- one grid split over several GPUs (no reference counterpart: the reference is single-process).
  * One process per GPU.  Rank 0 makes a 128-byte id, the host program hands it to the other ranks

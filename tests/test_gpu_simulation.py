@@ -52,9 +52,15 @@ def test_zero_source_and_eps_reassignment(Simulation, golden):
     ez_vac = sim.solve_fields()[2]
     sim.eps_r = eps                      # re-assembles and refactorises
     assert sim.fields["Ez"] is None
+    sim.timings.pop('factor', None)
     ez = sim.solve_fields()[2]
+    # a NEW factorisation was done (not the vacuum factors rescued by refinement / BiCGSTAB): no refinement cascade
+    assert sim.timings.get('factor', 0) > 0 and sim.last_solve["refine_steps"] <= 2, (sim.timings, sim.last_solve)
     assert relerr(ez, g["Ez_fz"]) < 1e-8
     assert relerr(ez_vac, g["Ez_fz"]) > 1e-2
+    sim.timings.pop('factor', None)
+    sim.solve_fields()                   # unchanged operator: the cached factors are reused
+    assert 'factor' not in sim.timings
     # exported matrix equals the oracle's
     A = sim.A.to_scipy()
     ref = orc.construct_A(omega, eps, dl, [int(npx), int(npy)], "Ez", L0)
@@ -268,3 +274,32 @@ def test_input_layouts_and_lossy_media(Simulation):
             for mine, theirs in zip(f, ref):
                 assert relerr(mine, theirs) < 1e-8, (pol, name)
             assert sim.last_solve["relres"] < 1e-10
+
+
+def test_large_grid_checks_run_on_the_device():
+    """Above Simulation._HOST_SCAN_MAX cells the negative-permittivity check and the all-zero-source short cut are
+    evaluated by the library (a flag kernel at assembly, the norm of b in the solve) instead of numpy scans on the
+    host; behaviour is the reference's (simulation.py:256-265, linalg.py:129-130): same exception, zero fields."""
+    from fdfdpy_b200 import Simulation
+    OMEGA = 2 * np.pi * 200e12
+    n = 1100
+    assert n * n > Simulation._HOST_SCAN_MAX
+    eps = np.ones((n, n))
+    eps[300:800, 500:600] = 6.0
+    sim = Simulation(OMEGA, eps, 0.04, [12, 12], 'Ez', 1e-6)
+    bad = eps.copy()
+    bad[1000, 3] = -0.5
+    with pytest.raises(ValueError):
+        sim.eps_r = bad
+    assert np.array_equal(sim.eps_r, eps)                 # the previous permittivity is kept
+    with pytest.raises(ValueError):
+        Simulation(OMEGA, bad, 0.04, [12, 12], 'Ez', 1e-6)
+    # zero source: zero fields, as the reference returns them
+    hx, hy, ez = sim.solve_fields()
+    assert not ez.any() and not hx.any() and not hy.any()
+    # and a real solve after the failed assignment: one call factorises and solves (timings carry the device time)
+    sim.src[n // 2, n // 2] = 1.0
+    hx, hy, ez = sim.solve_fields()
+    assert sim.last_solve["relres"] < 1e-10 and sim.timings["factor"] > 0
+    ref = orc.solve_fields(OMEGA, eps, 0.04, [12, 12], 'Ez', 1e-6, sim.src)
+    assert relerr(ez, ref[2]) < 1e-8
