@@ -15,19 +15,18 @@ POL = {"Ez": 0, "Hz": 1}
 _plan_cache = {}
 
 
-def get_plan(nx, ny):
-    """Elimination plan of an nx x ny grid (cached).  FDFD_SPLIT_MIN / FDFD_SPLIT_PARTS override the separator
-    splitting of ndplan.build_plan for A/B measurements."""
+def get_plan(nx, ny, sharded=False):
+    """Elimination plan of an nx x ny grid (cached).  FDFD_SPLIT_MIN / FDFD_SPLIT_PARTS / FDFD_SPLIT_MAX_STEPS override
+    the separator splitting of ndplan.build_plan for A/B measurements.  ``sharded``: the plan of a tree split over
+    several GPUs eliminates the top separators in up to 16 pieces instead of 8 (see ndplan.SPLIT_MAX_STEPS)."""
     import os
     sm, sp = os.environ.get("FDFD_SPLIT_MIN"), os.environ.get("FDFD_SPLIT_PARTS")
     ms = os.environ.get("FDFD_SPLIT_MAX_STEPS")
-    key = (int(nx), int(ny), sm, sp, ms)
+    max_steps = int(ms) if ms else (16 if sharded else None)
+    key = (int(nx), int(ny), sm, sp, max_steps)
     if key not in _plan_cache:
-        if ms:
-            from . import ndplan
-            ndplan.SPLIT_MAX_STEPS = int(ms)
         _plan_cache[key] = build_plan(int(nx), int(ny), split_min=int(sm) if sm else None,
-                                      split_parts=int(sp) if sp else None)
+                                      split_parts=int(sp) if sp else None, split_max_steps=max_steps)
     return _plan_cache[key]
 
 
@@ -204,7 +203,7 @@ class DirectSolver:
         self.lib = op.lib
         self.h = C.c_void_p()
         check(self.lib.fdfd_direct_create(C.byref(self.h), op.nx, op.ny, int(tile)))
-        self.levels = get_plan(op.nx, op.ny)
+        self.levels = get_plan(op.nx, op.ny, sharded=comm is not None and comm.world > 1)
         self.comm = comm
         if comm is not None and comm.world > 1:
             import os

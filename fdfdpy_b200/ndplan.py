@@ -24,7 +24,8 @@ import numpy as np
 WMIN = 3          # smallest leaf interval (cells); leaves are WMIN..2*WMIN-1 cells wide
 SPLIT_MIN = 1000  # separators with at least this many nodes are eliminated in several steps
 SPLIT_PARTS = -512   # > 0: that many steps; < 0: pieces of about -SPLIT_PARTS nodes (at most SPLIT_MAX_STEPS steps)
-SPLIT_MAX_STEPS = 8
+SPLIT_MAX_STEPS = 8       # single GPU; sharded trees use 16 (core.get_plan): on a distributed front the pivot-block inversions
+                          # are the critical path, and sixteen 512-blocks invert faster than eight 1024-blocks (116 -> 105 ms on 8 GPUs)
 
 
 def _parts(k, p):
@@ -85,7 +86,7 @@ class Level:
     pass
 
 
-def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
+def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None, split_max_steps=None):
     """Return the list of levels, leaves first, root last.
 
     A merge whose separator has >= split_min nodes is emitted as a CHAIN of levels that eliminate the
@@ -96,6 +97,7 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
     while the solve phase still streams plain matrix-vector products."""
     split_min = SPLIT_MIN if split_min is None else split_min
     split_parts = SPLIT_PARTS if split_parts is None else split_parts
+    split_max_steps = SPLIT_MAX_STEPS if split_max_steps is None else split_max_steps
     ax, ay = _depth_for(nx, wmin), _depth_for(ny, wmin)
     levels = []
 
@@ -213,7 +215,7 @@ def build_plan(nx, ny, wmin=WMIN, split_min=None, split_parts=None):
             fronts.append((elim, pring, p1, p2))
             new_rings[(pw, ph)] = pring
         kfull = max(len(f[0]) for f in fronts)
-        want = split_parts if split_parts > 0 else max(1, min(SPLIT_MAX_STEPS, int(round(kfull / float(-split_parts)))))
+        want = split_parts if split_parts > 0 else max(1, min(split_max_steps, int(round(kfull / float(-split_parts)))))
         nparts = want if (want > 1 and kfull >= split_min and min(len(f[0]) for f in fronts) >= want) else 1
         # pieces are identical for every shape class except the last one, which absorbs the (<= 2 node) size
         # differences: the intermediate chain levels then have no padded pivots and are factorised in place
