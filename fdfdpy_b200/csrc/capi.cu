@@ -705,7 +705,11 @@ int fdfd_factor_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src
     }
     // factors of another operator, or of this operator before its last assembly, are not this system's factors
     const bool factor = !s->factored || s->fact_op != op || s->fact_version != op->version;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct EventPair {                                   // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    cudaEvent_t &e0 = ev.a, &e1 = ev.b;
     if (factor) {
         FDFD_CHECK(cudaEventCreate(&e0));
         FDFD_CHECK(cudaEventCreate(&e1));
@@ -724,8 +728,6 @@ int fdfd_factor_solve_fields_host(fdfd_direct* s, fdfd_op* op, const double* src
         if (nd_factor_check(s, op)) rc = -1;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && factor_ms) *factor_ms = ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     } else if (factor_ms) *factor_ms = 0.0;
     if (rc) return -1;
     if (op_derive_fields(op, xx, g1, g2, averaging)) return -1;
