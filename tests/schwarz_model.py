@@ -49,9 +49,7 @@ def build(omega, eps, dl, npml, L0, slabs, overlap, npml_s):
     ext = overlap + npml_s
     subs = []
     for r in range(slabs):
-        base, extra = divmod(nx, slabs)
-        x0 = r * base + min(r, extra)
-        x1 = x0 + base + (1 if r < extra else 0)
+        x0, x1 = slab_rows(nx, slabs, r)
         rows = np.arange(x0 - ext, x1 + ext) % nx
         isxf, isxb = subdomain_sfactors(gis, rows, npml_s, dl, omega, L0)
         Al = orc.planes_to_csr(ez_planes(omega, eps[rows], dl, L0, isxf, isxb, gis[2], gis[3]))
@@ -67,6 +65,44 @@ def build(omega, eps, dl, npml, L0, slabs, overlap, npml_s):
             out[x0:x1] = lu.solve(rl.ravel()).reshape(nl, ny)[ext:ext + (x1 - x0)]     # restricted: owned rows only
         return out.ravel()
     return A, M
+
+
+def slab_rows(nx, slabs, r):
+    base, extra = divmod(nx, slabs)
+    x0 = r * base + min(r, extra)
+    return x0, x0 + base + (1 if r < extra else 0)
+
+
+def build_rank(omega, eps, dl, npml, L0, slabs, rank, overlap, npml_s):
+    """What ONE rank holds (SlabOperator.setup_schwarz): its rows, the subdomain's rows and the subdomain's factors."""
+    nx, ny = eps.shape
+    gis = orc.pml_inverse_factors(omega, L0, (nx, ny), npml, dl)
+    ext = overlap + npml_s
+    x0, x1 = slab_rows(nx, slabs, rank)
+    rows = np.arange(x0 - ext, x1 + ext) % nx
+    isxf, isxb = subdomain_sfactors(gis, rows, npml_s, dl, omega, L0)
+    Al = orc.planes_to_csr(ez_planes(omega, eps[rows], dl, L0, isxf, isxb, gis[2], gis[3]))
+    return dict(x0=x0, x1=x1, rows=rows, lu=spl.splu(sp.csc_matrix(Al)), ny=ny)
+
+
+def rank_apply(sub, r_owned, comm, rank, world, overlap, npml_s):
+    """z = M^-1 r on this rank's rows with the message pattern of csrc/krylov.cu schwarz_apply: the first / last
+    ``overlap`` owned rows go to the lower / upper neighbour (periodic in the rank index), theirs fill the overlap
+    rows of the zero-extended subdomain right-hand side, only the owned rows of the local solution are kept.
+    ``comm`` has sendrecv(send_array, dst, recv_shape, src) (tests/test_dist_cpu.GlooComm)."""
+    ny, nown, ext = sub["ny"], sub["x1"] - sub["x0"], overlap + npml_s
+    rl = np.zeros((len(sub["rows"]), ny), complex)
+    rl[ext:ext + nown] = r_owned
+    if overlap > 0:
+        lower, upper = (rank - 1) % world, (rank + 1) % world
+        if world == 1:
+            hi, lo = r_owned[:overlap], r_owned[-overlap:]
+        else:
+            hi = comm.sendrecv(r_owned[:overlap], lower, (overlap, ny), upper)
+            lo = comm.sendrecv(r_owned[-overlap:], upper, (overlap, ny), lower)
+        rl[npml_s:ext] = lo
+        rl[ext + nown:ext + nown + overlap] = hi
+    return sub["lu"].solve(rl.ravel()).reshape(-1, ny)[ext:ext + nown]
 
 
 def solve(omega, eps, dl, npml, L0, b, slabs, overlap=4, npml_s=12, tol=1e-10, maxiter=2000, method="gmres", restart=80):

@@ -259,3 +259,46 @@ def test_schwarz_model_converges_and_matches_direct():
     ref = orc.sparse_solve(A0, b).reshape(nx, ny)
     assert rr < 1e-10 and its <= 30, (its, rr)
     assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-8
+
+
+def _worker_schwarz(rank, world, port, shape, overlap, npml_s, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        from tests import schwarz_model as sm
+        omega, dl, L0, npml = 2 * np.pi * 200e12, 0.03, 1e-6, [6, 5]
+        nx, ny = shape
+        rng = np.random.default_rng(3)
+        eps = 1 + 8 * (rng.random((nx, ny)) > 0.7)
+        r = rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny))
+        _, M = sm.build(omega, eps, dl, npml, L0, world, overlap, npml_s)        # the whole preconditioner, one process
+        ref = M(r.ravel()).reshape(nx, ny)
+        sub = sm.build_rank(omega, eps, dl, npml, L0, world, rank, overlap, npml_s)
+        z = sm.rank_apply(sub, r[sub["x0"]:sub["x1"]], GlooComm(dist, torch), rank, world, overlap, npml_s)
+        q.put((rank, float(np.linalg.norm(z - ref[sub["x0"]:sub["x1"]]) / np.linalg.norm(ref[sub["x0"]:sub["x1"]]))))
+    except Exception as e:
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,overlap,npml_s", [(2, (40, 24), 3, 5), (3, (47, 20), 2, 4), (4, (64, 18), 4, 6)])
+def test_schwarz_apply_rank_local_gloo(world, shape, overlap, npml_s):
+    """One application of the Schwarz preconditioner computed rank by rank (each rank: its rows, its subdomain
+    factors, the overlap rows exchanged with both neighbours over gloo in the order csrc/krylov.cu schwarz_apply
+    uses over NCCL, world 2 included where both neighbours are the same peer) equals the single-process model."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_schwarz, args=(r, world, port, shape, overlap, npml_s, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err in res:
+        assert isinstance(err, float), (rank, err)
+        assert err < 1e-12, (rank, err)
