@@ -33,6 +33,32 @@ def gj_inverse(E, tile=32):
     return F
 
 
+def gj_inverse_pingpong(E, tile=64):
+    """The block Gauss-Jordan inversion as csrc/direct.cu gj_invert_batch runs it: per pivot tile p one tile inverse
+    P = M_pp^-1 and one OUT-OF-PLACE update of every tile (src -> dst, buffers swapped after each step):
+        dst_pp = P     dst_pj = P src_pj     dst_ip = -src_ip P     dst_ij = src_ij - src_ip (P src_pj)
+    The last tile may be ragged."""
+    src = np.array(E, dtype=complex)
+    nb, n, _ = src.shape
+    nt = (n + tile - 1) // tile
+    sl = [slice(t * tile, min((t + 1) * tile, n)) for t in range(nt)]
+    for p in range(nt):
+        dst = np.empty_like(src)
+        P = np.linalg.inv(src[:, sl[p], sl[p]])
+        for i in range(nt):
+            for j in range(nt):
+                if i == p and j == p:
+                    dst[:, sl[p], sl[p]] = P
+                elif i == p:
+                    dst[:, sl[p], sl[j]] = P @ src[:, sl[p], sl[j]]
+                elif j == p:
+                    dst[:, sl[i], sl[p]] = -src[:, sl[i], sl[p]] @ P
+                else:
+                    dst[:, sl[i], sl[j]] = src[:, sl[i], sl[j]] - src[:, sl[i], sl[p]] @ (P @ src[:, sl[p], sl[j]])
+        src = dst
+    return src
+
+
 def _lower_to_full(L):
     """Symmetric matrix from its lower triangle (the upper one of the input is ignored)."""
     T = np.tril(L)
